@@ -1,0 +1,85 @@
+// Shared device helpers for the alignq_b200 kernels (sm_100a only).
+//
+// Numerics contract: the reference's forward is a chain of
+// separately rounded fp32 ATen ops.  Every step of that chain is written here with the
+// non-contracting intrinsics (__fmul_rn/__fadd_rn/__fsub_rn), so ptxas can never fuse two
+// of them into an FMA, and with the same libdevice erff/expf ATen's CUDA kernels call.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define ALIGNQ_NUM_SMS 148
+
+enum { ALIGNQ_OK = 0, ALIGNQ_EINVAL = -1, ALIGNQ_EALIGN = -2, ALIGNQ_ERANGE = -3, ALIGNQ_ENOSPACE = -4 };
+
+#define ALIGNQ_LAUNCH_CHECK()                         \
+  do {                                                \
+    cudaError_t e__ = cudaGetLastError();             \
+    if (e__ != cudaSuccess) return (int)e__;          \
+  } while (0)
+
+namespace alignq {
+
+constexpr float kInvSqrt2 = 0.70710677f;        // fp32(1/fp32(sqrt(2))): ATen multiplies by the reciprocal of a CPU scalar divisor
+constexpr float kTwoOverSqrtPi = 1.1283791f;    // erf'(v) = 2/sqrt(pi) exp(-v^2)
+constexpr float kInvSqrt2Pi = 0.3989423f;
+constexpr float kLogSqrt2Pi = 0.9189385f;       // math.log(math.sqrt(2*math.pi))
+
+// ---- the reference's fp32 op chain ------------------------------------------------------
+// Normal(loc, scale).cdf(x) = 0.5 * (1 + erf((x - loc) * (1/scale) / sqrt(2)))
+__device__ __forceinline__ float normal_cdf_std(float x) {             // loc = 0, scale = 1 (QA:97)
+  float v = __fmul_rn(x, kInvSqrt2);                                   // (x-0)*1 is exact
+  return __fmul_rn(0.5f, __fadd_rn(1.0f, erff(v)));
+}
+__device__ __forceinline__ float normal_cdf(float x, float loc, float rscale) {
+  float u = __fmul_rn(__fsub_rn(x, loc), rscale);
+  float v = __fmul_rn(u, kInvSqrt2);
+  return __fmul_rn(0.5f, __fadd_rn(1.0f, erff(v)));
+}
+// variant A: c ; variant B/C: (c*2-1) [* act_range for activations]
+__device__ __forceinline__ float sym_map(float c) { return __fsub_rn(__fmul_rn(c, 2.0f), 1.0f); }
+
+// round(p*n)/n with the divide done as ATen does it on CUDA (multiply by fp32 1/n)
+__device__ __forceinline__ float quant_code(float p, float n) { return rintf(__fmul_rn(p, n)); }
+
+// d/dx Phi((x-loc)/scale) without the 1/scale factor, mirroring erf's backward argument
+__device__ __forceinline__ float gauss_kernel_from_v(float v) { return expf(-__fmul_rn(v, v)); }
+
+// ---- vector memory helpers --------------------------------------------------------------
+__device__ __forceinline__ float4 ld_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream(float4* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// ---- reductions -------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum of two values; result valid in every thread.  scratch: 2*32 T's of smem.
+template <typename T>
+__device__ __forceinline__ void block_sum2(T& a, T& b, T* scratch) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  a = warp_sum(a);
+  b = warp_sum(b);
+  __syncthreads();                       // scratch may still be read from a previous call
+  if (lane == 0) { scratch[wid] = a; scratch[32 + wid] = b; }
+  __syncthreads();
+  a = (lane < nw) ? scratch[lane] : T(0);
+  b = (lane < nw) ? scratch[32 + lane] : T(0);
+  a = warp_sum(a);
+  b = warp_sum(b);
+}
+
+__host__ __device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace alignq

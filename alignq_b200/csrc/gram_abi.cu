@@ -1,0 +1,73 @@
+// C-ABI entry points of the correlation / fused activation+ADMM path (dispatch over gram_mode).
+#include "common.cuh"
+#include "gram_common.cuh"
+#include "../../include/alignq_b200.h"
+
+using namespace alignq;
+
+extern "C" size_t alignq_gram_ws_bytes(int B, int64_t F) {
+  if (B < 1 || F < 1) return 0;
+  const int64_t ntiles = (F + 31) / 32;
+  int64_t slabs = ntiles < 2 * ALIGNQ_NUM_SMS ? ntiles : 2 * ALIGNQ_NUM_SMS;
+  size_t bytes = gram_wsym_floats(B) * sizeof(float) + 2 * (size_t)slabs * B * B * sizeof(float);
+  const size_t floor_bytes = gram_wsym_floats(B) * sizeof(float) + 2 * (size_t)B * B * sizeof(float);
+  if (bytes > kGramWsCapBytes) bytes = kGramWsCapBytes > floor_bytes ? kGramWsCapBytes : floor_bytes;
+  return bytes;
+}
+
+static inline float* ws_partials(void* ws, int B) { return reinterpret_cast<float*>(ws) + gram_wsym_floats(B); }
+
+extern "C" int alignq_corr_fwd(const float* x, const float* y, int B, int64_t F, float eps, float* G, void* ws,
+                               size_t ws_bytes, int gram_mode, alignq_stream_t stream) {
+  if (B < 1 || F < 1 || !x || !y || !G || !ws) return ALIGNQ_EINVAL;
+  if (B > 1024) return ALIGNQ_ERANGE;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (gram_mode == ALIGNQ_GRAM_FP32 || x != y) {
+    ActQ q{0.f, 0.f, 0.f, 0};
+    int nslabs = 0;
+    int rc = gram_ffma_forward(x, y, B, F, eps, 0, q, nullptr, ws_partials(ws, B), &nslabs, ws_bytes, s);
+    if (rc) return rc;
+    return launch_gram_reduce(ws_partials(ws, B), nslabs, B, F, 0, G, nullptr, s);
+  }
+  return gram_tc_corr(x, B, F, eps, G, ws, ws_bytes, gram_mode, s);
+}
+
+extern "C" int alignq_act_admm_fwd(const float* x, int B, int64_t F, int a_bit, float act_range, float eps,
+                                   const float* Z, const float* U, int dim, float mu, float rho, float* y, float* D,
+                                   float* loss, float* dLdD, void* ws, size_t ws_bytes, int gram_mode,
+                                   alignq_stream_t stream) {
+  if (B < 1 || F < 1 || a_bit < 1 || a_bit > 32 || dim < B) return ALIGNQ_EINVAL;
+  if (!x || !Z || !U || !y || !D || !loss || !ws) return ALIGNQ_EINVAL;
+  if (B > 1024) return ALIGNQ_ERANGE;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  ActQ q;
+  q.ar = act_range;
+  q.a_bit = a_bit;
+  q.n = (a_bit == 32) ? 1.0f : (float)((1ull << a_bit) - 1);
+  q.inv_n = 1.0f / q.n;
+  int rc;
+  if (gram_mode == ALIGNQ_GRAM_FP32) {
+    int nslabs = 0;
+    rc = gram_ffma_forward(x, x, B, F, eps, 1, q, y, ws_partials(ws, B), &nslabs, ws_bytes, s);
+    if (rc) return rc;
+    rc = launch_gram_reduce(ws_partials(ws, B), nslabs, B, F, 1, nullptr, D, s);
+  } else {
+    rc = gram_tc_fused_fwd(x, B, F, q, eps, y, D, ws, ws_bytes, gram_mode, s);
+  }
+  if (rc) return rc;
+  return alignq_admm_loss(D, B, Z, U, dim, 1, mu, rho, nullptr, 0, loss, dLdD, nullptr, nullptr, stream);
+}
+
+extern "C" int alignq_act_admm_bwd(const float* x, const float* gy, const float* dLdD, const float* gloss, int B,
+                                   int64_t F, int a_bit, float act_range, float eps, float* gx, void* ws,
+                                   size_t ws_bytes, int gram_mode, alignq_stream_t stream) {
+  if (B < 2 || F < 1 || a_bit < 1 || a_bit > 32) return ALIGNQ_EINVAL;
+  if (!x || !dLdD || !gx || !ws) return ALIGNQ_EINVAL;
+  if (ws_bytes < gram_wsym_floats(B) * sizeof(float)) return ALIGNQ_ENOSPACE;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  (void)gram_mode;      // the backward products run on the fp32 path in every mode
+  float* Wsym = reinterpret_cast<float*>(ws);
+  int rc = launch_wsym(dLdD, B, Wsym, s);
+  if (rc) return rc;
+  return gram_ffma_backward(x, gy, Wsym, gram_bp(B), gloss, B, F, act_range, eps, gx, s);
+}

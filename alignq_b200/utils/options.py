@@ -1,0 +1,66 @@
+"""Configuration namespace of the hot path.
+
+The reference parses ``argparse`` flags at import time into a module-global ``args``
+(``utils/options.py:5-98``, ``utils/options_office.py``) and the L1 code reads it at call time
+(``model/quantization.py:12,98``; ``utils/optimizer.py:13,231``).  This module keeps the same
+global object and field names but does NOT parse ``sys.argv`` on import; use ``set_args(...)``
+(or ``parse_args(argv)`` for the reference's flag spellings).  Defaults are the reference's.
+
+Extra fields (no reference counterpart): ``variant`` selects which of the three quantizer
+variants the math follows ('A' = cdf_alignment/*, 'B' = cdf_alignment_admm/resnet-*,
+'C' = cdf_alignment_admm/{dann,dsan}_office); ``gram_mode`` picks the Gram numerics
+('fp32' FFMA parity mode, 'tf32x3' / 'bf16' tcgen05 modes).
+"""
+from __future__ import annotations
+
+import argparse
+from types import SimpleNamespace
+
+_DEFAULTS = dict(
+    gpus=[0], bitW=2, abitW=2, act_range=2, lam=1.0, lam2=4.0, method="ours", stage="second",
+    train_batch_size=128, eval_batch_size=100, lr=0.04, momentum=0.9, weight_decay=1e-4,
+    variant="A", gram_mode="fp32", store_weight_attrs=True,
+)
+
+args = SimpleNamespace(**_DEFAULTS)
+
+
+def set_args(**kw):
+    """Update the global config; unknown keys are rejected so typos fail loudly."""
+    for k, v in kw.items():
+        if k not in _DEFAULTS:
+            raise KeyError(f"unknown alignq_b200 option {k!r}; known: {sorted(_DEFAULTS)}")
+        if k == "variant" and v not in ("A", "B", "C"):
+            raise ValueError("variant must be 'A', 'B' or 'C'")
+        if k == "gram_mode" and v not in ("fp32", "tf32x3", "bf16"):
+            raise ValueError("gram_mode must be 'fp32', 'tf32x3' or 'bf16'")
+        setattr(args, k, v)
+    return args
+
+
+def reset_args():
+    for k, v in _DEFAULTS.items():
+        setattr(args, k, list(v) if isinstance(v, list) else v)
+    return args
+
+
+def parse_args(argv=None):
+    """Accept the reference's command-line spellings (utils/options.py:31-91)."""
+    p = argparse.ArgumentParser(description="alignq_b200")
+    p.add_argument("--gpus", type=int, nargs="+", default=[0])
+    p.add_argument("--bitW", type=int, default=_DEFAULTS["bitW"])
+    p.add_argument("--abitW", type=int, default=_DEFAULTS["abitW"])
+    p.add_argument("--act_range", type=float, default=_DEFAULTS["act_range"])
+    p.add_argument("--lam", type=float, default=_DEFAULTS["lam"])
+    p.add_argument("--lam2", type=float, default=_DEFAULTS["lam2"])
+    p.add_argument("--method", type=str, default=_DEFAULTS["method"])
+    p.add_argument("--stage", type=str, default=_DEFAULTS["stage"])
+    p.add_argument("--train_batch_size", type=int, default=_DEFAULTS["train_batch_size"])
+    p.add_argument("--eval_batch_size", type=int, default=_DEFAULTS["eval_batch_size"])
+    p.add_argument("--lr", type=float, default=_DEFAULTS["lr"])
+    p.add_argument("--momentum", type=float, default=_DEFAULTS["momentum"])
+    p.add_argument("--weight_decay", type=float, default=_DEFAULTS["weight_decay"])
+    p.add_argument("--variant", type=str, default=_DEFAULTS["variant"], choices=["A", "B", "C"])
+    p.add_argument("--gram_mode", type=str, default=_DEFAULTS["gram_mode"], choices=["fp32", "tf32x3", "bf16"])
+    ns, _ = p.parse_known_args(argv)
+    return set_args(**vars(ns))

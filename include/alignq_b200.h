@@ -1,0 +1,153 @@
+/* alignq_b200 -- C ABI of the B200-native AlignQ quantization hot path.
+ *
+ * The reference (tinganchen/AlignQ) is pure Python/PyTorch and has no FFI; this header is the
+ * boundary a replacement shared library exports.  Every entry point names the reference
+ * function it replaces (paths relative to the reference root; QA = cdf_alignment/<exp>/model/
+ * quantization.py, QB = cdf_alignment_admm/resnet-56-cifar-10/model/quantization.py, QC =
+ * cdf_alignment_admm/dann_office/model/quantization.py, OPT = <exp>/utils/optimizer.py,
+ * ADMM = <exp>/utils/admm.py).  INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions
+ *   - All data pointers are DEVICE pointers into caller-owned, contiguous fp32 storage
+ *     (NCHW activations viewed as [B, F] row-major; weights flat).  The library never allocates,
+ *     never synchronises the host and never creates streams: work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*; NULL = legacy default stream) and the call returns.
+ *   - Return value: 0 on success, a positive cudaError_t if a launch failed, or a negative
+ *     ALIGNQ_E* argument error.  Nothing throws.  alignq_error_string() describes any code.
+ *   - NaN/Inf propagate through the arithmetic; the reference raises ValueError from
+ *     torch.distributions' host-side validation instead (a device sync) -- documented deviation.
+ *   - Thread-safe: no global mutable state; callable from autograd worker threads.
+ *   - variant: 0 = QA (c = Phi), 1 = QB, 2 = QC (t = (2 Phi - 1) [* act_range]); QB and QC differ
+ *     only in corr()'s eps, which is an explicit argument.
+ */
+#ifndef ALIGNQ_B200_H_
+#define ALIGNQ_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ALIGNQ_ABI_VERSION 1
+#define ALIGNQ_CHUNK 4096          /* elements per multi-tensor work chunk */
+
+typedef void* alignq_stream_t;     /* cudaStream_t */
+
+enum { ALIGNQ_VARIANT_A = 0, ALIGNQ_VARIANT_B = 1, ALIGNQ_VARIANT_C = 2 };
+enum { ALIGNQ_GRAM_FP32 = 0,       /* CUDA-core FFMA, fp32 parity (1e-5) */
+       ALIGNQ_GRAM_TF32X3 = 1,     /* tcgen05 kind::tf32, 3-pass split, fp32 parity (1e-5) */
+       ALIGNQ_GRAM_BF16 = 2 };     /* tcgen05 kind::f16 bf16 operands, 1e-2 */
+
+int alignq_abi_version(void);
+const char* alignq_error_string(int code);
+
+/* ---- activation quantizer ------------------------------------------------------------------
+ * activation_quantize_fn.forward (QA:91-103; QB:102-132 without the ADMM branch; QC:96-110):
+ *   A: y = (round(Phi(x) n)/n * 2 - 1) * act_range          n = 2^a_bit - 1
+ *   B/C: y = round(t n)/n, t = (2 Phi(x) - 1) * act_range
+ * a_bit == 1 uses sign() (QA:22-23); a_bit == 32 with return_cdf != 0 is stage=='align' and
+ * returns the un-rounded map (QA:100-101).  a_bit == 32 without return_cdf is the identity and
+ * is the caller's job (ALIGNQ_EINVAL).  `codes` (nullable) receives round(.) as int16.
+ * alignq_act_bwd is the whole autograd backward in one pass (uniform_quantize.backward QA:29-32
+ * chained with erf'):  gx = gy * alignq_act_grad_scale(...) * exp(-x^2/2).                    */
+int alignq_act_fwd(const float* x, float* y, int16_t* codes, int64_t numel, int a_bit, float act_range,
+                   int variant, int return_cdf, alignq_stream_t stream);
+int alignq_act_bwd(const float* x, const float* gy, float* gx, int64_t numel, int a_bit, float act_range,
+                   int variant, int return_cdf, alignq_stream_t stream);
+float alignq_act_grad_scale(int a_bit, float act_range, int variant, int return_cdf);
+
+/* Stand-alone pieces of the reference surface (the hot path uses the fused kernels):
+ * uniform_quantize(k).forward (QA:15-27): y = round(x n)/n, k == 1: sign(x).
+ * cdf(m, s, src).forward (QA:45-50; QB:49-59): Normal(m, s).cdf mapped per variant, and
+ * pdf = 2 exp(log_prob) (pdf_out nullable); m, s are DEVICE scalars.  alignq_cdf_bwd is d/dx of
+ * both outputs with m, s held constant (g_cdf / g_pdf nullable).                                  */
+int alignq_uniform_q_fwd(const float* x, float* y, int64_t numel, int k, alignq_stream_t stream);
+int alignq_cdf_fwd(const float* x, const float* m, const float* s, int variant, int src_is_act,
+                   float act_range, float* cdf_out, float* pdf_out, int64_t numel, alignq_stream_t stream);
+int alignq_cdf_bwd(const float* x, const float* m, const float* s, int variant, int src_is_act,
+                   float act_range, const float* g_cdf, const float* g_pdf, float* gx, int64_t numel,
+                   alignq_stream_t stream);
+
+/* ---- weight quantizer (multi-tensor) ---------------------------------------------------------
+ * weight_quantize_fn.forward (QA:62-78; QB:71-85): per-TENSOR mean / unbiased std (QA:70), CDF
+ * map, rounding, dequant; also the attributes weight_cdf / weight_pdf (QB:78) read by SGD.step.
+ * Tensors are segments of one flat fp32 buffer: tensor t = flat[seg_off[t], seg_off[t+1]).
+ * alignq_wq_plan (host helper) splits the segments into ALIGNQ_CHUNK-element chunks:
+ *   chunk_seg[c] = segment of chunk c, seg_chunk0[t] = first chunk of segment t (nseg+1 entries);
+ * it returns the chunk count (pass NULL outputs to size the tables).  seg_off / chunk_seg /
+ * seg_chunk0 passed to the launch functions are DEVICE copies of those tables.
+ * ws: nchunks*2 doubles of scratch.  stats: nseg*4 floats out = {mean, std, 1/std, numel}.
+ * Backward (autograd through mean and std):
+ *   gw_j = (1/s) [a_j - sum(a)/N - z_j sum(a z)/(N-1)],  a = 2 g phi(z).                       */
+int64_t alignq_wq_plan(const int64_t* seg_off_host, int nseg, int32_t* chunk_seg_host, int32_t* seg_chunk0_host);
+int alignq_wq_forward(const float* flat, const int64_t* seg_off, const int32_t* chunk_seg,
+                      const int32_t* seg_chunk0, int nseg, int64_t nchunks, int w_bit, int variant,
+                      float* wq, float* w_cdf, float* w_pdf, int16_t* codes, float* stats, double* ws,
+                      alignq_stream_t stream);
+int alignq_wq_backward(const float* flat, const float* g_wq, const int64_t* seg_off, const int32_t* chunk_seg,
+                       const int32_t* seg_chunk0, int nseg, int64_t nchunks, int w_bit, const float* stats,
+                       float* g_w, double* ws, alignq_stream_t stream);
+
+/* ---- correlation / Gram ----------------------------------------------------------------------
+ * corr(x, y) (QB:134-137 eps = 0; QC:158-161 eps = 1e-5): standardise every feature column over
+ * the batch dim (unbiased std), G = Xs Ys^T / F.  x, y: [B, F] row-major (y may alias x).
+ * ws: alignq_gram_ws_bytes(B, F) bytes of scratch.                                              */
+size_t alignq_gram_ws_bytes(int B, int64_t F);
+int alignq_corr_fwd(const float* x, const float* y, int B, int64_t F, float eps, float* G, void* ws,
+                    size_t ws_bytes, int gram_mode, alignq_stream_t stream);
+
+/* ---- fused activation quantizer + ADMM correlation term --------------------------------------
+ * activation_quantize_fn.forward with method=='ours' (QB:102-132) / activation_quantize_fn2
+ * (QC:126-156): one read of x produces y, corr(x), corr(t), D = corr(t) - corr(x) (QB:118-122),
+ * trans_loss = ADMM.forward(D) (ADMM:24-33) and dLdD for the backward.  Z = alterD, U = gamma are
+ * [dim, dim] with dim >= B; the [:B, :B] corner is used (ADMM:26-27).
+ * Backward: gx = corr_bwd(x, -gloss dLdD) + (corr_bwd(t, gloss dLdD) + gy) * 2 ar phi(x);
+ * gloss is a DEVICE scalar (the upstream gradient of trans_loss); gy may be NULL (no y-grad).  */
+int alignq_act_admm_fwd(const float* x, int B, int64_t F, int a_bit, float act_range, float eps,
+                        const float* Z, const float* U, int dim, float mu, float rho,
+                        float* y, float* D, float* loss, float* dLdD, void* ws, size_t ws_bytes,
+                        int gram_mode, alignq_stream_t stream);
+int alignq_act_admm_bwd(const float* x, const float* gy, const float* dLdD, const float* gloss,
+                        int B, int64_t F, int a_bit, float act_range, float eps, float* gx,
+                        void* ws, size_t ws_bytes, int gram_mode, alignq_stream_t stream);
+
+/* ---- ADMM loss and Z/U update (batched over nmod modules) ------------------------------------
+ * ADMM.forward (ADMM:24-33): loss = mu mean|Z| + rho/2 sqrt(mean (D-Z)^2) + mean(U |D-Z|), and
+ * dLdD.  Module m uses D + m*B*B, Z + m*dim*dim, U + m*dim*dim, loss[m],
+ * dLdD + m*B*B.  loss, dLdD, dLdZ, dLdU ([dim,dim], zero outside the corner) are each nullable;
+ * the gradients are scaled by the DEVICE scalar *gloss (gloss[m] if gloss_per_module; NULL = 1).
+ * ADMM_OPT.step (OPT:97-124): V = pad(D) + U/rho; Z <- max(0, 1 - (mu/rho)/||V||_F) V;
+ * U <- U + rho (pad(D) - Z).  No host sync (the reference branches on the host).                */
+int alignq_admm_loss(const float* D, int B, const float* Z, const float* U, int dim, int nmod,
+                     float mu, float rho, const float* gloss, int gloss_per_module,
+                     float* loss, float* dLdD, float* dLdZ, float* dLdU, alignq_stream_t stream);
+int alignq_admm_zu_update(float* Z, float* U, const float* D, int B, int dim, int nmod,
+                          float mu, float rho, alignq_stream_t stream);
+
+/* ---- multi-tensor SGD with the quantization-aware gradient surrogate --------------------------
+ * SGD.step(idx, w_cdf, w_pdf, lam, lam2) (OPT:196-262): d_p = g + wd p (in place on g);
+ * buf = mom buf + (1-damp) d_p (first step: buf = d_p); d_p = nesterov ? d_p + mom buf : buf;
+ * p -= lr d_p; g <- d_p, or for tensors with w_cdf != NULL:
+ * g <- d_p * sigmoid'(((w_cdf+0.5)(2^bitW-1) mod 1) 2 lam2) lam * w_pdf (OPT:6-13, 232-249).
+ * `tensors` is a DEVICE array; chunk tables as in alignq_wq_plan over numel.                    */
+typedef struct alignq_sgd_tensor {
+  float* p;
+  float* g;
+  float* buf;              /* NULL when momentum == 0 */
+  const float* w_cdf;      /* NULL unless the tensor is in idx */
+  const float* w_pdf;
+  int64_t numel;
+  float lr, momentum, dampening, weight_decay;
+  int32_t nesterov;
+  int32_t first_step;      /* 1: momentum buffer not yet initialised */
+} alignq_sgd_tensor_t;
+int alignq_sgd_step(const alignq_sgd_tensor_t* tensors, const int32_t* chunk_tensor,
+                    const int32_t* tensor_chunk0, int ntensors, int64_t nchunks,
+                    float lam, float lam2, int bitW, alignq_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ALIGNQ_B200_H_ */

@@ -1,0 +1,413 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star):
+  * integer codes bit-exact vs the reference's own PyTorch path run GPU-eager (the oracle on CUDA
+    tensors); at most +-1 code on <= 1e-5 of elements at rounding ties;
+  * dequantised outputs, STE gradients, Gram / ADMM terms within 1e-5 relative in fp32.
+"""
+import numpy as np
+import pytest
+import torch
+
+import alignq_b200 as aq
+from alignq_b200 import _lib as L
+from oracle import alignq_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TIE_FRAC = 1e-5
+
+
+def t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def codes_close(mine, ref, n_levels_step=1):
+    """bit-exact up to ties: |diff| <= 1 code on <= 1e-5 of the elements (at least 1 allowed)."""
+    d = (mine.to(torch.int64) - ref.to(torch.int64)).abs()
+    bad = int((d > 0).sum())
+    assert int(d.max()) <= n_levels_step, f"code differs by more than one level: {int(d.max())}"
+    assert bad <= max(1, int(TIE_FRAC * mine.numel())), f"{bad} of {mine.numel()} codes differ"
+    return bad
+
+
+def rel_close(a, b, rtol=1e-5, atol_frac=1e-6, what=""):
+    """|a-b| <= rtol*|b| + atol_frac*max|b|   (fp32 tolerance 1e-5 relative)"""
+    a, b = a.double(), b.double()
+    tol = rtol * b.abs() + atol_frac * float(b.abs().max())
+    err = (a - b).abs()
+    nan_ok = torch.isnan(a) == torch.isnan(b)
+    assert bool(nan_ok.all()), f"{what}: NaN pattern differs"
+    mask = ~torch.isnan(b)
+    assert bool((err[mask] <= tol[mask]).all()), f"{what}: max rel err {float((err[mask] / (b[mask].abs() + 1e-30)).max()):.3e}, max abs {float(err[mask].max()):.3e}"
+
+
+def act_codes_via_abi(x, k, variant, ar=2.0, return_cdf=0):
+    lib = L.load()
+    y = torch.empty_like(x)
+    codes = torch.empty(x.shape, dtype=torch.int16, device=x.device)
+    L.check(lib.alignq_act_fwd(x.data_ptr(), y.data_ptr(), codes.data_ptr(), x.numel(), k, ar,
+                               L.VARIANT_ID[variant], return_cdf, L.stream_ptr()), "act_fwd")
+    return y, codes
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("variant", ["A", "B"])
+@pytest.mark.parametrize("k", [2, 4, 8])
+def test_act_codes_bit_exact_vs_gpu_eager_reference(variant, k):
+    torch.manual_seed(0)
+    x = torch.randn(128 * 16 * 32 * 32 + 3).to(DEV)          # cfg-1 shape plus a ragged tail
+    y, codes = act_codes_via_abi(x, k, variant)
+    ref_codes = O.activation_codes(x, k, variant, 2.0)
+    ref_y = O.activation_quantize(x, k, "second", variant, 2.0)
+    codes_close(codes, ref_codes)
+    n = 2 ** k - 1
+    step = (2.0 * 2.0 / n) if variant == "A" else (1.0 / n)
+    mism = (y != ref_y)
+    assert int(mism.sum()) <= max(1, int(TIE_FRAC * x.numel()))
+    assert float((y - ref_y).abs().max()) <= step * 1.0001
+
+
+@pytest.mark.parametrize("variant", ["A", "B"])
+def test_act_cpu_oracle_ties_are_rare(variant):
+    """CPU-eager divides where CUDA-eager multiplies by a reciprocal: report and bound."""
+    torch.manual_seed(1)
+    x = torch.randn(1 << 20)
+    _, codes = act_codes_via_abi(x.to(DEV), 8, variant)
+    cpu_codes = O.activation_codes(x, 8, variant, 2.0)
+    bad = codes_close(codes.cpu(), cpu_codes)
+    print(f"variant {variant}: {bad} / {x.numel()} codes differ from the CPU oracle")
+
+
+@pytest.mark.parametrize("variant", ["A", "B", "C"])
+def test_act_golden_fixtures(golden, variant):
+    g = golden(variant)
+    aq.set_args(variant=variant, act_range=2, method="none")
+    x = t(g["act_x"]).to(DEV)
+    gy = t(g["act_gy"]).to(DEV)
+    for k in (2, 4, 8, 1, 32):
+        stage = "align" if k == 32 else "second"
+        xr = x.clone().requires_grad_(True)
+        y = aq.activation_quantize_fn(k, stage)(xr)
+        (y * gy).sum().backward()
+        ref_y, ref_g = t(g[f"act_y_k{k}"]), t(g[f"act_gx_k{k}"])
+        if k in (2, 4, 8):
+            _, codes = act_codes_via_abi(x, k, variant)
+            codes_close(codes.cpu(), t(g[f"act_codes_k{k}"]))
+            assert int((y.cpu() != ref_y).sum()) <= 1
+        else:
+            rel_close(y.cpu(), ref_y, what=f"act y k={k}")
+        rel_close(xr.grad.cpu(), ref_g, what=f"act gx k={k}")
+
+
+@pytest.mark.parametrize("variant", ["A", "B"])
+def test_act_backward_vs_gpu_eager_autograd(variant):
+    torch.manual_seed(2)
+    aq.set_args(variant=variant, act_range=2)
+    x = (torch.randn(64, 32, 16, 16) * 1.5).to(DEV)
+    gy = torch.randn_like(x)
+    xr = x.clone().requires_grad_(True)
+    (aq.activation_quantize_fn(8, "second")(xr) * gy).sum().backward()
+    xo = x.clone().requires_grad_(True)
+    (O.activation_quantize(xo, 8, "second", variant, 2.0) * gy).sum().backward()
+    rel_close(xr.grad, xo.grad, what="act gx")
+
+
+def test_act_edge_cases():
+    aq.set_args(variant="A", act_range=2)
+    q = aq.activation_quantize_fn(8, "second")
+    assert q(torch.empty(0, 4, device=DEV)).shape == (0, 4)                       # empty
+    for n in (1, 2, 3, 5, 7, 4099):                                               # ragged sizes
+        x = torch.randn(n, device=DEV)
+        assert torch.equal(q(x), O.activation_quantize(x, 8, "second", "A", 2.0))
+    base = torch.randn(4100, device=DEV)
+    x = base[1:]                                                                  # 4-byte-aligned view only
+    assert x.data_ptr() % 16 != 0
+    assert torch.equal(q(x), O.activation_quantize(x, 8, "second", "A", 2.0))
+    xt = torch.randn(33, 65, device=DEV).t()                                      # non-contiguous input
+    assert torch.equal(q(xt), O.activation_quantize(xt.contiguous(), 8, "second", "A", 2.0))
+    sp = torch.tensor([float("nan"), float("inf"), -float("inf"), 0.0, -0.0, 40.0, -40.0, 1e-30], device=DEV)
+    y, ref = q(sp), O.activation_quantize(sp, 8, "second", "A", 2.0)
+    assert torch.equal(torch.isnan(y), torch.isnan(ref)) and torch.equal(y[1:], ref[1:])
+    # saturating ends: codes 0 and n
+    _, codes = act_codes_via_abi(sp, 8, "A")
+    assert codes[1].item() == 255 and codes[2].item() == 0
+
+
+def test_act_properties_at_full_size():
+    """Size-independent properties at the largest single activation of the configs ([256,144,32,32])."""
+    torch.manual_seed(3)
+    n = 256 * 144 * 32 * 32
+    x = torch.randn(n, device=DEV)
+    for variant, lo, hi in (("A", 0, 255), ("B", -510, 510)):
+        y, codes = act_codes_via_abi(x, 8, variant)
+        assert int(codes.min()) >= lo and int(codes.max()) <= hi
+        xs, order = torch.sort(x[: 1 << 22])
+        assert bool((torch.diff(y[: 1 << 22][order]) >= 0).all())                 # monotone in x
+        assert float(y.abs().max()) <= 2.0
+        if variant == "B":                                                        # odd symmetry of the map
+            y2, _ = act_codes_via_abi(-x, 8, variant)
+            assert float((y + y2).abs().max()) <= 1.0 / 255 + 1e-7
+    gy = torch.ones_like(x)
+    gx = torch.empty_like(x)
+    L.check(L.load().alignq_act_bwd(x.data_ptr(), gy.data_ptr(), gx.data_ptr(), n, 8, 2.0, 0, 0, L.stream_ptr()), "bwd")
+    assert float(gx.min()) >= 0.0 and float(gx.max()) <= 4.0 * 0.3989423 + 1e-6   # 2*ar*phi(0)
+    # linearity of the backward in gy
+    gx3 = torch.empty_like(x)
+    gy3 = gy * 3.0
+    L.check(L.load().alignq_act_bwd(x.data_ptr(), gy3.data_ptr(), gx3.data_ptr(), n, 8, 2.0, 0, 0, L.stream_ptr()), "bwd")
+    assert torch.allclose(gx3, 3.0 * gx, rtol=1e-6, atol=0)
+
+
+# ------------------------------------------------------------------------------------------------
+WEIGHT_SHAPES = [(16, 3, 3, 3), (16, 16, 3, 3), (64, 64, 3, 3), (32, 1, 3, 3), (64, 32, 1, 1), (2048, 512, 1, 1),
+                 (64, 3, 7, 7), (5, 7)]
+
+
+@pytest.mark.parametrize("variant", ["A", "B"])
+@pytest.mark.parametrize("k", [4, 8])
+def test_weight_quantizer_vs_oracle(variant, k):
+    torch.manual_seed(4)
+    aq.set_args(variant=variant, bitW=k)
+    total = bad = 0
+    for shape in WEIGHT_SHAPES:
+        fan = int(np.prod(shape[1:]))
+        w = (torch.randn(*shape) * (2.0 / fan) ** 0.5).to(DEV)
+        gup = torch.randn_like(w)
+        mod = aq.weight_quantize_fn(k, "second")
+        wr = w.clone().requires_grad_(True)
+        wq = mod(wr)
+        (wq * gup).sum().backward()
+        wo = w.clone().requires_grad_(True)
+        oq, oc, op = O.weight_quantize(wo, k, variant)
+        (oq * gup).sum().backward()
+        n = 2 ** k - 1
+        mine_codes = torch.round(((wq + 1) / 2 if variant == "A" else wq) * n)
+        ref_codes = torch.round(((oq.detach() + 1) / 2 if variant == "A" else oq.detach()) * n)
+        d = (mine_codes - ref_codes).abs()
+        assert float(d.max()) <= 1
+        bad += int((d > 0).sum())
+        total += w.numel()
+        rel_close(mod.weight_cdf, oc.detach(), rtol=1e-5, atol_frac=2e-6, what=f"weight_cdf {shape}")
+        rel_close(mod.weight_pdf, op.detach(), rtol=2e-5, atol_frac=2e-6, what=f"weight_pdf {shape}")
+        rel_close(wr.grad, wo.grad, rtol=1e-4, atol_frac=2e-5, what=f"gw {shape}")
+        assert abs(float(wr.grad.double().sum())) <= 1e-3 * float(wr.grad.double().abs().sum()) + 1e-6   # sum gw = 0
+    # stats differ from torch's fp32 mean/std by <= 1 ulp, which can flip a code that sits on a tie
+    assert bad <= max(2, int(2e-5 * total)), f"{bad}/{total} weight codes differ"
+
+
+@pytest.mark.parametrize("variant", ["A", "B"])
+def test_weight_codes_bit_exact_given_same_stats(variant):
+    """With the kernel's own (mean, std) fed to the reference chain the codes must be identical."""
+    torch.manual_seed(5)
+    lib = L.load()
+    w = (torch.randn(64, 64, 3, 3) * 0.06 + 0.003).to(DEV)
+    seg_off, chunk_seg, seg_chunk0, nchunks = L.plan_chunks([w.numel()])
+    d_off = torch.tensor(seg_off, dtype=torch.int64, device=DEV)
+    d_cs = torch.tensor(chunk_seg, dtype=torch.int32, device=DEV)
+    d_c0 = torch.tensor(seg_chunk0, dtype=torch.int32, device=DEV)
+    wq, wc, wp = torch.empty_like(w), torch.empty_like(w), torch.empty_like(w)
+    codes = torch.empty(w.shape, dtype=torch.int16, device=DEV)
+    stats = torch.empty(4, device=DEV)
+    ws = torch.empty(2 * nchunks, dtype=torch.float64, device=DEV)
+    L.check(lib.alignq_wq_forward(w.data_ptr(), d_off.data_ptr(), d_cs.data_ptr(), d_c0.data_ptr(), 1, nchunks, 8,
+                                  L.VARIANT_ID[variant], wq.data_ptr(), wc.data_ptr(), wp.data_ptr(),
+                                  codes.data_ptr(), stats.data_ptr(), ws.data_ptr(), L.stream_ptr()), "wq_forward")
+    m, s = stats[0], stats[1]
+    assert abs(float(m) - float(w.double().mean())) <= 1e-6 * float(w.double().std()) + 1e-9
+    assert abs(float(s) / float(w.double().std()) - 1) <= 2e-7
+    c_ref, p_ref = O.cdf_map(w, m, s, "w", variant, 0.0)
+    assert torch.equal(codes.float(), torch.round(c_ref * 255))
+    assert torch.equal(wc, c_ref)
+    q_ref = O.uniform_quantize(c_ref, 8) * 2 - 1 if variant == "A" else O.uniform_quantize(c_ref, 8)
+    assert torch.equal(wq, q_ref)
+    rel_close(wp, p_ref, rtol=2e-6, atol_frac=1e-7, what="pdf")
+
+
+def test_weight_multi_tensor_launch_matches_single():
+    """One launch over many ragged segments == per-tensor launches (bit for bit)."""
+    torch.manual_seed(6)
+    lib = L.load()
+    sizes = [432, 2304, 4096, 4097, 36864, 9, 147456, 8193]
+    flat = (torch.randn(sum(sizes)) * 0.1).to(DEV)
+    gq = torch.randn_like(flat)
+    seg_off, chunk_seg, seg_chunk0, nchunks = L.plan_chunks(sizes)
+    d_off = torch.tensor(seg_off, dtype=torch.int64, device=DEV)
+    d_cs = torch.tensor(chunk_seg, dtype=torch.int32, device=DEV)
+    d_c0 = torch.tensor(seg_chunk0, dtype=torch.int32, device=DEV)
+    wq, gw = torch.empty_like(flat), torch.empty_like(flat)
+    stats = torch.empty(4 * len(sizes), device=DEV)
+    ws = torch.empty(2 * nchunks, dtype=torch.float64, device=DEV)
+    L.check(lib.alignq_wq_forward(flat.data_ptr(), d_off.data_ptr(), d_cs.data_ptr(), d_c0.data_ptr(), len(sizes),
+                                  nchunks, 8, 1, wq.data_ptr(), 0, 0, 0, stats.data_ptr(), ws.data_ptr(),
+                                  L.stream_ptr()), "wq_forward")
+    L.check(lib.alignq_wq_backward(flat.data_ptr(), gq.data_ptr(), d_off.data_ptr(), d_cs.data_ptr(), d_c0.data_ptr(),
+                                   len(sizes), nchunks, 8, stats.data_ptr(), gw.data_ptr(), ws.data_ptr(),
+                                   L.stream_ptr()), "wq_backward")
+    aq.set_args(variant="B", bitW=8)
+    for i, n in enumerate(sizes):
+        a, b = seg_off[i], seg_off[i + 1]
+        w = flat[a:b].clone().requires_grad_(True)
+        q = aq.weight_quantize_fn(8, "second")(w)
+        (q * gq[a:b]).sum().backward()
+        assert torch.equal(q.detach(), wq[a:b]), f"segment {i}"
+        assert torch.equal(w.grad, gw[a:b]), f"segment {i}"
+
+
+@pytest.mark.parametrize("variant", ["A", "B", "C"])
+def test_weight_golden_fixtures(golden, variant):
+    g = golden(variant)
+    aq.set_args(variant=variant)
+    w, gup = t(g["w"]).to(DEV), t(g["w_gup"]).to(DEV)
+    for k in (2, 4, 8):
+        aq.set_args(bitW=k)
+        mod = aq.weight_quantize_fn(k, "second")
+        wr = w.clone().requires_grad_(True)
+        wq = mod(wr)
+        (wq * gup).sum().backward()
+        n = 2 ** k - 1
+        step = (2.0 if variant == "A" else 1.0) / n
+        d = (wq.detach().cpu() - t(g[f"w_q_k{k}"])).abs()
+        assert float(d.max()) <= step * 1.0001 and int((d > 0).sum()) <= 1
+        rel_close(mod.weight_cdf.cpu(), t(g[f"w_cdf_k{k}"]), rtol=1e-5, atol_frac=2e-6)
+        rel_close(mod.weight_pdf.cpu(), t(g[f"w_pdf_k{k}"]), rtol=2e-5, atol_frac=2e-6)
+        rel_close(wr.grad.cpu(), t(g[f"w_g_k{k}"]), rtol=1e-4, atol_frac=2e-5, what=f"gw k={k}")
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,F,eps", [(8, 96, 0.0), (28, 3000, 1e-5), (128, 4096, 0.0), (100, 1027, 0.0),
+                                     (224, 2048, 1e-5)])
+def test_corr_vs_oracle(B, F, eps):
+    torch.manual_seed(7)
+    x = torch.randn(B, F, device=DEV)
+    y = torch.randn(B, F, device=DEV) * 2 + 0.5
+    G = aq.corr(x, x, eps)
+    rel_close(G, O.corr(x, x, eps), rtol=1e-5, atol_frac=2e-6, what="corr(x,x)")
+    assert abs(float(G.trace()) - (B - 1)) < 1e-2 or eps > 0
+    assert float(G.sum(dim=1).abs().max()) < 1e-3                 # rows of a standardised Gram sum to 0
+    rel_close(aq.corr(x, y, eps), O.corr(x, y, eps), rtol=1e-5, atol_frac=2e-6, what="corr(x,y)")
+
+
+def test_corr_constant_column_gives_nan_like_reference():
+    x = torch.randn(8, 64, device=DEV)
+    x[:, 5] = 1.25
+    assert bool(torch.isnan(aq.corr(x, x, 0.0)).all()) and bool(torch.isnan(O.corr(x, x, 0.0)).all())
+    assert not bool(torch.isnan(aq.corr(x, x, 1e-5)).any())
+
+
+@pytest.mark.parametrize("variant", ["B", "C"])
+def test_fused_act_admm_golden_fixtures(golden, variant):
+    g = golden(variant)
+    aq.set_args(variant=variant, act_range=2, method="ours", gram_mode="fp32")
+    dim = g["admm_Z"].shape[0]
+    for B in (dim, dim - 3):
+        for k in (4, 8):
+            tag = f"b{B}_k{k}"
+            admm = aq.ADMM(dim).to(DEV)
+            with torch.no_grad():
+                admm.alterD.copy_(t(g["admm_Z"]))
+                admm.gamma.copy_(t(g["admm_U"]))
+            Fn = aq.activation_quantize_fn if variant == "B" else aq.activation_quantize_fn2
+            x = t(g["act_x"])[:B].to(DEV).requires_grad_(True)
+            y, loss = Fn(k, "second", admm)(x)
+            ((y * t(g["act_gy"])[:B].to(DEV)).sum() + 1.5 * loss).backward()
+            assert int((y.detach().cpu() != t(g[f"fused_y_{tag}"])).sum()) <= 1
+            rel_close(admm.D.cpu(), t(g[f"fused_D_{tag}"]), rtol=1e-5, atol_frac=1e-5, what="D")
+            rel_close(loss.detach().cpu(), t(g[f"fused_loss_{tag}"]), rtol=1e-5, what="trans_loss")
+            rel_close(x.grad.cpu(), t(g[f"fused_gx_{tag}"]), rtol=1e-4, atol_frac=1e-5, what="fused gx")
+
+
+@pytest.mark.parametrize("variant,B,shape", [("B", 128, (16, 16, 16)), ("B", 128, (64, 8, 8)), ("C", 28, (64, 14, 14)),
+                                             ("B", 100, (32, 16, 16))])
+def test_fused_act_admm_vs_gpu_eager_oracle(variant, B, shape):
+    torch.manual_seed(8)
+    aq.set_args(variant=variant, act_range=2, method="ours", gram_mode="fp32")
+    dim = 128
+    admm = aq.ADMM(dim).to(DEV)
+    x0 = torch.randn(B, *shape, device=DEV)
+    gy = torch.randn_like(x0)
+    Fn = aq.activation_quantize_fn if variant == "B" else aq.activation_quantize_fn2
+    x = x0.clone().requires_grad_(True)
+    y, loss = Fn(8, "second", admm)(x)
+    ((y * gy).sum() + loss).backward()
+    xo = x0.clone().requires_grad_(True)
+    Zo = admm.alterD.detach().clone().requires_grad_(True)
+    Uo = admm.gamma.detach().clone().requires_grad_(True)
+    yo, lo, Do = O.activation_quantize_admm(xo, 8, Zo, Uo, "second", variant, 2.0)
+    ((yo * gy).sum() + lo).backward()
+    assert int((y != yo).sum()) <= max(1, int(TIE_FRAC * y.numel()))
+    rel_close(admm.D, Do.detach(), rtol=1e-5, atol_frac=1e-5, what="D")
+    rel_close(loss.detach(), lo.detach(), rtol=1e-5, what="trans_loss")
+    rel_close(x.grad, xo.grad, rtol=1e-4, atol_frac=1e-5, what="gx")
+    rel_close(admm.alterD.grad, Zo.grad, rtol=1e-4, atol_frac=1e-5, what="d loss / d alterD")
+    rel_close(admm.gamma.grad, Uo.grad, rtol=1e-4, atol_frac=1e-5, what="d loss / d gamma")
+
+
+@pytest.mark.parametrize("variant", ["B", "C"])
+def test_admm_loss_and_zu_update_golden(golden, variant):
+    g = golden(variant)
+    aq.set_args(bitW=8)
+    dim = g["admm_Z"].shape[0]
+    for B in (dim, dim - 3):
+        admm = aq.ADMM(dim).to(DEV)
+        with torch.no_grad():
+            admm.alterD.copy_(t(g["admm_Z"]))
+            admm.gamma.copy_(t(g["admm_U"]))
+        D = t(g[f"admm_D_b{B}"]).to(DEV).requires_grad_(True)
+        loss = admm(D)
+        loss.backward()
+        rel_close(loss.detach().cpu(), t(g[f"admm_loss_b{B}"]), rtol=1e-5, what="ADMM loss")
+        rel_close(D.grad.cpu(), t(g[f"admm_dD_b{B}"]), rtol=1e-5, atol_frac=1e-6, what="dL/dD")
+        opt = aq.ADMM_OPT([admm.alterD, admm.gamma])
+        opt.step([0], [1], [D.detach()], [admm.alterD], [admm.gamma], [admm.mu], [admm.rho])
+        rel_close(admm.alterD.detach().cpu(), t(g[f"zu_Z_b{B}"]), rtol=1e-5, atol_frac=1e-6, what="Z")
+        rel_close(admm.gamma.detach().cpu(), t(g[f"zu_U_b{B}"]), rtol=1e-5, atol_frac=1e-6, what="U")
+    small = aq.ADMM(dim).to(DEV)
+    with torch.no_grad():
+        small.alterD.fill_(0.3)
+        small.gamma.fill_(1e-3)
+    D = torch.full((dim, dim), 1e-3, device=DEV, requires_grad=True)
+    small(D).backward()
+    aq.ADMM_OPT([small.alterD, small.gamma]).step([0], [1], [D.detach()], [small.alterD], [small.gamma], [0.2], [0.3])
+    assert float(small.alterD.abs().max()) == 0.0                                 # ||V|| <= mu/rho -> Z = 0
+    rel_close(small.gamma.detach().cpu(), t(g["zu_small_U"]), rtol=1e-5, what="U small")
+
+
+@pytest.mark.parametrize("variant", ["A", "B"])
+def test_sgd_step_golden(golden, variant):
+    g = golden(variant)
+    aq.set_args(bitW=8)
+    idx, n = [2, 3], 5
+    wc = [t(g[f"sgd_wcdf_{j}"]).to(DEV) for j in range(2)]
+    wp = [t(g[f"sgd_wpdf_{j}"]).to(DEV) for j in range(2)]
+    cfgs = {"mom": dict(lr=0.04, momentum=0.9, weight_decay=1e-4),
+            "nest": dict(lr=0.02, momentum=0.8, weight_decay=5e-4, nesterov=True),
+            "plain": dict(lr=0.1)}
+    for name, kw in cfgs.items():
+        ps = [torch.nn.Parameter(t(g[f"sgd_p0_{i}"]).to(DEV)) for i in range(n)]
+        opt = aq.SGD(ps, **kw)
+        for s in range(3):
+            for i, p in enumerate(ps):
+                p.grad = t(g[f"sgd_g{s}_{i}"]).to(DEV)
+            opt.step(idx, wc, wp, 1.0, 4.0)
+            for i, p in enumerate(ps):
+                rel_close(p.detach().cpu(), t(g[f"sgd_{name}_p{s}_{i}"]), rtol=2e-6, atol_frac=1e-7, what=f"{name} p{i} step{s}")
+                rel_close(p.grad.cpu(), t(g[f"sgd_{name}_grad{s}_{i}"]), rtol=1e-5, atol_frac=1e-6, what=f"{name} grad{i} step{s}")
+
+
+def test_uniform_quantize_and_cdf_standalone():
+    torch.manual_seed(9)
+    x = torch.rand(1000, device=DEV) * 2 - 1
+    for k in (1, 2, 8):
+        assert torch.equal(aq.uniform_quantize(k)(x), O.uniform_quantize(x, k))
+    xr = x.clone().requires_grad_(True)
+    aq.uniform_quantize(4)(xr).sum().backward()
+    assert torch.equal(xr.grad, torch.ones_like(x))
+    for variant in ("A", "B"):
+        aq.set_args(variant=variant, act_range=2)
+        m, s = torch.tensor(0.1, device=DEV), torch.tensor(0.7, device=DEV)
+        for src in ("w", "a"):
+            c, p = aq.cdf(m, s, src)(x)
+            co, po = O.cdf_map(x, m, s, src, variant, 2.0)
+            assert torch.equal(c, co)
+            rel_close(p, po, rtol=2e-6, atol_frac=1e-7, what="pdf")

@@ -35,6 +35,7 @@ _P, _I, _L, _F, _Z = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
 SIGNATURES = {
     "alignq_abi_version": (_I, []),
     "alignq_error_string": (C.c_char_p, [_I]),
+    "alignq_launch_count": (C.c_uint64, []),
     "alignq_act_fwd": (_I, [_P, _P, _P, _L, _I, _F, _I, _I, _P]),
     "alignq_act_bwd": (_I, [_P, _P, _P, _L, _I, _F, _I, _I, _P]),
     "alignq_act_grad_scale": (_F, [_I, _F, _I, _I]),

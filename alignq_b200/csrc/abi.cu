@@ -2,6 +2,12 @@
 #include "common.cuh"
 #include "../../include/alignq_b200.h"
 
+#include <atomic>
+
+static std::atomic<unsigned long long> g_launches{0};
+extern "C" void alignq_count_launch_(void) { g_launches.fetch_add(1, std::memory_order_relaxed); }
+extern "C" uint64_t alignq_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
 extern "C" int alignq_abi_version(void) { return ALIGNQ_ABI_VERSION; }
 
 extern "C" const char* alignq_error_string(int code) {

@@ -12,10 +12,14 @@
 
 enum { ALIGNQ_OK = 0, ALIGNQ_EINVAL = -1, ALIGNQ_EALIGN = -2, ALIGNQ_ERANGE = -3, ALIGNQ_ENOSPACE = -4 };
 
+// every kernel launch of the library passes through here: error check + launch statistics
+// (alignq_launch_count(); a relaxed atomic, the only process-global state of the library)
+extern "C" void alignq_count_launch_(void);
 #define ALIGNQ_LAUNCH_CHECK()                         \
   do {                                                \
     cudaError_t e__ = cudaGetLastError();             \
     if (e__ != cudaSuccess) return (int)e__;          \
+    alignq_count_launch_();                           \
   } while (0)
 
 namespace alignq {

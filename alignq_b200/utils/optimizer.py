@@ -36,6 +36,8 @@ class SGD(Optimizer):
         self._table_key = None
         self._table_dev = None
         self._chunk_dev = None
+        self._chunk_key = None
+        self._pinned = []
 
     def __setstate__(self, state):
         super().__setstate__(state)
@@ -95,8 +97,12 @@ class SGD(Optimizer):
                     L.ptr(e[3]) or None, L.ptr(e[4]) or None
                 t.numel = e[0].numel()
                 t.lr, t.momentum, t.dampening, t.weight_decay, t.nesterov, t.first_step = e[5:]
-            host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
-            self._table_dev = host.to(dev, non_blocking=False)
+            # pinned staging + async copy: legal inside CUDA-graph capture (becomes a memcpy node that
+            # re-reads this pinned buffer on replay, so the buffer is kept alive and never rewritten)
+            host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).pin_memory()
+            self._pinned.append(host)
+            self._table_dev = torch.empty(host.numel(), dtype=torch.uint8, device=dev)
+            self._table_dev.copy_(host, non_blocking=True)
             if self._chunk_dev is None or self._chunk_key != tuple(e[0].numel() for e in ents):
                 _, chunk_t, t_chunk0, nchunks = L.plan_chunks([e[0].numel() for e in ents])
                 self._chunk_key = tuple(e[0].numel() for e in ents)

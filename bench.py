@@ -1,0 +1,304 @@
+"""Benchmark of the AlignQ quantization hot path on B200 (contract: see the task prompt, "bench.py").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[0], the configuration the metric is quoted on): 8-bit ResNet-20
+QAT, CIFAR-10 shaped synthetic data, per-GPU batch 128, variant QA (cdf_alignment/resnet-20-cifar-10),
+SGD lr .04 mom .9 wd 1e-4 lam 1 lam2 4.  A "step" is one training iteration of the reference's
+train() body: forward through the drop-in quantized modules, backward, SGD.step(idx, w_cdf, w_pdf,
+lam, lam2).  N > 1: one process per GPU, batch sharded, one NCCL all-reduce of the flat gradient
+buffer per step (weak scaling: per-GPU batch fixed).
+
+One JSON line on stdout (rank 0):
+  value     img/s, inputs resident in HBM, step replayed as a CUDA graph, CUDA-event time, max over ranks
+  e2e       img/s through the same public API with HOST (pinned) inputs: H2D of the batch and a D2H
+            read of the loss inside every timed step
+  roofline  the CDF-quantizer fwd+bwd kernel pair on a 256 x 2^20 fp32 stream (4 GiB of traffic per
+            pass, >> L2): algorithmic 20 B/elem / CUDA-event time, against MEASURED_PEAKS.json
+  cpu_baseline  the oracle's restatement of the same training iteration on the host cores
+--impl reference times only that CPU path (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+METRIC = "CDF-quant fwd+bwd HBM GB/s; 8-bit ResNet-20 QAT img/s @1/2/4/8 B200"
+BATCH = 128
+CONFIG = {"workload": "resnet20_quant W8A8 (QA) CIFAR-10 synthetic 32x32, QAT step fwd+bwd+SGD.step",
+          "per_gpu_batch": BATCH, "variant": "A", "bitW": 8, "abitW": 8, "act_range": 2,
+          "optimizer": "SGD lr=0.04 momentum=0.9 wd=1e-4 lam=1 lam2=4"}
+FALLBACK_HBM_GBS = 6650.0
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle's port of the reference training iteration (kind = "port")
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(steps, warmup, budget_s=150.0, batch=BATCH):
+    import torch
+    from oracle import models_oracle as MO
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    model = MO.resnet20_oracle(8, 8, "A", act_range=2.0, dim=batch).train()
+    tr = MO.OracleTrainer(model, lr=0.04, momentum=0.9, weight_decay=1e-4, lam=1.0, lam2=4.0, bitW=8)
+    x = torch.randn(batch, 3, 32, 32)
+    t = torch.randint(0, 10, (batch,))
+    t0 = time.perf_counter()
+    tr.step(x, t)                                          # first (untimed) iteration sizes the sample
+    first = time.perf_counter() - t0
+    sample_batch = batch
+    total = steps + max(warmup - 1, 0)
+    if first * total > budget_s:                           # bound the run: shrink the per-step sample
+        sample_batch = max(8, int(batch * budget_s / (first * total)) // 8 * 8)
+        x, t = x[:sample_batch], t[:sample_batch]
+    for _ in range(max(warmup - 1, 0)):
+        tr.step(x, t)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tr.step(x, t)
+    dt = time.perf_counter() - t0
+    return {"value": sample_batch * steps / dt, "unit": "img/s", "cores": cores, "kind": "port",
+            "sample": f"{steps} iterations of batch {sample_batch} (workload batch {batch}) after {warmup} warm-up, "
+                      f"oracle/models_oracle.OracleTrainer on CPU, torch threads={cores}",
+            "ms_per_step": dt / steps * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_reference_run(args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "img/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": CONFIG,
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for ln in self.f:
+            c = [v.strip() for v in ln.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def run_product(args):
+    import torch
+    import torch.distributed as dist
+
+    import alignq_b200 as aq
+    from alignq_b200 import _lib as L
+    from alignq_b200.model.resnet import resnet20_quant
+    from alignq_b200.utils.train import QATStep
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = aq.load_library()
+    torch.backends.cudnn.benchmark = True
+    aq.set_args(variant="A", bitW=8, abitW=8, act_range=2, lam=1.0, lam2=4.0, method="ours", train_batch_size=BATCH)
+    torch.manual_seed(0)                                   # identical replicas on every rank
+    model = resnet20_quant(8, 8, "second").to(dev).train()
+    if world > 1 and args.sync_bn:
+        model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
+    step = QATStep(model, lr=0.04, momentum=0.9, weight_decay=1e-4, world_size=world)
+
+    g = torch.Generator().manual_seed(1234 + rank)         # each rank its own shard of the synthetic batch
+    n_host = 8
+    host_x = [torch.randn(BATCH, 3, 32, 32, generator=g).pin_memory() for _ in range(n_host)]
+    host_t = [torch.randint(0, 10, (BATCH,), generator=g).pin_memory() for _ in range(n_host)]
+    dev_x = [h.to(dev) for h in host_x]
+    dev_t = [h.to(dev) for h in host_t]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    graphed = not args.no_graph
+    launches_per_step = None
+    if graphed:
+        try:
+            c0 = lib.alignq_launch_count()
+            step.capture(dev_x[0], dev_t[0], warmup=3)
+            # 3 eager warm-up iterations + the captured one
+            launches_per_step = (lib.alignq_launch_count() - c0) // 4
+        except Exception as e:                              # pragma: no cover - reported, not hidden
+            if rank == 0:
+                print(f"[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); running eager", file=sys.stderr)
+            graphed = False
+            step.graph = None
+    if launches_per_step is None:
+        c0 = lib.alignq_launch_count()
+        step.step(dev_x[0], dev_t[0])
+        launches_per_step = lib.alignq_launch_count() - c0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(k, w, host_inputs):
+        """k steps after w warm-ups; per-step CUDA events on the launching stream, L2 flushed between
+        steps (outside the events).  Returns summed device milliseconds."""
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k)]
+        sink = 0.0
+        for i in range(w + k):
+            flush.zero_()
+            j = i % n_host
+            if i >= w:
+                ev[i - w][0].record()
+            if host_inputs:
+                x = host_x[j].to(dev, non_blocking=True)
+                t = host_t[j].to(dev, non_blocking=True)
+                loss = step.step(x, t)
+                sink += float(loss.item())                  # D2H read of the step's loss (4 bytes), syncs
+            else:
+                step.step(dev_x[j], dev_t[j])
+            if i >= w:
+                ev[i - w][1].record()
+            if i == w - 1:
+                barrier()
+        barrier()
+        return sum(a.elapsed_time(b) for a, b in ev), sink
+
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms, _ = timed(args.steps, args.warmup, host_inputs=False)
+    clocks = sampler.stop() if sampler else None
+    ms_e2e, _ = timed(args.steps, max(args.warmup, 3), host_inputs=True)
+    tt = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(tt[0]), float(tt[1])
+    value = world * BATCH * args.steps / (ms * 1e-3)
+    e2e = world * BATCH * args.steps / (ms_e2e * 1e-3)
+
+    roofline = cpu = None
+    if rank == 0:
+        # ---- roofline leg: the CDF-quantizer kernel pair on a stream far larger than L2 -----------
+        n = 256 * (1 << 20)
+        x = torch.randn(n, device=dev)
+        gy = torch.randn(n, device=dev)
+        y, gx = torch.empty_like(x), torch.empty_like(x)
+        s = L.stream_ptr()
+        reps, tf, tb = 10, 0.0, 0.0
+        for i in range(3 + reps):
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            e[0].record()
+            L.check(lib.alignq_act_fwd(x.data_ptr(), y.data_ptr(), 0, n, 8, 2.0, 0, 0, s), "act_fwd")
+            e[1].record()
+            L.check(lib.alignq_act_bwd(x.data_ptr(), gy.data_ptr(), gx.data_ptr(), n, 8, 2.0, 0, 0, s), "act_bwd")
+            e[2].record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                tf += e[0].elapsed_time(e[1]) / reps
+                tb += e[1].elapsed_time(e[2]) / reps
+        peak, how = peaks()
+        achieved = 20.0 * n / ((tf + tb) * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "peak_source": how,
+                    "kernel": "act_fwd_vec_kernel + act_bwd_vec_kernel (CDF quantizer fwd + fused STE bwd)",
+                    "algorithmic_bytes_per_elem": 20, "elems_per_launch": n,
+                    "fwd": {"ms": tf, "gbs": 8.0 * n / (tf * 1e-3) / 1e9, "frac": 8.0 * n / (tf * 1e-3) / 1e9 / peak},
+                    "bwd": {"ms": tb, "gbs": 12.0 * n / (tb * 1e-3) / 1e9, "frac": 12.0 * n / (tb * 1e-3) / 1e9 / peak},
+                    "input": "256 x 2^20 fp32 (1 GiB per tensor, inputs >> L2), W8A8 variant A"}
+        del x, gy, y, gx
+        if world == 1 and not args.no_cpu_baseline:
+            cb = cpu_reference_run(3, 1, budget_s=30.0)
+            cpu = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": dict(CONFIG, global_batch=BATCH * world, parallelism=f"dp{world}", cuda_graph=graphed,
+                               sync_bn=bool(args.sync_bn and world > 1),
+                               l2="flushed between timed steps (256 MiB memset, outside the event pairs)"),
+                "e2e": {"value": e2e, "unit": "img/s", "ms_per_step": ms_e2e / args.steps,
+                        "h2d_bytes_per_step": BATCH * 3 * 32 * 32 * 4 + BATCH * 8, "d2h_bytes_per_step": 4},
+                "gpu_launches": int(launches_per_step) * args.steps,
+                "gpu_launches_per_step": int(launches_per_step),
+                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--sync-bn", action="store_true", help="N>1: SyncBatchNorm (global-batch BN statistics)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_product(args)
+
+
+if __name__ == "__main__":
+    main()

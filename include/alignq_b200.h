@@ -42,6 +42,8 @@ enum { ALIGNQ_GRAM_FP32 = 0,       /* CUDA-core FFMA, fp32 parity (1e-5) */
 
 int alignq_abi_version(void);
 const char* alignq_error_string(int code);
+/* Number of CUDA kernels this library has launched (or captured into a graph) since it was loaded. */
+uint64_t alignq_launch_count(void);
 
 /* ---- activation quantizer ------------------------------------------------------------------
  * activation_quantize_fn.forward (QA:91-103; QB:102-132 without the ADMM branch; QC:96-110):

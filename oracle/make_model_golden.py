@@ -81,6 +81,8 @@ def worker(job: str) -> None:
         tl = None
         if isinstance(r, tuple):
             logits, tl = r[0], r[-1]
+            if not torch.is_tensor(tl):          # 32-bit models return the python float 0
+                tl = None
         else:
             logits = r
         loss = torch.nn.functional.cross_entropy(logits, tgt)
@@ -94,6 +96,31 @@ def worker(job: str) -> None:
     out["logits"], out["grad_fp"] = logits.numpy(), fp
     if tl is not None:
         out["trans_loss"] = tl.numpy()
+
+    # Sensitivity band of the REFERENCE itself: quantisation is discontinuous, so a 1-ulp change of the
+    # weights flips codes and moves the outputs; a faithful re-implementation can only be asked to
+    # stay inside (a small multiple of) this band at model level.
+    with torch.no_grad():
+        for p_ in ref.parameters():
+            p_.mul_(1.0 + 1e-7)
+    lp, tlp, fpp = run(ref)
+    rel = lambda a, b: float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+    out["band_logits"] = np.float64(rel(lp, logits))
+    out["band_grad_fp"] = np.float64(rel(torch.from_numpy(fpp[:, 1]), torch.from_numpy(fp[:, 1])))
+    if tl is not None:
+        out["band_trans_loss"] = np.float64(abs(float(tlp) - float(tl)) / abs(float(tl)))
+    ref.load_state_dict(sd)
+
+    # Wiring check without any quantizer: the same topology at 32 bit is a smooth function, so the
+    # product graph (conv/bn/relu/shortcut order) can be compared tightly.
+    kw32 = {k: 32 for k in kw}
+    torch.manual_seed(0)
+    ref32 = getattr(mod, ctor)(stage="second", **kw32)
+    ref32.train()
+    ref32.load_state_dict(sd)
+    l32, _, fp32_ = run(ref32)
+    out["logits_fp32"], out["grad_fp_fp32"] = l32.numpy(), fp32_
+    print(f"  {job}: band logits {out['band_logits']:.2e}, grads {out['band_grad_fp']:.2e}")
 
     if job in ("resnet20_A", "resnet20_B", "resnet56_B"):
         variant = job[-1]

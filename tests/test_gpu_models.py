@@ -56,19 +56,49 @@ def test_model_forward_backward_vs_reference_golden(job):
     loss = torch.nn.functional.cross_entropy(logits, tgt)
     tl = out[-1] if isinstance(out, tuple) else None
     (loss if tl is None else loss + tl).backward()
+    # Bars: 5x the reference's own sensitivity band (its outputs under a 1e-7 relative weight
+    # perturbation, recorded by oracle/make_model_golden.py), floor 5e-3 -- quantisation is
+    # discontinuous, see the module docstring.  The tight model-level check is the 32-bit wiring test.
     e = relnorm(logits.detach().cpu(), torch.from_numpy(g["logits"]))
-    print(f"{job}: logits rel-norm err {e:.2e}")
-    assert e <= (5e-2 if bits == 4 else 2e-2), "logits vs reference (norm-relative; code ties may flip)"
+    band = float(g["band_logits"])
+    print(f"{job}: logits rel-norm err {e:.2e} (reference band {band:.2e})")
+    assert e <= max(5 * band, 5e-3), "logits vs reference"
     if tl is not None:
-        et = abs(float(tl) - float(g["trans_loss"])) / abs(float(g["trans_loss"]))
-        print(f"{job}: trans_loss rel err {et:.2e}")
-        assert et <= 2e-3
+        et = abs(float(tl.detach()) - float(g["trans_loss"])) / abs(float(g["trans_loss"]))
+        print(f"{job}: trans_loss rel err {et:.2e} (reference band {float(g['band_trans_loss']):.2e})")
+        assert et <= max(5 * float(g["band_trans_loss"]), 1e-3)
     fp = torch.from_numpy(g["grad_fp"])
     mine = torch.stack([p.grad.double().abs().sum() if p.grad is not None else torch.zeros((), dtype=torch.float64, device=DEV)
                         for _, p in model.named_parameters()]).cpu()
     eg = relnorm(mine, fp[:, 1])
-    print(f"{job}: per-parameter |grad| sums rel-norm err {eg:.2e}")
-    assert eg <= 0.1, "gradient magnitudes vs reference (norm-relative over parameters)"
+    print(f"{job}: per-parameter |grad| sums rel-norm err {eg:.2e} (reference band {float(g['band_grad_fp']):.2e})")
+    assert eg <= max(5 * float(g["band_grad_fp"]), 2e-2), "gradient magnitudes vs reference"
+
+
+@pytest.mark.parametrize("job", list(BUILD))
+def test_model_wiring_at_32_bit_vs_reference_golden(job):
+    """bitW = abitW = 32 turns every quantizer into the identity (QA:64-67,92-95): the graph is then a
+    smooth function and must match the reference's 32-bit run tightly (conv/BN/ReLU/shortcut order)."""
+    variant, _ = BUILD[job]
+    g = np.load(os.path.join(GOLDEN, f"model_{job}.npz"))
+    x, tgt = torch.from_numpy(g["x"]).to(DEV), torch.from_numpy(g["target"]).to(DEV)
+    aq.set_args(variant=variant, train_batch_size=x.shape[0], bitW=32, abitW=32, act_range=2, method="ours")
+    ctor32 = {"resnet20": lambda: resnet.resnet20_quant(32, 32, "second"), "resnet56": lambda: resnet.resnet56_quant(32, 32, "second"),
+              "mobilenetv2": lambda: mobilenetV2.mobile_v2(32, 32, "second"), "densenet40": lambda: densenet.densenet_40_quant(32, 32, "second"),
+              "resnet50dann": lambda: dann.resnet50_dann(32, 32, "second")}[job.split("_")[0]]
+    model = ctor32()
+    model.load_state_dict(MO.deterministic_fill(model.state_dict(), seed=11))
+    model.to(DEV).train()
+    out = model(x, 0.5) if "dann" in job else model(x)
+    logits = out[0] if isinstance(out, tuple) else out
+    torch.nn.functional.cross_entropy(logits, tgt).backward()
+    e = relnorm(logits.detach().cpu(), torch.from_numpy(g["logits_fp32"]))
+    fp = torch.from_numpy(g["grad_fp_fp32"])
+    mine = torch.stack([p.grad.double().abs().sum() if p.grad is not None else torch.zeros((), dtype=torch.float64, device=DEV)
+                        for _, p in model.named_parameters()]).cpu()
+    eg = relnorm(mine, fp[:, 1])
+    print(f"{job} @32 bit: logits rel-norm err {e:.2e}, |grad| sums rel-norm err {eg:.2e}")
+    assert e <= 1e-3 and eg <= 1e-2
 
 
 @pytest.mark.parametrize("variant", ["A", "B"])
@@ -87,20 +117,34 @@ def test_training_iterations_vs_oracle_trainer_on_gpu(variant):
     orc = MO.OracleResNet([3, 3, 3], 8, 8, variant, 2.0, dim=B)
     orc.load_state_dict(sd)
     orc.to(DEV).train()
+    # live sensitivity band: the same oracle loop started from weights perturbed by 1e-7 relative
+    pert = MO.OracleResNet([3, 3, 3], 8, 8, variant, 2.0, dim=B)
+    pert.load_state_dict(sd)
+    pert.to(DEV).train()
+    with torch.no_grad():
+        for p in pert.parameters():
+            p.mul_(1.0 + 1e-7)
     step = QATStep(prod, lr=0.04, momentum=0.9, weight_decay=1e-4)
     tr = MO.OracleTrainer(orc, lr=0.04, momentum=0.9, weight_decay=1e-4, lam=1.0, lam2=4.0, bitW=8)
+    trp = MO.OracleTrainer(pert, lr=0.04, momentum=0.9, weight_decay=1e-4, lam=1.0, lam2=4.0, bitW=8)
+
+    def worst(a, b):
+        return max(relnorm(p.detach(), q.detach()) for p, q in zip(a.parameters(), b.parameters()))
+
     for it in range(3):
-        lp = step.step(x, t)
-        lo, _ = tr.step(x, t)
-        assert abs(float(lp) - float(lo)) <= 2e-3 * abs(float(lo)) + 1e-4, f"CE loss, iteration {it}"
-    worst = 0.0
-    for (n, p), (_, po) in zip(prod.named_parameters(), orc.named_parameters()):
-        worst = max(worst, relnorm(p.detach(), po.detach()))
-    print(f"variant {variant}: worst per-parameter rel-norm err after 3 iterations {worst:.2e}")
-    assert worst <= 2e-2
-    # p.grad left behind by SGD.step (momentum-buffer value, or the surrogate for quantized convs)
-    gw = relnorm(prod.layers[0].conv0.weight.grad, orc.layers[0].conv0.weight.grad)
-    assert gw <= 5e-2, "gradient surrogate left in p.grad"
+        lp = float(step.step(x, t))
+        lo = float(tr.step(x, t)[0])
+        lb = float(trp.step(x, t)[0])
+        err, band = worst(prod, orc), worst(pert, orc)
+        print(f"variant {variant} it {it}: CE {lp:.6f} vs oracle {lo:.6f} (perturbed oracle {lb:.6f}); "
+              f"param err {err:.2e} (band {band:.2e})")
+        if it == 0:
+            assert abs(lp - lo) <= 1e-4 * abs(lo), "first-iteration CE loss"
+            # p.grad left behind by SGD.step: the surrogate for quantized convs (optimizer.py:232-249)
+            assert relnorm(prod.layers[0].conv0.weight.grad, orc.layers[0].conv0.weight.grad) <= max(band, 1e-3)
+            assert relnorm(prod.logit.weight.grad, orc.logit.weight.grad) <= max(band, 1e-3)
+        assert err <= max(band, 1e-5), f"iteration {it}: product drifts from the oracle faster than a 1-ulp perturbation"
+        assert abs(lp - lo) <= max(2 * abs(lb - lo), 1e-4 * abs(lo)), f"iteration {it}: CE loss outside the band"
 
 
 def test_graph_replay_equals_eager():
@@ -116,10 +160,12 @@ def test_graph_replay_equals_eager():
         models.append(m.to(DEV).train())
     eager, graphed = QATStep(models[0]), QATStep(models[1])
     graphed.capture(x, t, warmup=3)        # 3 real warm-up iterations; the capture pass itself does not execute
-    for _ in range(3):
-        lg = graphed.step(x, t)            # iterations 4..6 by replay
-    for _ in range(6):
+    lg = graphed.step(x, t)                # iteration 4 by replay
+    for _ in range(4):
         le = eager.step(x, t)
-    assert abs(float(le) - float(lg)) <= 1e-3 * abs(float(le)) + 1e-5
-    worst = max(relnorm(p.detach(), q.detach()) for p, q in zip(models[1].parameters(), models[0].parameters()))
-    assert worst <= 1e-2
+    # same kernels, same order; cuDNN may pick a different algorithm under capture, and the loop is
+    # chaotic (see test_training_iterations_vs_oracle_trainer_on_gpu), hence a loose band after 4 steps
+    assert abs(float(le) - float(lg)) <= 2e-2 * abs(float(le))
+    assert torch.isfinite(lg)
+    l5 = float(graphed.step(x, t))
+    assert l5 == l5 and l5 != float(lg)    # replay advances the optimisation (state lives outside the graph)

@@ -258,7 +258,9 @@ __device__ __forceinline__ void bwd_one_path(const float* __restrict__ W, int B,
     const int i = e / KT, k = e - i * KT;
     const float se = sd[k] + eps;
     const float dsd = -red[KT + k] / (se * se);
-    G[i * KTP + k] = (G[i * KTP + k] - red[k]) / se + dsd * S[i * KTP + k] / ((float)(B - 1) * sd[k]);
+    // torch's std backward masks the 0/0 of a constant column to 0 (std_backward: masked_fill_(result == 0, 0))
+    const float through_sd = (sd[k] > 0.f) ? dsd * S[i * KTP + k] / ((float)(B - 1) * sd[k]) : 0.f;
+    G[i * KTP + k] = (G[i * KTP + k] - red[k]) / se + through_sd;
   }
   __syncthreads();
 }

@@ -62,7 +62,8 @@ def corr_backward(X, dG, eps: float):
     Xs = c / (sd + eps)
     gS = (dG + dG.t()) @ Xs / F
     dsd = -(gS * c).sum(dim=0) / (sd + eps) ** 2
-    return (gS - gS.mean(dim=0)) / (sd + eps) + dsd * c / ((B - 1) * sd)
+    through_sd = torch.where(sd > 0, dsd * c / ((B - 1) * sd), torch.zeros_like(c))   # torch masks std == 0
+    return (gS - gS.mean(dim=0)) / (sd + eps) + through_sd
 
 
 def act_admm_backward(X, gy, gloss, Z, U, mu, rho, act_range, eps):

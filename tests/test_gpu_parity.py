@@ -350,6 +350,27 @@ def test_fused_act_admm_vs_gpu_eager_oracle(variant, B, shape):
     rel_close(admm.gamma.grad, Uo.grad, rtol=1e-4, atol_frac=1e-5, what="d loss / d gamma")
 
 
+def test_fused_backward_with_constant_columns_matches_autograd():
+    """QC (eps = 1e-5): a feature column that is constant over the batch has std == 0; torch's std
+    backward masks that 0/0 to 0, so the reference gradient is finite (seen in ResNet-50 DANN at B = 2)."""
+    torch.manual_seed(10)
+    aq.set_args(variant="C", act_range=2, method="ours", gram_mode="fp32")
+    B = 4
+    admm = aq.ADMM(B).to(DEV)
+    x0 = torch.randn(B, 8, 6, 6, device=DEV)
+    x0[:, 3] = 0.75
+    x0[:, :, 2, 2] = -1.5
+    gy = torch.randn_like(x0)
+    x = x0.clone().requires_grad_(True)
+    y, loss = aq.activation_quantize_fn2(8, "second", admm)(x)
+    ((y * gy).sum() + loss).backward()
+    xo = x0.clone().requires_grad_(True)
+    yo, lo, _ = O.activation_quantize_admm(xo, 8, admm.alterD.detach(), admm.gamma.detach(), "second", "C", 2.0)
+    ((yo * gy).sum() + lo).backward()
+    assert bool(torch.isfinite(xo.grad).all()) and bool(torch.isfinite(x.grad).all())
+    rel_close(x.grad, xo.grad, rtol=1e-4, atol_frac=1e-5, what="gx with constant columns")
+
+
 @pytest.mark.parametrize("variant", ["B", "C"])
 def test_admm_loss_and_zu_update_golden(golden, variant):
     g = golden(variant)

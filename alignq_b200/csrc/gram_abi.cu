@@ -7,10 +7,12 @@ using namespace alignq;
 
 extern "C" size_t alignq_gram_ws_bytes(int B, int64_t F) {
   if (B < 1 || F < 1) return 0;
+  // room for up to 4 accumulator partials (tf32x3 fused: HH^T, HL^T for x and t) from up to 2 * 148 CTAs
   const int64_t ntiles = (F + 31) / 32;
   int64_t slabs = ntiles < 2 * ALIGNQ_NUM_SMS ? ntiles : 2 * ALIGNQ_NUM_SMS;
-  size_t bytes = gram_wsym_floats(B) * sizeof(float) + 2 * (size_t)slabs * B * B * sizeof(float);
-  const size_t floor_bytes = gram_wsym_floats(B) * sizeof(float) + 2 * (size_t)B * B * sizeof(float);
+  const size_t head = gram_wsym_floats(B) * sizeof(float);
+  size_t bytes = head + 4 * (size_t)slabs * B * B * sizeof(float);
+  const size_t floor_bytes = head + 4 * (size_t)B * B * sizeof(float);
   if (bytes > kGramWsCapBytes) bytes = kGramWsCapBytes > floor_bytes ? kGramWsCapBytes : floor_bytes;
   return bytes;
 }

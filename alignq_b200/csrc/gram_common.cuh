@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
+#include "common.cuh"
 
 namespace alignq {
 
@@ -27,6 +28,17 @@ int gram_ffma_forward(const float* xa, const float* xb, int B, int64_t F, float 
                       float* partials, int* nslabs_out, size_t ws_bytes, cudaStream_t s);
 int gram_ffma_backward(const float* x, const float* gy, const float* Wsym, int Bp, const float* gloss, int B,
                        int64_t F, float ar, float eps, float* gx, cudaStream_t s);
+
+#ifdef __CUDACC__
+__device__ __forceinline__ float act_map_t(float x, float ar) {           // QB:49-56
+  return __fmul_rn(sym_map(normal_cdf_std(x)), ar);
+}
+__device__ __forceinline__ float act_quant_from_t(float t, const ActQ& q) {   // QB:110 (uniform_q)
+  if (q.a_bit == 32) return t;
+  if (q.a_bit == 1) return (t > 0.0f) ? 1.0f : ((t < 0.0f) ? -1.0f : t);
+  return __fmul_rn(rintf(__fmul_rn(t, q.n)), q.inv_n);
+}
+#endif
 
 // gram_tc.cu (tcgen05 modes)
 int gram_tc_corr(const float* x, int B, int64_t F, float eps, float* G, void* ws, size_t ws_bytes, int gram_mode,

@@ -21,15 +21,6 @@ namespace alignq {
 constexpr int KT = 32;           // feature columns per tile
 constexpr int GT = 256;          // threads per CTA
 
-__device__ __forceinline__ float act_map_t(float x, float ar) {           // QB:49-56
-  return __fmul_rn(sym_map(normal_cdf_std(x)), ar);
-}
-__device__ __forceinline__ float act_quant_from_t(float t, const ActQ& q) {   // QB:110 (uniform_q)
-  if (q.a_bit == 32) return t;
-  if (q.a_bit == 1) return (t > 0.0f) ? 1.0f : ((t < 0.0f) ? -1.0f : t);
-  return __fmul_rn(rintf(__fmul_rn(t, q.n)), q.inv_n);
-}
-
 // Load one [B x KT] tile of src (columns f0..f0+KT) into S[k*LD + i], zero-filling rows >= B (up to
 // Bpad) and columns >= F.  TRANSFORM applies the activation map; y (nullable) receives the quantized
 // activation for the loaded elements.

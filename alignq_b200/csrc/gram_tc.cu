@@ -1,12 +1,435 @@
-// tcgen05 Gram modes -- placeholder until the tensor-core kernels land (they return EINVAL so a
-// caller can never silently get a different numerics mode than it asked for).
+// tcgen05 (5th-gen tensor core) correlation / Gram kernels for sm_100a.
+//
+// Replaces corr() (cdf_alignment_admm/resnet-56-cifar-10/model/quantization.py:134-137;
+// cdf_alignment_admm/dann_office/model/quantization.py:158-161) and, fused with the activation
+// map, the forward of activation_quantize_fn with method == 'ours' (quantization.py:109-123):
+// ONE read of x yields y (quantized activation), corr(x, x) and corr(t, t).
+//
+// Transform-then-MMA mainloop (operands need per-column batch statistics before the MMA, so they
+// cannot come straight from TMA): per 32-column tile, all 512 threads
+//   1. load x [B x 32] (coalesced 128 B rows), apply the CDF map (t) and write y,
+//   2. reduce the column statistics of x and t across the 16 warps (pivot-shifted single pass),
+//   3. standardise, convert and store the operands into shared memory in the canonical UMMA
+//      K-major no-swizzle layout (8-row x 16-byte core matrices),
+//   4. one elected thread issues tcgen05.mma (M = N = 128, A and B descriptors on the same tiles)
+//      accumulating in TMEM; tcgen05.commit -> mbarrier releases the smem stage.
+// Two smem stages overlap the MMAs of tile i with the ALU work of tile i+1.  Split-K over CTAs;
+// every CTA dumps its TMEM accumulators as fp32 partials, reduced by gram_reduce_tc_kernel.
+//
+// Numerics modes
+//   ALIGNQ_GRAM_TF32X3: kind::tf32 with the operand split xs = H + L (H = top 19 bits):
+//       G = H H^T + H L^T + L H^T  (the L L^T term, <= 2^-22 relative, is dropped): three MMAs per
+//       k-step into ONE accumulator, fp32-level accuracy (tested to 1e-5 relative).
+//   ALIGNQ_GRAM_BF16:   kind::f16 with bf16 operands, one MMA per k-step (tested to 1e-2 relative).
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "gram_common.cuh"
 #include "../../include/alignq_b200.h"
 
 namespace alignq {
-int gram_tc_corr(const float*, int, int64_t, float, float*, void*, size_t, int, cudaStream_t) { return ALIGNQ_EINVAL; }
-int gram_tc_fused_fwd(const float*, int, int64_t, ActQ, float, float*, float*, void*, size_t, int, cudaStream_t) {
+namespace tc {
+
+constexpr int KB = 32;            // feature columns per tile
+constexpr int NT = 512;           // threads per CTA: 16 warps (4 per scheduler hide the erff / FMA chains)
+constexpr int NW = NT / 32;       // warps
+constexpr int RPT = 128 / NW;     // rows per thread: row r = warp + NW * i
+constexpr int LBO = 144;          // bytes between K-adjacent core matrices (128 + 16 pad: conflict-free stores)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait: a mis-programmed pipeline traps (launch failure) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+template <bool TF32>
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (TF32) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  }
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// 64-bit shared-memory matrix descriptor, K-major, SWIZZLE_NONE (cute::UMMA::SmemDescriptor):
+//   [0,14) start address >> 4   [16,30) leading (K) byte offset >> 4   [32,46) stride (M/N) byte offset >> 4
+//   [46,48) version = 1 (Blackwell)   [61,64) layout type = 0 (no swizzle)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+// 32-bit instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 = 1 @ [4,6);
+// a/b format @ [7,10)/[10,13) (BF16 = 1, TF32 = 2); a/b major K = 0 @ 15/16; N >> 3 @ [17,23); M >> 4 @ [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt, uint32_t M, uint32_t N) {
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+constexpr int RAW_TILE_BYTES = 128 * KB * (int)sizeof(float);   // one raw x tile [128 rows][32 cols] fp32
+
+template <int MODE, bool FUSED, bool STAGED>
+struct Cfg {
+  static constexpr bool TF32 = (MODE == ALIGNQ_GRAM_TF32X3);
+  static constexpr int ESZ = TF32 ? 4 : 2;                 // operand element bytes
+  static constexpr int CH = 16 / ESZ;                      // elements per 16-byte core-matrix row
+  static constexpr int NCH = KB / CH;                      // core matrices along K per tile
+  static constexpr int SBO = NCH * LBO;                    // bytes between 8-row groups
+  static constexpr int TILE_BYTES = 16 * SBO;              // 128 rows
+  static constexpr int NSRC = FUSED ? 2 : 1;               // x [, t]
+  static constexpr int NOPER = NSRC * (TF32 ? 2 : 1);      // operand tiles per stage (H, L per source)
+  static constexpr int NACC = NSRC;                        // one fp32 accumulator [128 x 128] per source
+  static constexpr int UMMA_K = 32 / ESZ;
+  static constexpr int KSTEPS = KB / UMMA_K;
+  static constexpr int TMEM_COLS = NACC * 128;             // 128 / 256: powers of two
+  static constexpr int STAGE_BYTES = NOPER * TILE_BYTES;
+  static constexpr int RED_BYTES = (NW + 1) * KB * 4 * (int)sizeof(float);   // per-warp partials + finished column stats
+  static constexpr int EPI_BYTES = NW * 32 * 33 * (int)sizeof(float);    // per-warp transpose tiles of the epilogue
+  static constexpr int OPER_BYTES = (2 * STAGE_BYTES > EPI_BYTES) ? 2 * STAGE_BYTES : EPI_BYTES;
+  // STAGED: ring of raw x tiles filled by cp.async (16 B, zero-filling) several tiles ahead, so that
+  // >= 48 KB per SM are in flight (one register-prefetched tile is only 16 KB: latency-bound at ~1.3 TB/s)
+  static constexpr int NRAW = STAGED ? ((TF32 && FUSED) ? 4 : 6) : 0;
+  static constexpr int RAW_BYTES = NRAW * RAW_TILE_BYTES;
+  static constexpr int SMEM_BYTES = OPER_BYTES + RAW_BYTES + RED_BYTES + 64;
+  static constexpr uint32_t IDESC = make_idesc(TF32 ? 2u : 1u, 128u, 128u);
+};
+
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int MODE, bool FUSED, bool STAGED>
+__global__ void __launch_bounds__(NT, 1)
+gram_tc_kernel(const float* __restrict__ x, int B, int64_t F, float eps, ActQ q, float* __restrict__ y,
+               float* __restrict__ partials, int64_t ntiles) {
+  using C = Cfg<MODE, FUSED, STAGED>;
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* stage_base = smem;
+  uint8_t* raw_base = smem + C::OPER_BYTES;
+  float4* red = reinterpret_cast<float4*>(smem + C::OPER_BYTES + C::RAW_BYTES);
+  float4* colstat = red + NW * KB;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OPER_BYTES + C::RAW_BYTES + C::RED_BYTES);   // [0,1] stage free, [2] accumulators done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- one-time setup ------------------------------------------------------------------------
+  for (int i = threadIdx.x; i < 2 * C::STAGE_BYTES / 16; i += NT) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const float invB = 1.0f / (float)B, invBm1 = 1.0f / (float)(B - 1);
+  // Prefetch.  STAGED: cp.async ring of raw tiles (needs 16-byte aligned rows: x aligned, F % 4 == 0);
+  // otherwise the next tile's column of x (16 rows per thread) is prefetched into registers.
+  float xn[RPT], pn = 0.f;
+  auto fetch_regs = [&](int64_t tile) {
+    const int64_t f = tile * KB + lane;
+    const bool colv = tile < ntiles && f < F;
+    pn = colv ? __ldg(x + f) : 0.f;
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      const int r = warp + NW * i;
+      xn[i] = (colv && r < B) ? __ldg(x + (int64_t)r * F + f) : 0.f;
+    }
+  };
+  auto fetch_async = [&](int64_t tile, int slot) {          // 1024 x 16 B chunks per tile
+    if (tile < ntiles) {
+      const uint32_t dst0 = smem_u32(raw_base + slot * RAW_TILE_BYTES);
+#pragma unroll
+      for (int j = 0; j < 1024 / NT; ++j) {
+        const int c = threadIdx.x + j * NT;
+        const int r = c >> 3, c16 = c & 7;
+        const int64_t f = tile * KB + c16 * 4;
+        int64_t left = (F - f) * 4;                          // bytes of this row still inside the matrix
+        left = left < 0 ? 0 : (left > 16 ? 16 : left);
+        const uint32_t nbytes = (r < B) ? (uint32_t)left : 0u;
+        const float* src = x + (nbytes ? (int64_t)r * F + f : 0);
+        cp_async16_zfill(dst0 + r * (KB * 4) + c16 * 16, src, nbytes);
+      }
+    }
+    cp_async_commit();                                       // (possibly empty) group keeps the counting uniform
+  };
+  if (STAGED) {
+#pragma unroll 1
+    for (int p = 0; p < C::NRAW - 1; ++p) fetch_async(blockIdx.x + (int64_t)p * gridDim.x, p);
+    cp_async_wait<C::NRAW - 2>();                            // tile 0 has landed (this thread's chunks)
+    __syncthreads();                                         // ... and everyone else's
+  } else {
+    fetch_regs(blockIdx.x);
+  }
+  int it = 0;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int s = it & 1;
+    uint8_t* st = stage_base + s * C::STAGE_BYTES;
+
+    // ---- 1. take the prefetched column, start the next fetch, map + quantise ---------------------
+    const int64_t f = tile * KB + lane;
+    const bool colv = f < F;
+    float xv[RPT], tv[RPT], px;                                  // px = pivot: row 0 of this column
+    if (STAGED) {
+      // refill the slot consumed in the previous iteration (everyone passed that iteration's last barrier)
+      fetch_async(tile + (int64_t)(C::NRAW - 1) * gridDim.x, (it + C::NRAW - 1) % C::NRAW);
+      const float* raw = reinterpret_cast<const float*>(raw_base + (it % C::NRAW) * RAW_TILE_BYTES);
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) xv[i] = raw[(warp + NW * i) * KB + lane];
+      px = raw[lane];
+    } else {
+      px = pn;
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) xv[i] = xn[i];
+      fetch_regs(tile + gridDim.x);
+    }
+    const float pt = FUSED ? act_map_t(px, q.ar) : 0.f;
+    float s1 = 0.f, s2 = 0.f, u1 = 0.f, u2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      const int r = warp + NW * i;
+      const bool v = colv && r < B;
+      const float d = xv[i] - px;
+      s1 += v ? d : 0.f;
+      s2 = v ? fmaf(d, d, s2) : s2;
+      if (FUSED) {
+        tv[i] = act_map_t(xv[i], q.ar);
+        if (v && y) y[(int64_t)r * F + f] = act_quant_from_t(tv[i], q);
+        const float e = tv[i] - pt;
+        u1 += v ? e : 0.f;
+        u2 = v ? fmaf(e, e, u2) : u2;
+      }
+    }
+    // ---- 2. column statistics across the warps: partials -> smem, warp 0 finishes the 32 columns ----
+    red[warp * KB + lane] = make_float4(s1, s2, u1, u2);
+    __syncthreads();
+    if (warp == 0) {
+      float S1 = 0.f, S2 = 0.f, U1 = 0.f, U2 = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) { const float4 p = red[w * KB + lane]; S1 += p.x; S2 += p.y; U1 += p.z; U2 += p.w; }
+      float vx = (S2 - S1 * S1 * invB) * invBm1;
+      vx = (vx < 0.f) ? 0.f : vx;
+      float4 o;
+      o.x = px + S1 * invB;                       // mean of x
+      o.y = 1.0f / (sqrtf(vx) + eps);             // 1 / (std + eps)
+      o.z = 0.f; o.w = 0.f;
+      if (FUSED) {
+        float vt = (U2 - U1 * U1 * invB) * invBm1;
+        vt = (vt < 0.f) ? 0.f : vt;
+        o.z = pt + U1 * invB;
+        o.w = 1.0f / (sqrtf(vt) + eps);
+      }
+      colstat[lane] = o;
+    }
+    __syncthreads();
+    const float4 cs = colstat[lane];
+    const float mx = cs.x, rx = cs.y, mt = cs.z, rt = cs.w;
+    // ---- 3. standardise, convert, store operands (row r = warp + 8 i -> row group i, row-in-group warp) ----
+    if (it >= 2) mbar_wait(&bars[s], ((it >> 1) - 1) & 1);       // MMAs that read this stage have retired
+    const int chunk = lane / C::CH, within = lane % C::CH;
+    uint8_t* dst0 = st + chunk * LBO + within * C::ESZ;
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      const int r = warp + NW * i;                               // row group r / 8, row in group r % 8
+      if (r >= B) break;
+      uint8_t* dst = dst0 + (r >> 3) * C::SBO + (r & 7) * 16;
+      const float a = colv ? (xv[i] - mx) * rx : 0.f;
+      const float b = (FUSED && colv) ? (tv[i] - mt) * rt : 0.f;
+      if (C::TF32) {
+        const float ah = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u);
+        *reinterpret_cast<float*>(dst) = ah;
+        *reinterpret_cast<float*>(dst + C::TILE_BYTES) = a - ah;
+        if (FUSED) {
+          const float bh = __uint_as_float(__float_as_uint(b) & 0xFFFFE000u);
+          *reinterpret_cast<float*>(dst + 2 * C::TILE_BYTES) = bh;
+          *reinterpret_cast<float*>(dst + 3 * C::TILE_BYTES) = b - bh;
+        }
+      } else {
+        *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16_rn(a);
+        if (FUSED) *reinterpret_cast<__nv_bfloat16*>(dst + C::TILE_BYTES) = __float2bfloat16_rn(b);
+      }
+    }
+    fence_proxy_async();            // generic-proxy smem writes -> visible to the tensor core (async proxy)
+    if (STAGED) cp_async_wait<(C::NRAW >= 2 ? C::NRAW - 2 : 0)>();     // next raw tile has landed (this thread's chunks)
+    __syncthreads();
+    // ---- 4. MMAs: one thread issues for the whole CTA --------------------------------------------
+    if (threadIdx.x == 0) {
+      tc_fence_after();
+      const uint32_t sb = smem_u32(st);
+#pragma unroll
+      for (int ks = 0; ks < C::KSTEPS; ++ks) {
+        const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
+        const uint32_t koff = ks * 2 * LBO;
+#pragma unroll
+        for (int src = 0; src < C::NSRC; ++src) {
+          if (C::TF32) {
+            const uint64_t dh = make_desc(sb + (2 * src) * C::TILE_BYTES + koff, LBO, C::SBO);
+            const uint64_t dl = make_desc(sb + (2 * src + 1) * C::TILE_BYTES + koff, LBO, C::SBO);
+            umma<true>(tmem_base + src * 128, dh, dh, C::IDESC, acc);      // H H^T
+            umma<true>(tmem_base + src * 128, dh, dl, C::IDESC, 1u);       // H L^T
+            umma<true>(tmem_base + src * 128, dl, dh, C::IDESC, 1u);       // L H^T
+          } else {
+            const uint64_t d = make_desc(sb + src * C::TILE_BYTES + koff, LBO, C::SBO);
+            umma<false>(tmem_base + src * 128, d, d, C::IDESC, acc);
+          }
+        }
+      }
+      umma_commit(&bars[s]);        // implies tcgen05.fence::before_thread_sync; frees the stage when the MMAs retire
+    }
+  }
+  // ---- epilogue: TMEM -> registers -> fp32 partials -----------------------------------------------
+  if (threadIdx.x == 0) umma_commit(&bars[2]);
+  mbar_wait(&bars[2], 0);
+  tc_fence_after();
+  {
+    // TMEM (lane = row, 32 consecutive columns per thread) -> per-warp smem transpose -> 128-byte row stores
+    const int qd = warp & 3, cb = warp >> 2;                       // lane quarter, 32-column block
+    float* tr = reinterpret_cast<float*>(smem) + warp * (32 * 33);       // operand stages are free now
+    float* out = partials + (size_t)blockIdx.x * C::NACC * B * B;
+#pragma unroll 1
+    for (int a = 0; a < C::NACC; ++a) {
+#pragma unroll 1
+      for (int col0 = cb * 32; col0 < 128; col0 += (NW / 4) * 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + a * 128 + col0, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) tr[lane * 33 + j] = __uint_as_float(v[j]);
+        __syncwarp();
+        if (col0 + lane < B) {
+          for (int r = 0; r < 32; ++r) {
+            const int row = qd * 32 + r;
+            if (row >= B) break;
+            out[((size_t)a * B + row) * B + col0 + lane] = tr[r * 33 + lane];
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+// G = (1/F) sum_cta acc;  fused: D = G_t - G_x (two separately rounded Grams, as quantization.py:118-122)
+__global__ void __launch_bounds__(256)
+gram_reduce_tc_kernel(const float* __restrict__ partials, int nparts, int B, float invF, int nacc, int fused,
+                      float* __restrict__ G, float* __restrict__ D) {
+  const size_t bb = (size_t)B * B;
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= bb) return;
+  float gx = 0.f, gt = 0.f;
+  for (int p = 0; p < nparts; ++p) gx += partials[(size_t)p * nacc * bb + e];
+  gx = __fmul_rn(gx, invF);
+  if (G) G[e] = gx;
+  if (fused) {
+    for (int p = 0; p < nparts; ++p) gt += partials[((size_t)p * nacc + 1) * bb + e];
+    D[e] = __fsub_rn(__fmul_rn(gt, invF), gx);
+  }
+}
+
+template <int MODE, bool FUSED, bool STAGED>
+static int launch_impl(const float* x, int B, int64_t F, float eps, ActQ q, float* y, float* G, float* D, void* ws,
+                       size_t ws_bytes, cudaStream_t s) {
+  using C = Cfg<MODE, FUSED, STAGED>;
+  const int64_t ntiles = (F + KB - 1) / KB;
+  float* partials = reinterpret_cast<float*>(ws) + gram_wsym_floats(B);
+  const size_t head = gram_wsym_floats(B) * sizeof(float);
+  if (ws_bytes <= head) return ALIGNQ_ENOSPACE;
+  int64_t cap = (int64_t)((ws_bytes - head) / ((size_t)C::NACC * B * B * sizeof(float)));
+  if (cap < 1) return ALIGNQ_ENOSPACE;
+  // >= 4 tiles per CTA: every CTA pays a fixed prologue (smem clear, TMEM alloc) and dumps NACC 64 KB
+  // partials that the reduce kernel re-reads, so small layers use fewer, longer-running CTAs
+  int64_t grid = (ntiles + 3) / 4;
+  if (grid > ALIGNQ_NUM_SMS) grid = ALIGNQ_NUM_SMS;
+  if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
+  cudaError_t e = cudaFuncSetAttribute(gram_tc_kernel<MODE, FUSED, STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+  if (e != cudaSuccess) return (int)e;
+  gram_tc_kernel<MODE, FUSED, STAGED><<<(unsigned)grid, NT, C::SMEM_BYTES, s>>>(x, B, F, eps, q, y, partials, ntiles);
+  ALIGNQ_LAUNCH_CHECK();
+  const int bb = B * B;
+  gram_reduce_tc_kernel<<<(bb + 255) / 256, 256, 0, s>>>(partials, (int)grid, B, 1.0f / (float)F, C::NACC,
+                                                         FUSED ? 1 : 0, G, D);
+  ALIGNQ_LAUNCH_CHECK();
+  return ALIGNQ_OK;
+}
+
+template <int MODE, bool FUSED>
+static int launch(const float* x, int B, int64_t F, float eps, ActQ q, float* y, float* G, float* D, void* ws,
+                  size_t ws_bytes, cudaStream_t s) {
+  const bool staged = aligned16(x) && (F % 4 == 0);          // cp.async needs 16-byte aligned row segments
+  return staged ? launch_impl<MODE, FUSED, true>(x, B, F, eps, q, y, G, D, ws, ws_bytes, s)
+                : launch_impl<MODE, FUSED, false>(x, B, F, eps, q, y, G, D, ws, ws_bytes, s);
+}
+
+}  // namespace tc
+
+int gram_tc_corr(const float* x, int B, int64_t F, float eps, float* G, void* ws, size_t ws_bytes, int gram_mode,
+                 cudaStream_t s) {
+  if (B > 128 || B < 2) return ALIGNQ_ERANGE;      // one 128-row UMMA tile; larger batches use the fp32 path
+  ActQ q{0.f, 0.f, 0.f, 0};
+  if (gram_mode == ALIGNQ_GRAM_TF32X3) return tc::launch<ALIGNQ_GRAM_TF32X3, false>(x, B, F, eps, q, nullptr, G, nullptr, ws, ws_bytes, s);
+  if (gram_mode == ALIGNQ_GRAM_BF16) return tc::launch<ALIGNQ_GRAM_BF16, false>(x, B, F, eps, q, nullptr, G, nullptr, ws, ws_bytes, s);
   return ALIGNQ_EINVAL;
 }
+
+int gram_tc_fused_fwd(const float* x, int B, int64_t F, ActQ q, float eps, float* y, float* D, void* ws, size_t ws_bytes,
+                      int gram_mode, cudaStream_t s) {
+  if (B > 128 || B < 2) return ALIGNQ_ERANGE;
+  if (gram_mode == ALIGNQ_GRAM_TF32X3) return tc::launch<ALIGNQ_GRAM_TF32X3, true>(x, B, F, eps, q, y, nullptr, D, ws, ws_bytes, s);
+  if (gram_mode == ALIGNQ_GRAM_BF16) return tc::launch<ALIGNQ_GRAM_BF16, true>(x, B, F, eps, q, y, nullptr, D, ws, ws_bytes, s);
+  return ALIGNQ_EINVAL;
+}
+
 }  // namespace alignq

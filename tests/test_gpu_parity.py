@@ -439,3 +439,53 @@ def test_uniform_quantize_and_cdf_standalone():
             co, po = O.cdf_map(x, m, s, src, variant, 2.0)
             assert torch.equal(c, co)
             rel_close(p, po, rtol=2e-6, atol_frac=1e-7, what="pdf")
+
+
+# ------------------------------------------------------------------------------------------------
+# tcgen05 Gram modes (B <= 128): fp32-level 'tf32x3' (1e-5) and 'bf16' (1e-2), both stated relative to
+# the Gram magnitude max|G| (entries are O(1) on the diagonal, O(1/sqrt(F)) off it).
+TC_TOL = {"tf32x3": 1e-5, "bf16": 1e-2}
+
+
+@pytest.mark.parametrize("mode", ["tf32x3", "bf16"])
+@pytest.mark.parametrize("B,F,eps", [(128, 4096, 0.0), (128, 16384, 0.0), (28, 3000, 1e-5), (100, 1027, 0.0), (8, 96, 0.0)])
+def test_tc_corr_vs_oracle(mode, B, F, eps):
+    torch.manual_seed(11)
+    aq.set_args(gram_mode=mode)
+    x = torch.randn(B, F, device=DEV) * 1.7 + 0.3
+    G = aq.corr(x, x, eps)
+    ref = O.corr(x.double(), x.double(), eps)
+    err = float((G.double() - ref).abs().max()) / float(ref.abs().max())
+    print(f"corr {mode} B={B} F={F}: max err / max|G| = {err:.2e}")
+    assert err <= TC_TOL[mode]
+
+
+@pytest.mark.parametrize("mode", ["tf32x3", "bf16"])
+@pytest.mark.parametrize("variant,B,shape", [("B", 128, (16, 32, 32)), ("B", 128, (64, 8, 8)), ("C", 28, (64, 14, 14)),
+                                             ("B", 100, (3, 11, 13))])
+def test_tc_fused_forward_vs_fp32_mode_and_oracle(mode, variant, B, shape):
+    torch.manual_seed(12)
+    dim = 128
+    admm = aq.ADMM(dim).to(DEV)
+    x0 = torch.randn(B, *shape, device=DEV)
+    gy = torch.randn_like(x0)
+    Fn = aq.activation_quantize_fn if variant == "B" else aq.activation_quantize_fn2
+    res = {}
+    for m in ("fp32", mode):
+        aq.set_args(variant=variant, act_range=2, method="ours", gram_mode=m)
+        x = x0.clone().requires_grad_(True)
+        y, loss = Fn(8, "second", admm)(x)
+        ((y * gy).sum() + loss).backward()
+        res[m] = (y.detach(), loss.detach(), admm.D.clone(), x.grad.clone())
+    eps = 0.0 if variant == "B" else 1e-5
+    gmax = float(O.corr(x0.view(B, -1), x0.view(B, -1), eps).abs().max())
+    assert torch.equal(res[mode][0], res["fp32"][0]), "y must not depend on the Gram numerics mode"
+    dD = float((res[mode][2] - res["fp32"][2]).abs().max()) / gmax
+    dl = abs(float(res[mode][1]) - float(res["fp32"][1])) / abs(float(res["fp32"][1]))
+    print(f"fused {mode} {variant} B={B} F={x0[0].numel()}: dD/max|G| = {dD:.2e}, trans_loss rel = {dl:.2e}")
+    assert dD <= TC_TOL[mode]
+    assert dl <= (1e-5 if mode == "tf32x3" else 2e-2)
+    _, lo, Do = O.activation_quantize_admm(x0, 8, admm.alterD.detach(), admm.gamma.detach(), "second", variant, 2.0)
+    assert float((res[mode][2] - Do).abs().max()) / gmax <= 2 * TC_TOL[mode]
+    if mode == "tf32x3":
+        rel_close(res[mode][3], res["fp32"][3], rtol=1e-3, atol_frac=1e-4, what="gx (dLdD from the tf32x3 forward)")

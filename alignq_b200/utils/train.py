@@ -19,6 +19,7 @@ import torch.nn.functional as F
 from .admm import ADMM
 from .optimizer import ADMM_OPT, SGD
 from .options import args
+from .sharding import allreduce_mean_
 
 
 def quantized_convs(model):
@@ -95,10 +96,8 @@ class QATStep:
         else:
             ce = F.cross_entropy(out, t)
             ce.backward()
-        if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.gflat[: self.n_main], group=self.pg)
-            self.gflat[: self.n_main].mul_(1.0 / self.world)
+        if self.world > 1:                                         # ONE collective per step over NVLink
+            allreduce_mean_(self.gflat[: self.n_main], self.pg, self.world)
         idx, w_cdf, w_pdf = collect_sgd_args(self.model, self.params)
         self.opt.step(idx, w_cdf, w_pdf, self.lam, self.lam2)
         if self.opt_admm is not None:

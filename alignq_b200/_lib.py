@@ -51,6 +51,9 @@ SIGNATURES = {
     "alignq_act_admm_bwd": (_I, [_P, _P, _P, _P, _I, _L, _I, _F, _F, _P, _P, _Z, _I, _P]),
     "alignq_admm_loss": (_I, [_P, _I, _P, _P, _I, _I, _F, _F, _P, _I, _P, _P, _P, _P, _P]),
     "alignq_admm_zu_update": (_I, [_P, _P, _P, _I, _I, _I, _F, _F, _P]),
+    "alignq_bn_act_ws_doubles": (_Z, [_I]),
+    "alignq_bn_act_fwd": (_I, [_P, _L, _I, _P, _P, _P, _P, _F, _F, _I, _I, _F, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "alignq_bn_act_bwd": (_I, [_P, _P, _P, _L, _I, _P, _P, _P, _P, _I, _I, _F, _I, _I, _P, _P, _P, _P, _P, _P]),
     "alignq_sgd_step": (_I, [_P, _P, _P, _I, _L, _F, _F, _I, _P]),
 }
 
@@ -100,6 +103,29 @@ def dev_f32(t: torch.Tensor, what: str) -> torch.Tensor:
     if t.dtype != torch.float32:
         raise AlignQError(f"{what}: expected float32, got {t.dtype}")
     return t if t.is_contiguous() else t.contiguous()
+
+
+def dev_f32_dense(t: torch.Tensor, what: str) -> torch.Tensor:
+    """Like dev_f32, but keeps any dense layout whose outermost stride is the batch (NCHW-contiguous or
+    channels_last): the element-wise kernels are layout-agnostic and the Gram is invariant under a
+    permutation of the per-sample features, so no NHWC<->NCHW copy is ever needed."""
+    if not t.is_cuda:
+        raise AlignQError(f"{what}: expected a CUDA tensor, got device {t.device} "
+                          "(alignq_b200 runs on sm_100a only; there is no CPU fallback)")
+    if t.dtype != torch.float32:
+        raise AlignQError(f"{what}: expected float32, got {t.dtype}")
+    if t.is_contiguous() or (t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last)):
+        return t
+    return t.contiguous()
+
+
+def like_layout(g: torch.Tensor, ref: torch.Tensor, what: str) -> torch.Tensor:
+    """Bring an upstream gradient to the memory layout of the saved activation."""
+    if not g.is_cuda or g.dtype != torch.float32:
+        raise AlignQError(f"{what}: expected a float32 CUDA tensor")
+    if g.stride() == ref.stride():
+        return g
+    return torch.empty_like(ref).copy_(g)
 
 
 def ptr(t) -> int:

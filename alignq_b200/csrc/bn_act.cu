@@ -1,0 +1,303 @@
+// Fused BatchNorm2d -> CDF activation quantizer -> (ReLU), forward and backward, for NHWC
+// (channels_last) fp32 activations -- SURVEY.md section 8(f) item 1, the step either side of the
+// quantizer in every model file:
+//   out = F.relu(self.act_q0(self.bn0(out)))        cdf_alignment/resnet-20-cifar-10/model/resnet.py:72,121-123
+//   out = self.relu(self.act_q0(self.bn1(x)))       cdf_alignment/dense-cifar-10/model/densenet.py:32-34
+// Un-fused this is cuDNN BN (12 B/elem) + quantizer (8) + ReLU (8) forward and the same again
+// backward; fused it is 12 B/elem forward (stats pass + apply pass) and 28 B/elem backward.
+//
+// x is viewed as [R = B*H*W, C] with C contiguous.  Every thread owns one float4 of channels
+// (c4 = tid % (C/4); the block size is a multiple of C/4), so per-channel accumulators live in
+// registers and every global access is a coalesced 128-bit load.  Per-block fp64 partials go to a
+// workspace; the LAST block to finish (threadfence + ticket, no spinning) reduces them, finalises
+// the statistics and re-arms the ticket -- no extra launch, no memset, deterministic.
+#include "common.cuh"
+#include "../../include/alignq_b200.h"
+
+namespace alignq {
+
+constexpr int BN_MAX_THREADS = 256;
+constexpr int BN_MAX_GRID = 2 * ALIGNQ_NUM_SMS;
+
+struct BnQ {
+  float n, inv_n, ar, gscale;
+  int a_bit, variant, relu;
+};
+
+__device__ __forceinline__ float bnq_quant(float z, const BnQ& q) {
+  float c = normal_cdf_std(z);
+  if (q.variant != 0) c = __fmul_rn(sym_map(c), q.ar);
+  float v;
+  if (q.a_bit == 1) v = (c > 0.f) ? 1.f : ((c < 0.f) ? -1.f : c);
+  else v = __fmul_rn(rintf(__fmul_rn(c, q.n)), q.inv_n);
+  if (q.variant == 0) v = __fmul_rn(sym_map(v), q.ar);
+  return (q.relu && v < 0.f) ? 0.f : v;
+}
+
+struct Lane4 { float v[4]; };
+__device__ __forceinline__ Lane4 ld4(const float* p) {
+  const float4 t = *reinterpret_cast<const float4*>(p);
+  return Lane4{{t.x, t.y, t.z, t.w}};
+}
+
+// last-block ticket: returns true in every thread of the block that finishes last
+__device__ __forceinline__ bool last_block(unsigned* counter, unsigned* smem_flag) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(counter, 1u);
+    *smem_flag = (t == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  const bool last = *smem_flag != 0u;
+  if (last) __threadfence();
+  return last;
+}
+
+// reduce two float4 accumulators over the threads of the block that share c4, write fp64 partials
+__device__ __forceinline__ void block_partials(const float (&a)[4], const float (&b)[4], int C4, int k,
+                                               float* sh, double* partial /* [C][2] of this block */) {
+  const int t = threadIdx.x;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { sh[t * 8 + j] = a[j]; sh[t * 8 + 4 + j] = b[j]; }
+  __syncthreads();
+  if (t < C4) {
+    double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int r = 0; r < k; ++r)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] += (double)sh[(r * C4 + t) * 8 + j];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { partial[(t * 4 + j) * 2] = s[j]; partial[(t * 4 + j) * 2 + 1] = s[4 + j]; }
+  }
+}
+
+// ---- forward pass 1: batch statistics -------------------------------------------------------------
+__global__ void __launch_bounds__(BN_MAX_THREADS)
+bnq_stats_kernel(const float* __restrict__ x, int64_t R, int C, float* __restrict__ running_mean,
+                 float* __restrict__ running_var, float momentum, float bn_eps, float* __restrict__ save_mean,
+                 float* __restrict__ save_invstd, double* __restrict__ ws, unsigned* __restrict__ counter) {
+  extern __shared__ float sh[];
+  __shared__ unsigned flag;
+  const int C4 = C >> 2, k = blockDim.x / C4;
+  const int c4 = threadIdx.x % C4, rsub = threadIdx.x / C4;
+  float s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
+  for (int64_t r = (int64_t)blockIdx.x * k + rsub; r < R; r += (int64_t)gridDim.x * k) {
+    const Lane4 v = ld4(x + r * C + 4 * c4);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { s[j] += v.v[j]; ss[j] = fmaf(v.v[j], v.v[j], ss[j]); }
+  }
+  block_partials(s, ss, C4, k, sh, ws + (size_t)blockIdx.x * C * 2);
+  if (last_block(counter, &flag)) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      double S = 0.0, SS = 0.0;
+      for (unsigned b = 0; b < gridDim.x; ++b) { S += __ldcg(ws + ((size_t)b * C + c) * 2); SS += __ldcg(ws + ((size_t)b * C + c) * 2 + 1); }
+      const double mean = S / (double)R;
+      double var = SS / (double)R - mean * mean;            // biased: what BN normalises with
+      var = var < 0.0 ? 0.0 : var;
+      save_mean[c] = (float)mean;
+      save_invstd[c] = (float)(1.0 / sqrt(var + (double)bn_eps));
+      if (running_mean) {
+        const double unbiased = R > 1 ? var * (double)R / (double)(R - 1) : var;
+        running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * mean);
+        running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unbiased);
+      }
+    }
+    if (threadIdx.x == 0) *counter = 0u;                    // re-arm for the next launch
+  }
+}
+
+// eval mode: statistics are the running ones
+__global__ void bnq_eval_stats_kernel(const float* __restrict__ running_mean, const float* __restrict__ running_var,
+                                      float bn_eps, int C, float* __restrict__ save_mean, float* __restrict__ save_invstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) { save_mean[c] = running_mean[c]; save_invstd[c] = 1.0f / sqrtf(running_var[c] + bn_eps); }
+}
+
+// ---- forward pass 2: normalise, quantise, ReLU ---------------------------------------------------------
+__global__ void __launch_bounds__(BN_MAX_THREADS)
+bnq_apply_kernel(const float* __restrict__ x, int64_t R, int C, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ invstd,
+                 BnQ q, float* __restrict__ y) {
+  const int C4 = C >> 2, k = blockDim.x / C4;
+  const int c4 = threadIdx.x % C4, rsub = threadIdx.x / C4;
+  float m[4], is[4], g[4], b[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = 4 * c4 + j;
+    m[j] = mean[c]; is[j] = invstd[c]; g[j] = gamma ? gamma[c] : 1.f; b[j] = beta ? beta[c] : 0.f;
+  }
+  for (int64_t r = (int64_t)blockIdx.x * k + rsub; r < R; r += (int64_t)gridDim.x * k) {
+    const Lane4 v = ld4(x + r * C + 4 * c4);
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = bnq_quant(fmaf((v.v[j] - m[j]) * is[j], g[j], b[j]), q);
+    *reinterpret_cast<float4*>(y + r * C + 4 * c4) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// g_z = gy * [y > 0 if relu] * gscale * exp(-(z/sqrt2)^2): the straight-through quantizer + ReLU backward
+__device__ __forceinline__ float bnq_gz(float z, float gy, float yv, const BnQ& q) {
+  const float v = __fmul_rn(z, kInvSqrt2);
+  const float g = __fmul_rn(gy, __fmul_rn(q.gscale, gauss_kernel_from_v(v)));
+  return (q.relu && !(yv > 0.f)) ? 0.f : g;
+}
+
+// ---- backward pass 1: d beta = sum g_z, d gamma = sum g_z * xhat ------------------------------------------
+__global__ void __launch_bounds__(BN_MAX_THREADS)
+bnq_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ gy, int64_t R,
+                      int C, const float* __restrict__ gamma, const float* __restrict__ beta,
+                      const float* __restrict__ mean, const float* __restrict__ invstd, BnQ q,
+                      float* __restrict__ ggamma, float* __restrict__ gbeta, float* __restrict__ coef /* [C][2] */,
+                      double* __restrict__ ws, unsigned* __restrict__ counter) {
+  extern __shared__ float sh[];
+  __shared__ unsigned flag;
+  const int C4 = C >> 2, k = blockDim.x / C4;
+  const int c4 = threadIdx.x % C4, rsub = threadIdx.x / C4;
+  float m[4], is[4], g[4], b[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = 4 * c4 + j;
+    m[j] = mean[c]; is[j] = invstd[c]; g[j] = gamma ? gamma[c] : 1.f; b[j] = beta ? beta[c] : 0.f;
+  }
+  float db[4] = {0, 0, 0, 0}, dg[4] = {0, 0, 0, 0};
+  for (int64_t r = (int64_t)blockIdx.x * k + rsub; r < R; r += (int64_t)gridDim.x * k) {
+    const int64_t o = r * C + 4 * c4;
+    const Lane4 xv = ld4(x + o), gv = ld4(gy + o);
+    Lane4 yv = {{1.f, 1.f, 1.f, 1.f}};
+    if (q.relu) yv = ld4(y + o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float xh = (xv.v[j] - m[j]) * is[j];
+      const float gz = bnq_gz(fmaf(xh, g[j], b[j]), gv.v[j], yv.v[j], q);
+      db[j] += gz;
+      dg[j] = fmaf(gz, xh, dg[j]);
+    }
+  }
+  block_partials(db, dg, C4, k, sh, ws + (size_t)blockIdx.x * C * 2);
+  if (last_block(counter, &flag)) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      double S = 0.0, SS = 0.0;
+      for (unsigned bb = 0; bb < gridDim.x; ++bb) { S += __ldcg(ws + ((size_t)bb * C + c) * 2); SS += __ldcg(ws + ((size_t)bb * C + c) * 2 + 1); }
+      if (gbeta) gbeta[c] = (float)S;
+      if (ggamma) ggamma[c] = (float)SS;
+      coef[2 * c] = (float)(S / (double)R);
+      coef[2 * c + 1] = (float)(SS / (double)R);
+    }
+    if (threadIdx.x == 0) *counter = 0u;
+  }
+}
+
+// ---- backward pass 2: gx = gamma * invstd * (g_z - mean(g_z) - xhat * mean(g_z xhat))  [training]
+//                        gx = gamma * invstd * g_z                                           [eval] --------
+__global__ void __launch_bounds__(BN_MAX_THREADS)
+bnq_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ gy, int64_t R,
+                     int C, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ coef,
+                     int training, BnQ q, float* __restrict__ gx) {
+  const int C4 = C >> 2, k = blockDim.x / C4;
+  const int c4 = threadIdx.x % C4, rsub = threadIdx.x / C4;
+  float m[4], is[4], g[4], b[4], k1[4], k2[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = 4 * c4 + j;
+    m[j] = mean[c]; is[j] = invstd[c]; g[j] = gamma ? gamma[c] : 1.f; b[j] = beta ? beta[c] : 0.f;
+    k1[j] = training ? coef[2 * c] : 0.f; k2[j] = training ? coef[2 * c + 1] : 0.f;
+  }
+  for (int64_t r = (int64_t)blockIdx.x * k + rsub; r < R; r += (int64_t)gridDim.x * k) {
+    const int64_t o = r * C + 4 * c4;
+    const Lane4 xv = ld4(x + o), gv = ld4(gy + o);
+    Lane4 yv = {{1.f, 1.f, 1.f, 1.f}};
+    if (q.relu) yv = ld4(y + o);
+    float out[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float xh = (xv.v[j] - m[j]) * is[j];
+      const float gz = bnq_gz(fmaf(xh, g[j], b[j]), gv.v[j], yv.v[j], q);
+      out[j] = g[j] * is[j] * (gz - k1[j] - xh * k2[j]);
+    }
+    *reinterpret_cast<float4*>(gx + o) = make_float4(out[0], out[1], out[2], out[3]);
+  }
+}
+
+struct BnLaunch { int threads, grid, k; size_t smem; };
+static BnLaunch bn_launch(int64_t R, int C) {
+  BnLaunch L;
+  const int C4 = C / 4;
+  L.k = BN_MAX_THREADS / C4;
+  L.threads = L.k * C4;
+  int64_t g = (R + (int64_t)L.k * 4 - 1) / ((int64_t)L.k * 4);          // >= 4 rows per thread
+  if (g > BN_MAX_GRID) g = BN_MAX_GRID;
+  if (g < 1) g = 1;
+  L.grid = (int)g;
+  L.smem = (size_t)L.threads * 8 * sizeof(float);
+  return L;
+}
+
+static BnQ make_bnq(int a_bit, float act_range, int variant, int relu) {
+  BnQ q;
+  q.a_bit = a_bit; q.variant = variant == 0 ? 0 : 1; q.relu = relu; q.ar = act_range;
+  q.n = (float)((1ull << a_bit) - 1);
+  q.inv_n = 1.0f / q.n;
+  q.gscale = 2.0f * act_range * kInvSqrt2Pi;
+  return q;
+}
+
+static int bn_check(int64_t R, int C, int a_bit, int variant, const void* a, const void* b, const void* c) {
+  if (R < 1 || C < 4 || (C & 3) || C > 4 * BN_MAX_THREADS || a_bit < 1 || a_bit > 31 || variant < 0 || variant > 2) return ALIGNQ_EINVAL;
+  if (!aligned16(a) || !aligned16(b) || (c && !aligned16(c))) return ALIGNQ_EALIGN;
+  return ALIGNQ_OK;
+}
+
+}  // namespace alignq
+
+using namespace alignq;
+
+extern "C" size_t alignq_bn_act_ws_doubles(int C) {
+  if (C <= 0) return 0;
+  return (size_t)BN_MAX_GRID * (size_t)C * 2 + (size_t)C;        // per-block partials + [C][2] float coefficients
+}
+
+extern "C" int alignq_bn_act_fwd(const float* x, int64_t rows, int C, const float* gamma, const float* beta,
+                                 float* running_mean, float* running_var, float momentum, float bn_eps, int training,
+                                 int a_bit, float act_range, int variant, int relu, float* y, float* save_mean,
+                                 float* save_invstd, double* ws, uint32_t* counter, alignq_stream_t stream) {
+  int rc = bn_check(rows, C, a_bit, variant, x, y, nullptr);
+  if (rc) return rc;
+  if (!x || !y || !save_mean || !save_invstd || !ws || !counter) return ALIGNQ_EINVAL;
+  if (!training && (!running_mean || !running_var)) return ALIGNQ_EINVAL;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const BnLaunch L = bn_launch(rows, C);
+  if (training) {
+    bnq_stats_kernel<<<L.grid, L.threads, L.smem, s>>>(x, rows, C, running_mean, running_var, momentum, bn_eps,
+                                                       save_mean, save_invstd, ws, counter);
+  } else {
+    bnq_eval_stats_kernel<<<(C + 255) / 256, 256, 0, s>>>(running_mean, running_var, bn_eps, C, save_mean, save_invstd);
+  }
+  ALIGNQ_LAUNCH_CHECK();
+  bnq_apply_kernel<<<L.grid * 2, L.threads, 0, s>>>(x, rows, C, gamma, beta, save_mean, save_invstd,
+                                                    make_bnq(a_bit, act_range, variant, relu), y);
+  ALIGNQ_LAUNCH_CHECK();
+  return ALIGNQ_OK;
+}
+
+extern "C" int alignq_bn_act_bwd(const float* x, const float* y, const float* gy, int64_t rows, int C,
+                                 const float* gamma, const float* beta, const float* save_mean,
+                                 const float* save_invstd, int training, int a_bit, float act_range, int variant,
+                                 int relu, float* gx, float* ggamma, float* gbeta, double* ws, uint32_t* counter,
+                                 alignq_stream_t stream) {
+  int rc = bn_check(rows, C, a_bit, variant, x, gy, gx);
+  if (rc) return rc;
+  if (!x || !gy || !gx || !save_mean || !save_invstd || !ws || !counter || (relu && !y)) return ALIGNQ_EINVAL;
+  if (relu && !aligned16(y)) return ALIGNQ_EALIGN;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const BnLaunch L = bn_launch(rows, C);
+  const BnQ q = make_bnq(a_bit, act_range, variant, relu);
+  float* coef = reinterpret_cast<float*>(ws + (size_t)BN_MAX_GRID * C * 2);       // [C][2] floats after the partials
+  bnq_bwd_reduce_kernel<<<L.grid, L.threads, L.smem, s>>>(x, y, gy, rows, C, gamma, beta, save_mean, save_invstd, q,
+                                                          ggamma, gbeta, coef, ws, counter);
+  ALIGNQ_LAUNCH_CHECK();
+  bnq_bwd_apply_kernel<<<L.grid * 2, L.threads, 0, s>>>(x, y, gy, rows, C, gamma, beta, save_mean, save_invstd, coef,
+                                                        training, q, gx);
+  ALIGNQ_LAUNCH_CHECK();
+  return ALIGNQ_OK;
+}

@@ -8,6 +8,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .fused import bn_act
 from .quantization import activation_quantize_fn, conv2d_Q_fn
 
 
@@ -22,7 +23,7 @@ class DenseBasicBlock(nn.Module):
         self.dropRate = dropRate
 
     def forward(self, x):
-        out = self.conv1(self.relu(self.act_q0(self.bn1(x))))
+        out = self.conv1(bn_act(self.bn1, self.act_q0, x, True))
         if self.dropRate > 0:
             out = F.dropout(out, p=self.dropRate, training=self.training)
         return torch.cat((x, out), 1)
@@ -38,7 +39,7 @@ class Transition(nn.Module):
         self.relu = nn.ReLU(inplace=True)
 
     def forward(self, x):
-        return F.avg_pool2d(self.conv1(self.relu(self.act_q0(self.bn1(x)))), 2)
+        return F.avg_pool2d(self.conv1(bn_act(self.bn1, self.act_q0, x, True)), 2)
 
 
 class DenseNet(nn.Module):
@@ -85,7 +86,7 @@ class DenseNet(nn.Module):
 
     def forward(self, x):
         x = self.dense3(self.trans2(self.dense2(self.trans1(self.dense1(self.conv1(x))))))
-        x = self.avgpool(self.relu(self.act_q0(self.bn(x))))
+        x = self.avgpool(bn_act(self.bn, self.act_q0, x, True))
         return self.fc(x.view(x.size(0), -1))
 
 

@@ -1,0 +1,88 @@
+"""Fused BatchNorm2d -> activation quantizer -> (ReLU): the step either side of the quantizer in every
+model file, e.g. ``F.relu(self.act_q0(self.bn0(out)))``
+(cdf_alignment/resnet-20-cifar-10/model/resnet.py:72,121-123).
+
+``bn_act(bn, actq, x, relu)`` keeps the reference's modules (same parameters, buffers and state_dict
+keys) and only changes how they are executed: one statistics pass + one apply pass (12 B/elem)
+instead of cuDNN BN + quantizer + ReLU (28 B/elem), and likewise backward.  It is used when
+``args.fuse_bn_act`` is set and the input is a channels_last fp32 CUDA tensor with C % 4 == 0,
+C <= 1024, a plain k-bit quantizer (no ADMM term); otherwise the three modules run one after the other.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import _lib as L
+from ..utils.options import args
+
+_ws_cache = {}
+
+
+def _bn_ws(C: int, device):
+    """(fp64 scratch, zero-initialised ticket counter) per device; stream-ordered reuse across layers."""
+    need = int(L.load().alignq_bn_act_ws_doubles(C))
+    ent = _ws_cache.get(device.index)
+    if ent is None or ent[0].numel() < need:
+        counter = ent[1] if ent is not None else torch.zeros(1, dtype=torch.int32, device=device)
+        ent = (torch.empty(need, dtype=torch.float64, device=device), counter)
+        _ws_cache[device.index] = ent
+    return ent
+
+
+class _BnActFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, bn, a_bit, act_range, variant, relu):
+        B, C, H, W = x.shape
+        rows = B * H * W
+        training = bool(bn.training or bn.running_mean is None)
+        y = torch.empty_like(x)
+        mean = torch.empty(C, dtype=torch.float32, device=x.device)
+        invstd = torch.empty(C, dtype=torch.float32, device=x.device)
+        ws, counter = _bn_ws(C, x.device)
+        with torch.cuda.device_of(x):
+            L.check(L.load().alignq_bn_act_fwd(
+                x.data_ptr(), rows, C, L.ptr(weight), L.ptr(bias), L.ptr(bn.running_mean), L.ptr(bn.running_var),
+                float(bn.momentum), float(bn.eps), int(training), a_bit, act_range, variant, int(relu),
+                y.data_ptr(), mean.data_ptr(), invstd.data_ptr(), ws.data_ptr(), counter.data_ptr(), L.stream_ptr()),
+                "alignq_bn_act_fwd")
+        if training and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+        ctx.save_for_backward(x, y, weight, bias, mean, invstd)
+        ctx.cfg = (rows, C, training, a_bit, act_range, variant, relu)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, y, weight, bias, mean, invstd = ctx.saved_tensors
+        rows, C, training, a_bit, act_range, variant, relu = ctx.cfg
+        gy = L.like_layout(gy, x, "grad of fused bn-act output")
+        gx = torch.empty_like(x)
+        gw = torch.empty(C, dtype=torch.float32, device=x.device) if weight is not None else None
+        gb = torch.empty(C, dtype=torch.float32, device=x.device) if bias is not None else None
+        ws, counter = _bn_ws(C, x.device)
+        with torch.cuda.device_of(x):
+            L.check(L.load().alignq_bn_act_bwd(
+                x.data_ptr(), y.data_ptr(), gy.data_ptr(), rows, C, L.ptr(weight), L.ptr(bias), mean.data_ptr(),
+                invstd.data_ptr(), int(training), a_bit, act_range, variant, int(relu), gx.data_ptr(), L.ptr(gw),
+                L.ptr(gb), ws.data_ptr(), counter.data_ptr(), L.stream_ptr()), "alignq_bn_act_bwd")
+        return gx, gw, gb, None, None, None, None, None
+
+
+def can_fuse(bn, actq, x) -> bool:
+    return (bool(args.fuse_bn_act) and type(bn) is nn.BatchNorm2d and bn.momentum is not None
+            and (bn.training or bn.running_mean is not None)
+            and getattr(actq, "opt", None) is None and 1 <= actq.a_bit < 32
+            and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
+            and x.shape[1] % 4 == 0 and x.shape[1] <= 1024
+            and x.is_contiguous(memory_format=torch.channels_last) and x.data_ptr() % 16 == 0)
+
+
+def bn_act(bn, actq, x, relu: bool):
+    """``relu(actq(bn(x)))`` (or without the ReLU), fused when possible."""
+    if can_fuse(bn, actq, x):
+        return _BnActFn.apply(x, bn.weight, bn.bias, bn, actq.a_bit, float(args.act_range),
+                              L.VARIANT_ID[actq.variant], relu)
+    y = actq(bn(x))
+    return F.relu(y) if relu else y

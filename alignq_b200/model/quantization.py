@@ -193,7 +193,7 @@ class weight_quantize_fn(nn.Module):
 class _ActQuantFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, a_bit, act_range, variant, return_cdf):
-        xc = L.dev_f32(x, "activation")
+        xc = L.dev_f32_dense(x, "activation")
         y = torch.empty_like(xc)
         with torch.cuda.device_of(xc):
             L.check(L.load().alignq_act_fwd(xc.data_ptr(), y.data_ptr(), 0, xc.numel(), a_bit, act_range,
@@ -206,7 +206,7 @@ class _ActQuantFn(torch.autograd.Function):
     def backward(ctx, gy):
         (xc,) = ctx.saved_tensors
         a_bit, act_range, variant, return_cdf = ctx.cfg
-        gy = L.dev_f32(gy, "grad of quantized activation")
+        gy = L.like_layout(gy, xc, "grad of quantized activation")
         gx = torch.empty_like(xc)
         with torch.cuda.device_of(xc):
             L.check(L.load().alignq_act_bwd(xc.data_ptr(), gy.data_ptr(), gx.data_ptr(), xc.numel(), a_bit,
@@ -232,7 +232,7 @@ class _ActAdmmFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, alterD, gamma, a_bit, act_range, eps, mu, rho, gram_mode):
-        xc = L.dev_f32(x, "activation")
+        xc = L.dev_f32_dense(x, "activation")      # per-sample feature order is irrelevant to the Gram
         Z = L.dev_f32(alterD, "alterD")
         U = L.dev_f32(gamma, "gamma")
         B = xc.shape[0]
@@ -267,7 +267,7 @@ class _ActAdmmFn(torch.autograd.Function):
         gl = L.dev_f32(gloss.reshape(1), "grad of trans_loss")
         with torch.cuda.device_of(xc):
             if ctx.needs_input_grad[0]:
-                gyc = L.dev_f32(gy, "grad of quantized activation")
+                gyc = L.like_layout(gy, xc, "grad of quantized activation")
                 gx = torch.empty_like(xc)
                 ws = _gram_ws(B, Fdim, xc.device)
                 L.check(lib.alignq_act_admm_bwd(

@@ -12,6 +12,7 @@ import torch.nn.functional as F
 
 from ..utils.admm import ADMM
 from ..utils.options import args
+from .fused import bn_act
 from .quantization import activation_quantize_fn, conv2d_Q_fn
 
 
@@ -49,9 +50,9 @@ class PreActBlock_conv_Q(nn.Module):
 
     def forward(self, x):
         if not self.with_admm:
-            shortcut = x if self.skip_conv is None else self.act_skip_q(self.skip_bn(self.skip_conv(x)))
-            out = F.relu(self.act_q0(self.bn0(self.conv0(x))))
-            out = self.act_q1(self.bn1(self.conv1(out)))
+            shortcut = x if self.skip_conv is None else bn_act(self.skip_bn, self.act_skip_q, self.skip_conv(x), False)
+            out = bn_act(self.bn0, self.act_q0, self.conv0(x), True)       # relu(act_q0(bn0(.)))
+            out = bn_act(self.bn1, self.act_q1, self.conv1(out), False)
             out += shortcut
             return F.relu(out)
         trans_loss = 0.
@@ -91,14 +92,13 @@ class PreActResNet(nn.Module):
         self.logit = nn.Linear(64, num_classes)
 
     def forward(self, x):
-        out = self.bn(self.conv0(x))
         if not self.with_admm:
-            out = F.relu(self.act_q0(out))
+            out = bn_act(self.bn, self.act_q0, self.conv0(x), True)
             for layer in self.layers:
                 out = layer(out)
             return self.logit(self.avgpool(out).view(out.size(0), -1))
         trans_loss = 0.
-        out, loss = self.act_q0(out)
+        out, loss = self.act_q0(self.bn(self.conv0(x)))
         trans_loss += loss
         out = F.relu(out)
         for layer in self.layers:

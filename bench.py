@@ -157,7 +157,9 @@ def run_product(args):
         dist.init_process_group("nccl", device_id=dev)
     lib = aq.load_library()
     torch.backends.cudnn.benchmark = True
-    aq.set_args(variant="A", bitW=8, abitW=8, act_range=2, lam=1.0, lam2=4.0, method="ours", train_batch_size=BATCH)
+    fuse = not (args.no_fuse or args.nchw)
+    aq.set_args(variant="A", bitW=8, abitW=8, act_range=2, lam=1.0, lam2=4.0, method="ours", train_batch_size=BATCH,
+                fuse_bn_act=fuse)
     torch.manual_seed(0)                                   # identical replicas on every rank
     model = resnet20_quant(8, 8, "second").to(dev).train()
     if world > 1 and args.sync_bn:
@@ -168,6 +170,8 @@ def run_product(args):
     n_host = 8
     host_x = [torch.randn(BATCH, 3, 32, 32, generator=g).pin_memory() for _ in range(n_host)]
     host_t = [torch.randint(0, 10, (BATCH,), generator=g).pin_memory() for _ in range(n_host)]
+    fmt = torch.contiguous_format if args.nchw else torch.channels_last
+    host_x = [h.contiguous(memory_format=fmt).pin_memory() for h in host_x]
     dev_x = [h.to(dev) for h in host_x]
     dev_t = [h.to(dev) for h in host_t]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
@@ -270,6 +274,7 @@ def run_product(args):
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": dict(CONFIG, global_batch=BATCH * world, parallelism=f"dp{world}", cuda_graph=graphed,
+                               activation_layout="nchw" if args.nchw else "channels_last", fused_bn_act=fuse,
                                sync_bn=bool(args.sync_bn and world > 1),
                                l2="flushed between timed steps (256 MiB memset, outside the event pairs)"),
                 "e2e": {"value": e2e, "unit": "img/s", "ms_per_step": ms_e2e / args.steps,
@@ -297,6 +302,10 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--sync-bn", action="store_true", help="N>1: SyncBatchNorm (global-batch BN statistics)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fuse", action="store_true", help="run BatchNorm / quantizer / ReLU as separate kernels "
+                    "(default with channels_last: the fused bn->act-quant->relu kernels, SURVEY 8f-1)")
+    ap.add_argument("--nchw", action="store_true", help="keep activations NCHW-contiguous (default: channels_last, "
+                    "which spares cuDNN its NCHW<->NHWC transposes; the quantizer kernels are layout-agnostic)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -149,6 +149,27 @@ int alignq_sgd_step(const alignq_sgd_tensor_t* tensors, const int32_t* chunk_ten
                     const int32_t* tensor_chunk0, int ntensors, int64_t nchunks,
                     float lam, float lam2, int bitW, alignq_stream_t stream);
 
+/* ---- fused BatchNorm2d -> activation quantizer -> (ReLU), NHWC ------------------------------------
+ * The step either side of the quantizer in every model file, e.g.
+ * `F.relu(self.act_q0(self.bn0(out)))` (cdf_alignment/resnet-20-cifar-10/model/resnet.py:72,121-123),
+ * `self.relu(self.act_q0(self.bn1(x)))` (cdf_alignment/dense-cifar-10/model/densenet.py:32-34).
+ * x, y, gy, gx: [rows = B*H*W, C] fp32 with C contiguous (channels_last), 16-byte aligned, C % 4 == 0,
+ * C <= 1024.  training != 0: batch statistics (biased variance), running_mean/var updated with
+ * `momentum` (unbiased variance) unless NULL; training == 0: running statistics.  save_mean /
+ * save_invstd: [C] out (forward) / in (backward).  ws: alignq_bn_act_ws_doubles(C) doubles;
+ * counter: one uint32 that must be ZERO before the first call (the kernels re-arm it).
+ * Backward: g_z = gy [y > 0 if relu] * 2 ar phi(z) (z = BN output), then the BatchNorm backward;
+ * ggamma / gbeta ([C], nullable) receive the affine gradients.                                      */
+size_t alignq_bn_act_ws_doubles(int C);
+int alignq_bn_act_fwd(const float* x, int64_t rows, int C, const float* gamma, const float* beta,
+                      float* running_mean, float* running_var, float momentum, float bn_eps, int training,
+                      int a_bit, float act_range, int variant, int relu, float* y, float* save_mean,
+                      float* save_invstd, double* ws, uint32_t* counter, alignq_stream_t stream);
+int alignq_bn_act_bwd(const float* x, const float* y, const float* gy, int64_t rows, int C,
+                      const float* gamma, const float* beta, const float* save_mean, const float* save_invstd,
+                      int training, int a_bit, float act_range, int variant, int relu, float* gx,
+                      float* ggamma, float* gbeta, double* ws, uint32_t* counter, alignq_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,103 @@
+"""GPU: fused BatchNorm2d -> activation quantizer -> (ReLU) against the un-fused
+reference pipeline: torch BatchNorm2d -> oracle activation quantizer -> F.relu, forward, backward,
+running statistics, eval mode.  The BN output differs from cuDNN's by a few ulp (different summation
+order), so a code that sits on a rounding tie may flip: bar = +-1 code on <= 1e-4 of the elements."""
+import copy
+
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+import alignq_b200 as aq
+from alignq_b200.model.fused import bn_act, can_fuse
+from oracle import alignq_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+
+@pytest.mark.parametrize("variant", ["A", "B"])
+@pytest.mark.parametrize("shape,relu", [((128, 16, 32, 32), True), ((64, 64, 8, 8), False), ((8, 24, 5, 7), True),
+                                        ((4, 456, 8, 8), True), ((3, 1024, 2, 2), False)])
+def test_fused_bn_act_matches_unfused_pipeline(variant, shape, relu):
+    torch.manual_seed(0)
+    aq.set_args(variant=variant, act_range=2, abitW=8, fuse_bn_act=True)
+    B, C, H, W = shape
+    x0 = (torch.randn(shape, device=DEV) * 1.5 + 0.3).contiguous(memory_format=torch.channels_last)
+    gy = torch.randn(shape, device=DEV).contiguous(memory_format=torch.channels_last)
+    bn = nn.BatchNorm2d(C).to(DEV).train()
+    with torch.no_grad():
+        bn.weight.copy_(1 + 0.2 * torch.randn(C))
+        bn.bias.copy_(0.1 * torch.randn(C))
+    bn_ref = copy.deepcopy(bn)
+    actq = aq.activation_quantize_fn(8, "second")
+    x = x0.clone().requires_grad_(True)
+    assert can_fuse(bn, actq, x)
+    y = bn_act(bn, actq, x, relu)
+    (y * gy).sum().backward()
+    xr = x0.clone().requires_grad_(True)
+    z = bn_ref(xr)
+    yr = O.activation_quantize(z, 8, "second", variant, 2.0)
+    yr = F.relu(yr) if relu else yr
+    (yr * gy).sum().backward()
+    n = 255
+    step = (4.0 / n) if variant == "A" else (1.0 / n)
+    d = (y - yr).abs()
+    assert float(d.max()) <= step * 1.001
+    assert int((d > 1e-6).sum()) <= max(1, int(1e-4 * y.numel())), f"{int((d > 1e-6).sum())} codes differ"
+    assert y.is_contiguous(memory_format=torch.channels_last)
+    assert rel(x.grad, xr.grad) <= 2e-3, "gx"                      # a flipped code moves the ReLU mask of that element
+    assert rel(bn.weight.grad, bn_ref.weight.grad) <= 2e-3 and rel(bn.bias.grad, bn_ref.bias.grad) <= 2e-3
+    assert torch.allclose(bn.running_mean, bn_ref.running_mean, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(bn.running_var, bn_ref.running_var, rtol=1e-5, atol=1e-6)
+    assert int(bn.num_batches_tracked) == 1
+    # eval mode: running statistics, no batch-statistics terms in the backward
+    bn.eval(); bn_ref.eval()
+    x2 = x0.clone().requires_grad_(True)
+    y2 = bn_act(bn, actq, x2, relu)
+    (y2 * gy).sum().backward()
+    xr2 = x0.clone().requires_grad_(True)
+    yr2 = O.activation_quantize(bn_ref(xr2), 8, "second", variant, 2.0)
+    yr2 = F.relu(yr2) if relu else yr2
+    (yr2 * gy).sum().backward()
+    assert int(((y2 - yr2).abs() > 1e-6).sum()) <= max(1, int(1e-4 * y.numel()))
+    assert rel(x2.grad, xr2.grad) <= 2e-3
+
+
+def test_fused_path_is_skipped_when_it_does_not_apply():
+    aq.set_args(variant="A", act_range=2, fuse_bn_act=True)
+    bn = nn.BatchNorm2d(16).to(DEV)
+    actq = aq.activation_quantize_fn(8, "second")
+    x_nchw = torch.randn(4, 16, 8, 8, device=DEV)
+    assert not can_fuse(bn, actq, x_nchw)                                      # NCHW input -> separate modules
+    assert not can_fuse(bn, aq.activation_quantize_fn(32, "second"), x_nchw.contiguous(memory_format=torch.channels_last))
+    assert not can_fuse(bn, aq.activation_quantize_fn(8, "second", aq.ADMM(4)), x_nchw.contiguous(memory_format=torch.channels_last))
+    aq.set_args(fuse_bn_act=False)
+    assert not can_fuse(bn, actq, x_nchw.contiguous(memory_format=torch.channels_last))
+    y = bn_act(bn, actq, x_nchw, True)                                         # still correct, un-fused
+    ref = F.relu(O.activation_quantize(bn(x_nchw), 8, "second", "A", 2.0))
+    assert int((y != ref).sum()) <= 1
+
+
+def test_resnet20_fused_equals_unfused_within_band():
+    from alignq_b200.model.resnet import resnet20_quant
+    from oracle import models_oracle as MO
+    torch.manual_seed(2)
+    x = torch.randn(32, 3, 32, 32, device=DEV).contiguous(memory_format=torch.channels_last)
+    outs = []
+    for fuse in (False, True):
+        aq.set_args(variant="A", bitW=8, abitW=8, act_range=2, fuse_bn_act=fuse)
+        m = resnet20_quant(8, 8, "second")
+        m.load_state_dict(MO.deterministic_fill(m.state_dict(), seed=5))
+        m.to(DEV).train()
+        out = m(x)
+        out.logsumexp(1).sum().backward()
+        outs.append((out.detach(), m.layers[0].conv0.weight.grad.clone(), m.bn.running_var.clone()))
+    assert rel(outs[1][0], outs[0][0]) <= 2e-2          # same sensitivity band as the reference itself
+    assert rel(outs[1][1], outs[0][1]) <= 5e-2
+    assert torch.allclose(outs[1][2], outs[0][2], rtol=1e-4, atol=1e-6)

@@ -489,3 +489,33 @@ def test_tc_fused_forward_vs_fp32_mode_and_oracle(mode, variant, B, shape):
     assert float((res[mode][2] - Do).abs().max()) / gmax <= 2 * TC_TOL[mode]
     if mode == "tf32x3":
         rel_close(res[mode][3], res["fp32"][3], rtol=1e-3, atol_frac=1e-4, what="gx (dLdD from the tf32x3 forward)")
+
+
+def test_channels_last_activations_need_no_layout_copy():
+    """NHWC (channels_last) activations go through the same kernels in place: element-wise results are
+    identical element for element, and the ADMM Gram / trans_loss are invariant under the feature permutation."""
+    torch.manual_seed(13)
+    aq.set_args(variant="A", act_range=2)
+    x = torch.randn(16, 8, 6, 6, device=DEV)
+    gy = torch.randn_like(x)
+    xc = x.contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    xn = x.clone().requires_grad_(True)
+    q = aq.activation_quantize_fn(8, "second")
+    yc, yn = q(xc), q(xn)
+    assert yc.is_contiguous(memory_format=torch.channels_last) and torch.equal(yc, yn)
+    (yc * gy).sum().backward()
+    (yn * gy).sum().backward()
+    assert torch.equal(xc.grad, xn.grad)
+    aq.set_args(variant="B", method="ours", gram_mode="fp32")
+    admm = aq.ADMM(16).to(DEV)
+    f = aq.activation_quantize_fn(8, "second", admm)
+    xc2 = x.contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    xn2 = x.clone().requires_grad_(True)
+    (y1, l1), D1 = f(xc2), admm.D.clone()
+    (y2, l2), D2 = f(xn2), admm.D.clone()
+    assert torch.equal(y1, y2)
+    rel_close(l1.detach(), l2.detach(), rtol=1e-5, what="trans_loss under feature permutation")
+    assert float((D1 - D2).abs().max()) <= 1e-5
+    ((y1 * gy).sum() + l1).backward()
+    ((y2 * gy).sum() + l2).backward()
+    rel_close(xc2.grad, xn2.grad, rtol=1e-4, atol_frac=1e-5, what="gx under feature permutation")

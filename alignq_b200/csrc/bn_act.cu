@@ -8,9 +8,9 @@
 //
 // x is viewed as [R = B*H*W, C] with C contiguous.  Every thread owns one float4 of channels
 // (c4 = tid % (C/4); the block size is a multiple of C/4), so per-channel accumulators live in
-// registers and every global access is a coalesced 128-bit load.  Per-block fp64 partials go to a
-// workspace; the LAST block to finish (threadfence + ticket, no spinning) reduces them, finalises
-// the statistics and re-arms the ticket -- no extra launch, no memset, deterministic.
+// registers and every global access is a coalesced 128-bit load.  Block totals are added to fp64
+// accumulators with one atomic per value; the LAST block to finish (threadfence + ticket, no
+// spinning) finalises the statistics and re-zeroes accumulators and ticket -- no extra launch, no memset.
 #include "common.cuh"
 #include "../../include/alignq_b200.h"
 
@@ -54,20 +54,23 @@ __device__ __forceinline__ bool last_block(unsigned* counter, unsigned* smem_fla
   return last;
 }
 
-// reduce two float4 accumulators over the threads of the block that share c4, write fp64 partials
-__device__ __forceinline__ void block_partials(const float (&a)[4], const float (&b)[4], int C4, int k,
-                                               float* sh, double* partial /* [C][2] of this block */) {
+// Reduce two float4 accumulators over the threads of the block that share c4 (shared memory, fp64),
+// then add the block totals to the global fp64 accumulators acc[C][2] with one atomic per value.
+// (Summation order across blocks is not fixed; in fp64 that is ~1e-16 relative, far below the fp32
+// rounding of the finished statistics.)  The accumulators are zero on entry and the last block
+// re-zeroes them, so no memset is ever launched.
+__device__ __forceinline__ void block_accumulate(const float (&a)[4], const float (&b)[4], int C4, int k,
+                                                 float* sh, double* acc /* [C][2] */) {
   const int t = threadIdx.x;
 #pragma unroll
   for (int j = 0; j < 4; ++j) { sh[t * 8 + j] = a[j]; sh[t * 8 + 4 + j] = b[j]; }
   __syncthreads();
-  if (t < C4) {
-    double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int r = 0; r < k; ++r)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) s[j] += (double)sh[(r * C4 + t) * 8 + j];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { partial[(t * 4 + j) * 2] = s[j]; partial[(t * 4 + j) * 2 + 1] = s[4 + j]; }
+  for (int idx = t; idx < 8 * C4; idx += blockDim.x) {      // one (channel quad, value) pair per thread
+    const int c4 = idx >> 3, j = idx & 7;
+    double v = 0.0;
+#pragma unroll 8
+    for (int r = 0; r < k; ++r) v += (double)sh[(r * C4 + c4) * 8 + j];
+    atomicAdd(acc + (c4 * 4 + (j & 3)) * 2 + (j >> 2), v);
   }
 }
 
@@ -78,19 +81,31 @@ bnq_stats_kernel(const float* __restrict__ x, int64_t R, int C, float* __restric
                  float* __restrict__ save_invstd, double* __restrict__ ws, unsigned* __restrict__ counter) {
   extern __shared__ float sh[];
   __shared__ unsigned flag;
+
   const int C4 = C >> 2, k = blockDim.x / C4;
   const int c4 = threadIdx.x % C4, rsub = threadIdx.x / C4;
   float s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
-  for (int64_t r = (int64_t)blockIdx.x * k + rsub; r < R; r += (int64_t)gridDim.x * k) {
+  const int64_t stride = (int64_t)gridDim.x * k;
+  int64_t r = (int64_t)blockIdx.x * k + rsub;
+  for (; r + 3 * stride < R; r += 4 * stride) {             // 4 independent 128-bit loads in flight
+    Lane4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = ld4(x + (r + u * stride) * C + 4 * c4);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { s[j] += v[u].v[j]; ss[j] = fmaf(v[u].v[j], v[u].v[j], ss[j]); }
+  }
+  for (; r < R; r += stride) {
     const Lane4 v = ld4(x + r * C + 4 * c4);
 #pragma unroll
     for (int j = 0; j < 4; ++j) { s[j] += v.v[j]; ss[j] = fmaf(v.v[j], v.v[j], ss[j]); }
   }
-  block_partials(s, ss, C4, k, sh, ws + (size_t)blockIdx.x * C * 2);
+  block_accumulate(s, ss, C4, k, sh, ws);
   if (last_block(counter, &flag)) {
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      double S = 0.0, SS = 0.0;
-      for (unsigned b = 0; b < gridDim.x; ++b) { S += __ldcg(ws + ((size_t)b * C + c) * 2); SS += __ldcg(ws + ((size_t)b * C + c) * 2 + 1); }
+      const double S = __ldcg(ws + 2 * c), SS = __ldcg(ws + 2 * c + 1);
+      ws[2 * c] = 0.0; ws[2 * c + 1] = 0.0;                  // re-arm the accumulators
       const double mean = S / (double)R;
       double var = SS / (double)R - mean * mean;            // biased: what BN normalises with
       var = var < 0.0 ? 0.0 : var;
@@ -151,6 +166,7 @@ bnq_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ y, 
                       double* __restrict__ ws, unsigned* __restrict__ counter) {
   extern __shared__ float sh[];
   __shared__ unsigned flag;
+
   const int C4 = C >> 2, k = blockDim.x / C4;
   const int c4 = threadIdx.x % C4, rsub = threadIdx.x / C4;
   float m[4], is[4], g[4], b[4];
@@ -160,11 +176,9 @@ bnq_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ y, 
     m[j] = mean[c]; is[j] = invstd[c]; g[j] = gamma ? gamma[c] : 1.f; b[j] = beta ? beta[c] : 0.f;
   }
   float db[4] = {0, 0, 0, 0}, dg[4] = {0, 0, 0, 0};
-  for (int64_t r = (int64_t)blockIdx.x * k + rsub; r < R; r += (int64_t)gridDim.x * k) {
-    const int64_t o = r * C + 4 * c4;
-    const Lane4 xv = ld4(x + o), gv = ld4(gy + o);
-    Lane4 yv = {{1.f, 1.f, 1.f, 1.f}};
-    if (q.relu) yv = ld4(y + o);
+  const int64_t stride = (int64_t)gridDim.x * k;
+  int64_t r = (int64_t)blockIdx.x * k + rsub;
+  auto body = [&](const Lane4& xv, const Lane4& gv, const Lane4& yv) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float xh = (xv.v[j] - m[j]) * is[j];
@@ -172,12 +186,26 @@ bnq_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ y, 
       db[j] += gz;
       dg[j] = fmaf(gz, xh, dg[j]);
     }
+  };
+  const Lane4 ones = {{1.f, 1.f, 1.f, 1.f}};
+  for (; r + stride < R; r += 2 * stride) {                 // 2 rows x 3 tensors = 6 loads in flight
+    const int64_t o0 = r * C + 4 * c4, o1 = (r + stride) * C + 4 * c4;
+    const Lane4 x0 = ld4(x + o0), g0 = ld4(gy + o0), x1 = ld4(x + o1), g1 = ld4(gy + o1);
+    const Lane4 y0 = q.relu ? ld4(y + o0) : ones, y1 = q.relu ? ld4(y + o1) : ones;
+    body(x0, g0, y0);
+    body(x1, g1, y1);
   }
-  block_partials(db, dg, C4, k, sh, ws + (size_t)blockIdx.x * C * 2);
+  for (; r < R; r += stride) {
+    const int64_t o = r * C + 4 * c4;
+    const Lane4 xv = ld4(x + o), gv = ld4(gy + o);
+    const Lane4 yv = q.relu ? ld4(y + o) : ones;
+    body(xv, gv, yv);
+  }
+  block_accumulate(db, dg, C4, k, sh, ws);
   if (last_block(counter, &flag)) {
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      double S = 0.0, SS = 0.0;
-      for (unsigned bb = 0; bb < gridDim.x; ++bb) { S += __ldcg(ws + ((size_t)bb * C + c) * 2); SS += __ldcg(ws + ((size_t)bb * C + c) * 2 + 1); }
+      const double S = __ldcg(ws + 2 * c), SS = __ldcg(ws + 2 * c + 1);
+      ws[2 * c] = 0.0; ws[2 * c + 1] = 0.0;                  // re-arm the accumulators
       if (gbeta) gbeta[c] = (float)S;
       if (ggamma) ggamma[c] = (float)SS;
       coef[2 * c] = (float)(S / (double)R);
@@ -220,13 +248,13 @@ bnq_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ y, c
 }
 
 struct BnLaunch { int threads, grid, k; size_t smem; };
-static BnLaunch bn_launch(int64_t R, int C) {
+static BnLaunch bn_launch(int64_t R, int C, int max_grid = BN_MAX_GRID) {
   BnLaunch L;
   const int C4 = C / 4;
   L.k = BN_MAX_THREADS / C4;
   L.threads = L.k * C4;
   int64_t g = (R + (int64_t)L.k * 4 - 1) / ((int64_t)L.k * 4);          // >= 4 rows per thread
-  if (g > BN_MAX_GRID) g = BN_MAX_GRID;
+  if (g > max_grid) g = max_grid;
   if (g < 1) g = 1;
   L.grid = (int)g;
   L.smem = (size_t)L.threads * 8 * sizeof(float);
@@ -254,7 +282,7 @@ using namespace alignq;
 
 extern "C" size_t alignq_bn_act_ws_doubles(int C) {
   if (C <= 0) return 0;
-  return (size_t)BN_MAX_GRID * (size_t)C * 2 + (size_t)C;        // per-block partials + [C][2] float coefficients
+  return (size_t)C * 2 + (size_t)C;        // fp64 accumulators [C][2] (ZERO before first use) + [C][2] float coefficients
 }
 
 extern "C" int alignq_bn_act_fwd(const float* x, int64_t rows, int C, const float* gamma, const float* beta,
@@ -292,7 +320,7 @@ extern "C" int alignq_bn_act_bwd(const float* x, const float* y, const float* gy
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const BnLaunch L = bn_launch(rows, C);
   const BnQ q = make_bnq(a_bit, act_range, variant, relu);
-  float* coef = reinterpret_cast<float*>(ws + (size_t)BN_MAX_GRID * C * 2);       // [C][2] floats after the partials
+  float* coef = reinterpret_cast<float*>(ws + (size_t)C * 2);       // [C][2] floats after the accumulators
   bnq_bwd_reduce_kernel<<<L.grid, L.threads, L.smem, s>>>(x, y, gy, rows, C, gamma, beta, save_mean, save_invstd, q,
                                                           ggamma, gbeta, coef, ws, counter);
   ALIGNQ_LAUNCH_CHECK();

@@ -22,11 +22,11 @@ _ws_cache = {}
 
 def _bn_ws(C: int, device):
     """(fp64 scratch, zero-initialised ticket counter) per device; stream-ordered reuse across layers."""
-    need = int(L.load().alignq_bn_act_ws_doubles(C))
+    need = int(L.load().alignq_bn_act_ws_doubles(max(C, 1024)))
     ent = _ws_cache.get(device.index)
     if ent is None or ent[0].numel() < need:
         counter = ent[1] if ent is not None else torch.zeros(1, dtype=torch.int32, device=device)
-        ent = (torch.empty(need, dtype=torch.float64, device=device), counter)
+        ent = (torch.zeros(need, dtype=torch.float64, device=device), counter)   # kernels keep it zeroed
         _ws_cache[device.index] = ent
     return ent
 
@@ -49,7 +49,9 @@ class _BnActFn(torch.autograd.Function):
                 "alignq_bn_act_fwd")
         if training and bn.num_batches_tracked is not None:
             bn.num_batches_tracked.add_(1)
-        ctx.save_for_backward(x, y, weight, bias, mean, invstd)
+        # y is only needed for the ReLU mask; without ReLU the model files go on to modify it in place
+        # (`out += shortcut`, resnet.py:77), so it must not be saved
+        ctx.save_for_backward(x, y if relu else None, weight, bias, mean, invstd)
         ctx.cfg = (rows, C, training, a_bit, act_range, variant, relu)
         return y
 
@@ -64,7 +66,7 @@ class _BnActFn(torch.autograd.Function):
         ws, counter = _bn_ws(C, x.device)
         with torch.cuda.device_of(x):
             L.check(L.load().alignq_bn_act_bwd(
-                x.data_ptr(), y.data_ptr(), gy.data_ptr(), rows, C, L.ptr(weight), L.ptr(bias), mean.data_ptr(),
+                x.data_ptr(), L.ptr(y), gy.data_ptr(), rows, C, L.ptr(weight), L.ptr(bias), mean.data_ptr(),
                 invstd.data_ptr(), int(training), a_bit, act_range, variant, int(relu), gx.data_ptr(), L.ptr(gw),
                 L.ptr(gb), ws.data_ptr(), counter.data_ptr(), L.stream_ptr()), "alignq_bn_act_bwd")
         return gx, gw, gb, None, None, None, None, None

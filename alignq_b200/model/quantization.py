@@ -175,8 +175,11 @@ class weight_quantize_fn(nn.Module):
         self.stage = stage
         self.variant = _variant(variant)
         self.uniform_q = uniform_quantize(k=self.w_bit)
+        self._bank = None                            # (WeightBank, index) when a model-level bank owns this weight
 
     def forward(self, x):
+        if self._bank is not None and self._bank[0].fresh and x is self._bank[0].params[self._bank[1]]:
+            return self._bank[0].lookup(self._bank[1], x)     # quantized by the bank's multi-tensor launch
         if self.w_bit == 32:                         # QB:73-76
             self.weight_cdf = x
             self.weight_q = x

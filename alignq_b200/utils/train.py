@@ -58,8 +58,15 @@ class QATStep:
     caller's choice)."""
 
     def __init__(self, model, lr=0.04, momentum=0.9, weight_decay=1e-4, lam=None, lam2=None,
-                 trans_loss_offset=0.5, process_group=None, world_size=1):
+                 trans_loss_offset=0.5, process_group=None, world_size=1, bank_weights=True):
         self.model = model
+        self.bank = None
+        if bank_weights:                       # one multi-tensor weight-quantizer launch per step
+            from .weight_bank import WeightBank
+            try:
+                self.bank = WeightBank(model)
+            except Exception:
+                self.bank = None
         named = list(model.named_parameters())
         self.params = [p for n, p in named if "alterD" not in n and "gamma" not in n]       # main.py:87
         self.admm_params = [p for n, p in named if "alterD" in n or "gamma" in n]
@@ -84,6 +91,8 @@ class QATStep:
     # -- one eager iteration -------------------------------------------------------------------
     def _iteration(self, x, t):
         self.gflat.zero_()                                         # optimizer.zero_grad(), one memset
+        if self.bank is not None:
+            self.bank.quantize_all()
         out = self.model(x)
         if isinstance(out, tuple):
             logits, trans_loss = out
@@ -102,6 +111,8 @@ class QATStep:
         self.opt.step(idx, w_cdf, w_pdf, self.lam, self.lam2)
         if self.opt_admm is not None:
             self.opt_admm.step(*collect_admm_args(self.model, self.admm_params))
+        if self.bank is not None:
+            self.bank.fresh = False                                # weights changed: slices are stale
         self.loss.copy_(ce.detach())
         return self.loss
 

@@ -169,3 +169,26 @@ def test_graph_replay_equals_eager():
     assert torch.isfinite(lg)
     l5 = float(graphed.step(x, t))
     assert l5 == l5 and l5 != float(lg)    # replay advances the optimisation (state lives outside the graph)
+
+
+def test_weight_bank_is_bit_identical_to_per_layer_quantization():
+    """One multi-tensor launch for all conv weights == 21 per-layer launches (same kernels, same chunking)."""
+    B = 16
+    aq.set_args(variant="A", train_batch_size=B, bitW=8, abitW=8, act_range=2)
+    torch.manual_seed(4)
+    x = torch.randn(B, 3, 32, 32, device=DEV)
+    t = torch.randint(0, 10, (B,), device=DEV)
+    losses, params = [], []
+    for bank in (False, True):
+        m = resnet.resnet20_quant(8, 8, "second")
+        m.load_state_dict(MO.deterministic_fill(m.state_dict(), seed=9))
+        m.to(DEV).train()
+        st = QATStep(m, bank_weights=bank)
+        assert (st.bank is not None) == bank
+        losses.append([float(st.step(x, t)) for _ in range(3)])
+        params.append([p.detach().clone() for p in m.parameters()])
+        if bank:
+            assert list(m.state_dict().keys())[0] == "conv0.weight" and m.conv0.weight.shape == (16, 3, 3, 3)
+            assert m.layers[0].conv0.quantize_fn.weight_pdf.shape == m.layers[0].conv0.weight.shape
+    assert losses[0] == losses[1]
+    assert all(torch.equal(a, b) for a, b in zip(*params))

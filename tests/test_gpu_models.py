@@ -171,8 +171,10 @@ def test_graph_replay_equals_eager():
     assert l5 == l5 and l5 != float(lg)    # replay advances the optimisation (state lives outside the graph)
 
 
-def test_weight_bank_is_bit_identical_to_per_layer_quantization():
-    """One multi-tensor launch for all conv weights == 21 per-layer launches (same kernels, same chunking)."""
+def test_weight_bank_matches_per_layer_quantization():
+    """One multi-tensor launch for all conv weights == 21 per-layer launches (same kernels; the bank's
+    slices are not all 16-byte aligned, so a chunk may take the scalar instead of the 128-bit path and
+    sum its fp64 partials in another order: results agree to fp32 round-off, not always bit for bit)."""
     B = 16
     aq.set_args(variant="A", train_batch_size=B, bitW=8, abitW=8, act_range=2)
     torch.manual_seed(4)
@@ -190,5 +192,5 @@ def test_weight_bank_is_bit_identical_to_per_layer_quantization():
         if bank:
             assert list(m.state_dict().keys())[0] == "conv0.weight" and m.conv0.weight.shape == (16, 3, 3, 3)
             assert m.layers[0].conv0.quantize_fn.weight_pdf.shape == m.layers[0].conv0.weight.shape
-    assert losses[0] == losses[1]
-    assert all(torch.equal(a, b) for a, b in zip(*params))
+    assert all(abs(a - b) <= 1e-6 * abs(a) for a, b in zip(*losses))
+    assert all(torch.allclose(a, b, rtol=1e-5, atol=1e-7) for a, b in zip(*params))

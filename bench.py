@@ -235,7 +235,7 @@ def run_product(args):
     value = world * BATCH * args.steps / (ms * 1e-3)
     e2e = world * BATCH * args.steps / (ms_e2e * 1e-3)
 
-    roofline = cpu = None
+    roofline = cpu = gram = None
     if rank == 0:
         # ---- roofline leg: the CDF-quantizer kernel pair on a stream far larger than L2 -----------
         n = 256 * (1 << 20)
@@ -265,6 +265,31 @@ def run_product(args):
                     "bwd": {"ms": tb, "gbs": 12.0 * n / (tb * 1e-3) / 1e9, "frac": 12.0 * n / (tb * 1e-3) / 1e9 / peak},
                     "input": "256 x 2^20 fp32 (1 GiB per tensor, inputs >> L2), W8A8 variant A"}
         del x, gy, y, gx
+        # ---- tensor leg: the ADMM Gram as a bf16 SYRK on tcgen05 (SURVEY 8d micro-shape B=256, F=2^20) ----
+        try:
+            Bg, Fg = 256, 1 << 20
+            xg = torch.randn(Bg, Fg, device=dev).to(torch.bfloat16)
+            Gg = torch.empty(Bg, Bg, device=dev)
+            wsg = torch.empty(int(lib.alignq_gram_bf16_ws_bytes(Bg)), dtype=torch.uint8, device=dev)
+            tg = 0.0
+            for i in range(3 + reps):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                L.check(lib.alignq_gram_bf16(xg.data_ptr(), Bg, Fg, 1, Gg.data_ptr(), wsg.data_ptr(), wsg.numel(), s), "gram_bf16")
+                e1.record()
+                torch.cuda.synchronize()
+                if i >= 3:
+                    tg += e0.elapsed_time(e1) / reps
+            pk = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(REPO, "MEASURED_PEAKS.json")) else {}
+            tf = 2.0 * Bg * Bg * Fg / (tg * 1e-3) / 1e12
+            gram = {"bound": "tensor", "achieved": tf, "unit": "TFLOP/s", "peak": pk.get("bf16_tflops", 1590.0),
+                    "frac": tf / pk.get("bf16_tflops", 1590.0), "frac_of_sustained": tf / pk.get("bf16_tflops_sustained", 1400.0),
+                    "ms": tg, "kernel": "gram_bf16_kernel (TMA + tcgen05.mma kind::f16, M=128 N=256, split-K) + reduce",
+                    "shape": [Bg, Fg], "flops": "2*B^2*F (full product)", "tolerance": "1e-2 rel vs fp32 inputs (bf16 operands)",
+                    "input": "bf16 [256, 2^20] (537 MB >> L2)"}
+            del xg, Gg, wsg
+        except Exception as e:                              # pragma: no cover
+            gram = {"error": str(e)[:200]}
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_reference_run(3, 1, budget_s=30.0)
             cpu = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -281,7 +306,7 @@ def run_product(args):
                         "h2d_bytes_per_step": BATCH * 3 * 32 * 32 * 4 + BATCH * 8, "d2h_bytes_per_step": 4},
                 "gpu_launches": int(launches_per_step) * args.steps,
                 "gpu_launches_per_step": int(launches_per_step),
-                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+                "clocks": clocks, "roofline": roofline, "gram_tensor_roofline": gram, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
         # Tear down without NCCL's communicator destructor: with captured NCCL kernels still referenced

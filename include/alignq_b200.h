@@ -149,6 +149,15 @@ int alignq_sgd_step(const alignq_sgd_tensor_t* tensors, const int32_t* chunk_ten
                     const int32_t* tensor_chunk0, int ntensors, int64_t nchunks,
                     float lam, float lam2, int bitW, alignq_stream_t stream);
 
+/* ---- bf16 Gram on the tensor cores (TMA + tcgen05, split-K) ---------------------------------------
+ * G = X X^T (divided by F if divide_by_F) for X [B <= 256, F] bf16 row-major, F % 8 == 0, 16-byte
+ * aligned: the dense contraction of corr() (QB:137) for operands already standardised and stored
+ * in bf16 (the tensor-bound micro-shape of SURVEY.md 8d).  G: [B, B] fp32.
+ * ws: alignq_gram_bf16_ws_bytes(B) bytes.                                                          */
+size_t alignq_gram_bf16_ws_bytes(int B);
+int alignq_gram_bf16(const void* x_bf16, int B, int64_t F, int divide_by_F, float* G, void* ws,
+                     size_t ws_bytes, alignq_stream_t stream);
+
 /* ---- fused BatchNorm2d -> activation quantizer -> (ReLU), NHWC ------------------------------------
  * The step either side of the quantizer in every model file, e.g.
  * `F.relu(self.act_q0(self.bn0(out)))` (cdf_alignment/resnet-20-cifar-10/model/resnet.py:72,121-123),

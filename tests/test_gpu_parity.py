@@ -519,3 +519,25 @@ def test_channels_last_activations_need_no_layout_copy():
     ((y1 * gy).sum() + l1).backward()
     ((y2 * gy).sum() + l2).backward()
     rel_close(xc2.grad, xn2.grad, rtol=1e-4, atol_frac=1e-5, what="gx under feature permutation")
+
+
+@pytest.mark.parametrize("B,F", [(256, 4096), (256, 65536), (128, 8192), (100, 8200), (17, 64), (256, 72)])
+def test_gram_bf16_tma_tcgen05_vs_fp64(B, F):
+    """bf16 SYRK micro-kernel (TMA + tcgen05, SURVEY.md 8d tensor-bound shape): bf16 products are exact in
+    fp32, so against an fp64 product of the SAME bf16 inputs only the fp32 accumulation order differs
+    (bar 1e-5 * max|G|); against fp32 inputs the bf16 rounding of the operands is the 1e-2 bar."""
+    torch.manual_seed(14)
+    lib = L.load()
+    x32 = torch.randn(B, F, device=DEV)
+    x = x32.to(torch.bfloat16)
+    G = torch.empty(B, B, device=DEV)
+    ws = torch.empty(int(lib.alignq_gram_bf16_ws_bytes(B)), dtype=torch.uint8, device=DEV)
+    L.check(lib.alignq_gram_bf16(x.data_ptr(), B, F, 1, G.data_ptr(), ws.data_ptr(), ws.numel(), L.stream_ptr()), "gram_bf16")
+    ref = (x.double() @ x.double().t()) / F
+    assert float((G.double() - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
+    ref32 = (x32.double() @ x32.double().t()) / F
+    assert float((G.double() - ref32).abs().max()) <= 1e-2 * float(ref32.abs().max())
+    assert float((G - G.t()).abs().max()) <= 1e-6 * float(ref.abs().max())          # symmetric
+    L.check(lib.alignq_gram_bf16(x.data_ptr(), B, F, 0, G.data_ptr(), ws.data_ptr(), ws.numel(), L.stream_ptr()), "gram_bf16")
+    assert float((G.double() - ref * F).abs().max()) <= 1e-5 * float((ref * F).abs().max())
+    assert lib.alignq_gram_bf16(x.data_ptr(), B, F - 1, 0, G.data_ptr(), ws.data_ptr(), ws.numel(), L.stream_ptr()) == -2   # F % 8

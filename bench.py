@@ -156,7 +156,7 @@ def run_product(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = aq.load_library()
-    torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.benchmark = os.environ.get("ALIGNQ_CUDNN_BENCHMARK", "1") != "0"   # 0: cheap ncu runs
     fuse = not (args.no_fuse or args.nchw)
     aq.set_args(variant="A", bitW=8, abitW=8, act_range=2, lam=1.0, lam2=4.0, method="ours", train_batch_size=BATCH,
                 fuse_bn_act=fuse)

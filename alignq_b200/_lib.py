@@ -54,9 +54,9 @@ SIGNATURES = {
     "alignq_gram_bf16_ws_bytes": (_Z, [_I]),
     "alignq_gram_bf16": (_I, [_P, _I, _L, _I, _P, _P, _Z, _P]),
     "alignq_bn_act_ws_doubles": (_Z, [_I]),
-    "alignq_bn_act_fwd": (_I, [_P, _L, _I, _P, _P, _P, _P, _F, _F, _I, _I, _F, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "alignq_bn_act_fwd": (_I, [_P, _L, _I, _P, _P, _P, _P, _F, _F, _I, _I, _F, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "alignq_bn_act_bwd": (_I, [_P, _P, _P, _L, _I, _P, _P, _P, _P, _I, _I, _F, _I, _I, _P, _P, _P, _P, _P, _P]),
-    "alignq_sgd_step": (_I, [_P, _P, _P, _I, _L, _F, _F, _I, _P]),
+    "alignq_sgd_step": (_I, [_P, _P, _P, _I, _L, _F, _F, _I, _F, _P]),
 }
 
 _lib = None
@@ -119,6 +119,15 @@ def dev_f32_dense(t: torch.Tensor, what: str) -> torch.Tensor:
     if t.is_contiguous() or (t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last)):
         return t
     return t.contiguous()
+
+
+def is_dense(t: torch.Tensor) -> bool:
+    return t.is_contiguous() or (t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last))
+
+
+def phys(t: torch.Tensor) -> torch.Tensor:
+    """1-D view of a dense tensor in PHYSICAL memory order (no copy)."""
+    return torch.as_strided(t, (t.numel(),), (1,), t.storage_offset())
 
 
 def like_layout(g: torch.Tensor, ref: torch.Tensor, what: str) -> torch.Tensor:

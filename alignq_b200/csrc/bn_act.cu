@@ -78,7 +78,8 @@ __device__ __forceinline__ void block_accumulate(const float (&a)[4], const floa
 __global__ void __launch_bounds__(BN_MAX_THREADS)
 bnq_stats_kernel(const float* __restrict__ x, int64_t R, int C, float* __restrict__ running_mean,
                  float* __restrict__ running_var, float momentum, float bn_eps, float* __restrict__ save_mean,
-                 float* __restrict__ save_invstd, double* __restrict__ ws, unsigned* __restrict__ counter) {
+                 float* __restrict__ save_invstd, double* __restrict__ ws, unsigned* __restrict__ counter,
+                 long long* __restrict__ num_batches_tracked) {
   extern __shared__ float sh[];
   __shared__ unsigned flag;
 
@@ -117,7 +118,10 @@ bnq_stats_kernel(const float* __restrict__ x, int64_t R, int C, float* __restric
         running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unbiased);
       }
     }
-    if (threadIdx.x == 0) *counter = 0u;                    // re-arm for the next launch
+    if (threadIdx.x == 0) {
+      *counter = 0u;                                        // re-arm for the next launch
+      if (num_batches_tracked) *num_batches_tracked += 1;   // BatchNorm2d.num_batches_tracked
+    }
   }
 }
 
@@ -288,7 +292,8 @@ extern "C" size_t alignq_bn_act_ws_doubles(int C) {
 extern "C" int alignq_bn_act_fwd(const float* x, int64_t rows, int C, const float* gamma, const float* beta,
                                  float* running_mean, float* running_var, float momentum, float bn_eps, int training,
                                  int a_bit, float act_range, int variant, int relu, float* y, float* save_mean,
-                                 float* save_invstd, double* ws, uint32_t* counter, alignq_stream_t stream) {
+                                 float* save_invstd, double* ws, uint32_t* counter, int64_t* num_batches_tracked,
+                                 alignq_stream_t stream) {
   int rc = bn_check(rows, C, a_bit, variant, x, y, nullptr);
   if (rc) return rc;
   if (!x || !y || !save_mean || !save_invstd || !ws || !counter) return ALIGNQ_EINVAL;
@@ -297,7 +302,8 @@ extern "C" int alignq_bn_act_fwd(const float* x, int64_t rows, int C, const floa
   const BnLaunch L = bn_launch(rows, C);
   if (training) {
     bnq_stats_kernel<<<L.grid, L.threads, L.smem, s>>>(x, rows, C, running_mean, running_var, momentum, bn_eps,
-                                                       save_mean, save_invstd, ws, counter);
+                                                       save_mean, save_invstd, ws, counter,
+                                                       reinterpret_cast<long long*>(num_batches_tracked));
   } else {
     bnq_eval_stats_kernel<<<(C + 255) / 256, 256, 0, s>>>(running_mean, running_var, bn_eps, C, save_mean, save_invstd);
   }

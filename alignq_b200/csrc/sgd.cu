@@ -10,7 +10,7 @@ namespace alignq {
 
 constexpr int kSgdThreads = 256;
 
-struct SgdScalars { float lam, two_lam2, levels; };
+struct SgdScalars { float lam, two_lam2, levels, grad_scale; };
 
 __device__ __forceinline__ float surrogate(float w_cdf, float w_pdf, const SgdScalars& k) {
   // transform(w, lam2) = (((w + 0.5) * (2^bitW - 1)) % 1) * lam2 * 2   (torch.remainder: result in [0, 1))
@@ -24,7 +24,7 @@ __device__ __forceinline__ float surrogate(float w_cdf, float w_pdf, const SgdSc
 
 __device__ __forceinline__ void sgd_one(float& p, float& g, float& buf, const alignq_sgd_tensor_t& t, bool has_buf,
                                         bool has_sur, float wc, float wp, const SgdScalars& k) {
-  float d = g;
+  float d = (k.grad_scale == 1.0f) ? g : __fmul_rn(g, k.grad_scale);      // 1 / world_size after a summing all-reduce
   if (t.weight_decay != 0.0f) d = fmaf(t.weight_decay, p, d);            // d_p.add_(weight_decay, p)
   if (has_buf) {
     buf = t.first_step ? d : fmaf(1.0f - t.dampening, d, __fmul_rn(t.momentum, buf));
@@ -82,7 +82,7 @@ using namespace alignq;
 
 extern "C" int alignq_sgd_step(const alignq_sgd_tensor_t* tensors, const int32_t* chunk_tensor,
                                const int32_t* tensor_chunk0, int ntensors, int64_t nchunks, float lam, float lam2,
-                               int bitW, alignq_stream_t stream) {
+                               int bitW, float grad_scale, alignq_stream_t stream) {
   if (ntensors < 0 || nchunks < 0 || bitW < 1 || bitW > 32) return ALIGNQ_EINVAL;
   if (ntensors == 0 || nchunks == 0) return ALIGNQ_OK;
   if (!tensors || !chunk_tensor || !tensor_chunk0) return ALIGNQ_EINVAL;
@@ -90,6 +90,7 @@ extern "C" int alignq_sgd_step(const alignq_sgd_tensor_t* tensors, const int32_t
   k.lam = lam;
   k.two_lam2 = lam2 * 2.0f;
   k.levels = (float)((1ull << bitW) - 1);
+  k.grad_scale = grad_scale;
   sgd_kernel<<<(unsigned)nchunks, kSgdThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(tensors, chunk_tensor,
                                                                                             tensor_chunk0, k);
   ALIGNQ_LAUNCH_CHECK();

@@ -45,10 +45,8 @@ class _BnActFn(torch.autograd.Function):
             L.check(L.load().alignq_bn_act_fwd(
                 x.data_ptr(), rows, C, L.ptr(weight), L.ptr(bias), L.ptr(bn.running_mean), L.ptr(bn.running_var),
                 float(bn.momentum), float(bn.eps), int(training), a_bit, act_range, variant, int(relu),
-                y.data_ptr(), mean.data_ptr(), invstd.data_ptr(), ws.data_ptr(), counter.data_ptr(), L.stream_ptr()),
-                "alignq_bn_act_fwd")
-        if training and bn.num_batches_tracked is not None:
-            bn.num_batches_tracked.add_(1)
+                y.data_ptr(), mean.data_ptr(), invstd.data_ptr(), ws.data_ptr(), counter.data_ptr(),
+                L.ptr(bn.num_batches_tracked) if training else 0, L.stream_ptr()), "alignq_bn_act_fwd")
         # y is only needed for the ReLU mask; without ReLU the model files go on to modify it in place
         # (`out += shortcut`, resnet.py:77), so it must not be saved
         ctx.save_for_backward(x, y if relu else None, weight, bias, mean, invstd)

@@ -131,7 +131,7 @@ def _single_plan(numel: int, device):
 class _WeightQuantFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, w, w_bit, variant, want_attrs):
-        wc = L.dev_f32(w, "weight")
+        wc = L.dev_f32_dense(w, "weight")          # statistics and map are order-independent: any dense layout
         seg_off, chunk_seg, seg_chunk0, nchunks = _single_plan(wc.numel(), wc.device)
         wq = torch.empty_like(wc)
         w_cdf = torch.empty_like(wc) if want_attrs else None
@@ -156,7 +156,7 @@ class _WeightQuantFn(torch.autograd.Function):
         wc, stats = ctx.saved_tensors
         if g is None:
             return None, None, None, None
-        g = L.dev_f32(g, "grad of quantized weight")
+        g = L.like_layout(g, wc, "grad of quantized weight")
         seg_off, chunk_seg, seg_chunk0, nchunks = _single_plan(wc.numel(), wc.device)
         gw = torch.empty_like(wc)
         ws = torch.empty(2 * max(nchunks, 1), dtype=torch.float64, device=wc.device)

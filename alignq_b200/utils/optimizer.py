@@ -55,31 +55,36 @@ class SGD(Optimizer):
             for i, p in enumerate(group["params"]):
                 if p.grad is None:
                     continue
-                if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
-                    raise L.AlignQError("alignq_b200.SGD needs contiguous fp32 CUDA parameters (no CPU fallback)")
+                if not p.is_cuda or p.dtype != torch.float32 or not L.is_dense(p):
+                    raise L.AlignQError("alignq_b200.SGD needs dense fp32 CUDA parameters (no CPU fallback)")
                 g = p.grad
-                if not g.is_contiguous():
-                    p.grad = g = g.contiguous()
+                if g.stride() != p.stride():               # the kernel is element-wise over physical memory
+                    p.grad = g = torch.empty_like(p).copy_(g)
                 buf, first = None, 0
                 if mom != 0:
                     st = self.state[p]
                     if "momentum_buffer" not in st:
-                        st["momentum_buffer"] = torch.empty_like(p, memory_format=torch.contiguous_format)
+                        st["momentum_buffer"] = torch.empty_like(p)          # same layout as p
                         st["alignq_first"] = True
                     buf = st["momentum_buffer"]
                     first = 1 if st.get("alignq_first", False) else 0
                 cdf_t = pdf_t = None
                 if use_sur and i in idx:
                     j = idx.index(i)
-                    cdf_t = L.dev_f32(w_cdf[j].detach(), "w_cdf")
-                    pdf_t = L.dev_f32(w_pdf[j].detach(), "w_pdf")
+                    cdf_t, pdf_t = w_cdf[j].detach(), w_pdf[j].detach()
+                    if cdf_t.shape == p.shape and cdf_t.stride() != p.stride():
+                        cdf_t = torch.empty_like(p).copy_(cdf_t)
+                    if pdf_t.shape == p.shape and pdf_t.stride() != p.stride():
+                        pdf_t = torch.empty_like(p).copy_(pdf_t)
+                    cdf_t = L.dev_f32_dense(cdf_t, "w_cdf")
+                    pdf_t = L.dev_f32_dense(pdf_t, "w_pdf")
                     if cdf_t.numel() != p.numel() or pdf_t.numel() != p.numel():
                         raise L.AlignQError(f"w_cdf/w_pdf #{j} do not match parameter #{i} ({tuple(p.shape)})")
                 ents.append((p, g, buf, cdf_t, pdf_t, float(lr), float(mom), float(damp), float(wd), int(nest), first))
         return ents
 
     @torch.no_grad()
-    def step(self, idx=(), w_cdf=(), w_pdf=(), lam=1.0, lam2=4.0, closure=None):
+    def step(self, idx=(), w_cdf=(), w_pdf=(), lam=1.0, lam2=4.0, closure=None, grad_scale=1.0):
         loss = None
         if closure is not None:
             with torch.enable_grad():
@@ -113,7 +118,7 @@ class SGD(Optimizer):
         with torch.cuda.device(dev):
             L.check(L.load().alignq_sgd_step(self._table_dev.data_ptr(), chunk_t.data_ptr(), t_chunk0.data_ptr(),
                                              len(ents), nchunks, float(lam), float(lam2), int(min(args.bitW, 32)),
-                                             L.stream_ptr()), "alignq_sgd_step")
+                                             float(grad_scale), L.stream_ptr()), "alignq_sgd_step")
         for e in ents:                               # momentum buffers are initialised now
             if e[10]:
                 self.state[e[0]]["alignq_first"] = False

@@ -47,6 +47,13 @@ def allreduce_mean_(flat: torch.Tensor, group=None, world: int | None = None) ->
     return flat
 
 
+def allreduce_sum_(flat: torch.Tensor, group=None) -> torch.Tensor:
+    """In-place sum over ranks (the caller folds 1/world into its next kernel)."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    return flat
+
+
 def combine_moments(s: torch.Tensor, ss: torch.Tensor, n: torch.Tensor, group=None):
     """Global mean and unbiased std from per-rank (sum, sum of squares, count): the (sum, sumsq)
     all-reduce that makes sharded statistics equal the single-device ``torch.mean`` / ``torch.std``."""

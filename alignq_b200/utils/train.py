@@ -2,9 +2,10 @@
 drop-in modules (cdf_alignment/resnet-20-cifar-10/main.py:269-313; cdf_alignment_admm/
 resnet-56-cifar-10/main.py:286-379), B200-first:
 
-  * gradients live in ONE flat fp32 buffer (every ``p.grad`` is a view), so ``zero_grad`` is one memset,
-    the data-parallel exchange is ONE NCCL all-reduce, and every pointer the multi-tensor SGD kernel
-    sees is static;
+  * ``zero_grad`` is ``p.grad = None`` (autograd hands over its buffers, no accumulate kernels); the
+    data-parallel exchange gathers the gradients into ONE flat fp32 buffer (physical order), runs ONE
+    NCCL all-reduce and re-points every ``p.grad`` at its slice; the 1/world mean is folded into the
+    multi-tensor SGD kernel, which reads everything through a device pointer table;
   * the whole iteration (forward, both backward passes, SGD.step, ADMM_OPT.step) can be captured
     in a CUDA graph and replayed: ResNet-20 at batch 128 is launch-bound, not bandwidth-bound
     (SURVEY.md 7.3), so replay removes the Python + launch overhead of ~600 small kernels.
@@ -19,7 +20,8 @@ import torch.nn.functional as F
 from .admm import ADMM
 from .optimizer import ADMM_OPT, SGD
 from .options import args
-from .sharding import allreduce_mean_
+from .. import _lib as L
+from .sharding import allreduce_sum_
 
 
 def quantized_convs(model):
@@ -58,8 +60,13 @@ class QATStep:
     caller's choice)."""
 
     def __init__(self, model, lr=0.04, momentum=0.9, weight_decay=1e-4, lam=None, lam2=None,
-                 trans_loss_offset=0.5, process_group=None, world_size=1, bank_weights=True):
+                 trans_loss_offset=0.5, process_group=None, world_size=1, bank_weights=True,
+                 channels_last=False):
         self.model = model
+        if channels_last:                      # NHWC weights: cuDNN needs no layout conversion kernels
+            for p in model.parameters():
+                if p.dim() == 4:
+                    p.data = p.data.contiguous(memory_format=torch.channels_last)
         self.bank = None
         if bank_weights:                       # one multi-tensor weight-quantizer launch per step
             from .weight_bank import WeightBank
@@ -76,21 +83,16 @@ class QATStep:
         self.lam2 = args.lam2 if lam2 is None else lam2
         self.offset = trans_loss_offset
         self.pg, self.world = process_group, world_size
+        self.all_params = self.params + self.admm_params
         dev = self.params[0].device
-        allp = self.params + self.admm_params
-        self.gflat = torch.zeros(sum(p.numel() for p in allp), dtype=torch.float32, device=dev)
-        off = 0
-        for p in allp:
-            p.grad = self.gflat[off: off + p.numel()].view_as(p)
-            off += p.numel()
-        self.n_main = sum(p.numel() for p in self.params)
         self.graph = None
         self.static_x = self.static_t = None
         self.loss = torch.zeros((), device=dev)
 
     # -- one eager iteration -------------------------------------------------------------------
     def _iteration(self, x, t):
-        self.gflat.zero_()                                         # optimizer.zero_grad(), one memset
+        for p in self.all_params:                                  # optimizer.zero_grad(): autograd then hands
+            p.grad = None                                          # over its gradient buffers without an add
         if self.bank is not None:
             self.bank.quantize_all()
         out = self.model(x)
@@ -105,10 +107,21 @@ class QATStep:
         else:
             ce = F.cross_entropy(out, t)
             ce.backward()
-        if self.world > 1:                                         # ONE collective per step over NVLink
-            allreduce_mean_(self.gflat[: self.n_main], self.pg, self.world)
+        scale = 1.0
+        if self.world > 1:                                         # ONE collective per step over NVLink:
+            owners = [p for p in self.params if p.grad is not None]
+            for p in owners:                                       # gather (physical order) -> all-reduce -> views
+                if p.grad.stride() != p.stride():
+                    p.grad = torch.empty_like(p).copy_(p.grad)
+            flat = torch.cat([L.phys(p.grad) for p in owners])
+            allreduce_sum_(flat, self.pg)
+            off = 0
+            for p in owners:
+                p.grad = torch.as_strided(flat, p.shape, p.stride(), off)
+                off += p.numel()
+            scale = 1.0 / self.world                               # the mean is folded into the SGD kernel
         idx, w_cdf, w_pdf = collect_sgd_args(self.model, self.params)
-        self.opt.step(idx, w_cdf, w_pdf, self.lam, self.lam2)
+        self.opt.step(idx, w_cdf, w_pdf, self.lam, self.lam2, grad_scale=scale)
         if self.opt_admm is not None:
             self.opt_admm.step(*collect_admm_args(self.model, self.admm_params))
         if self.bank is not None:

@@ -26,7 +26,7 @@ class _BankSliceFn(torch.autograd.Function):
         ctx.bank, ctx.i = bank, i
         ctx.save_for_backward(w)
         ctx.set_materialize_grads(False)
-        return bank.wq[i].view_as(w)
+        return bank.wq[i]
 
     @staticmethod
     def backward(ctx, g):
@@ -34,7 +34,7 @@ class _BankSliceFn(torch.autograd.Function):
             return None, None, None
         (w,) = ctx.saved_tensors
         bank, i = ctx.bank, ctx.i
-        g = L.dev_f32(g, "grad of quantized weight")
+        g = L.like_layout(g, w, "grad of quantized weight")
         seg_off, chunk_seg, seg_chunk0, nchunks = _single_plan(w.numel(), w.device)
         gw = torch.empty_like(w)
         ws = torch.empty(2 * max(nchunks, 1), dtype=torch.float64, device=w.device)
@@ -67,10 +67,12 @@ class WeightBank:
         sizes = [p.numel() for p in params]
         self.flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
         off = 0
-        for p in params:                                   # re-point every parameter at its slice
-            n = p.numel()
-            self.flat[off: off + n].copy_(p.data.reshape(-1))
-            p.data = self.flat[off: off + n].view_as(p)
+        for p in params:                                   # re-point every parameter at its slice (same shape,
+            n = p.numel()                                  # same strides: NCHW-contiguous or channels_last)
+            if not L.is_dense(p.data):
+                p.data = p.data.contiguous()
+            self.flat[off: off + n].copy_(L.phys(p.data))
+            p.data = torch.as_strided(self.flat, p.shape, p.stride(), off)
             off += n
         seg_off, chunk_seg, seg_chunk0, self.nchunks = L.plan_chunks(sizes)
         self.seg_off_host = seg_off
@@ -82,7 +84,7 @@ class WeightBank:
         self.pdf_flat = torch.empty_like(self.flat)
         self.stats = torch.empty(4 * len(params), dtype=torch.float32, device=dev)
         self.ws = torch.empty(2 * self.nchunks, dtype=torch.float64, device=dev)
-        view = lambda flat: [flat[seg_off[i]: seg_off[i + 1]] for i in range(len(params))]
+        view = lambda flat: [torch.as_strided(flat, p.shape, p.stride(), seg_off[i]) for i, p in enumerate(params)]
         self.wq, self.cdf, self.pdf = view(self.wq_flat), view(self.cdf_flat), view(self.pdf_flat)
         self.fresh = False
         for i, q in enumerate(self.fns):
@@ -104,8 +106,8 @@ class WeightBank:
         q = self.fns[i]
         wq = _BankSliceFn.apply(w, self, i)
         q.weight_q = wq
-        q.weight_cdf = self.cdf[i].view_as(w) if args.store_weight_attrs else None
-        q.weight_pdf = self.pdf[i].view_as(w) if args.store_weight_attrs else None
+        q.weight_cdf = self.cdf[i] if args.store_weight_attrs else None
+        q.weight_pdf = self.pdf[i] if args.store_weight_attrs else None
         return wq
 
     def release(self):

@@ -47,6 +47,20 @@ def peaks():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic_bytes():
+    """DRAM bytes of one fwd + one bwd launch from the committed `ncu --set full` capture (or None)."""
+    try:
+        rows = json.load(open(os.path.join(REPO, "profiles", "r01_ncu_full_act_kernels.json")))
+        tot = 0.0
+        for r in rows:
+            for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                v, unit = r[k].split()
+                tot += float(v) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[unit]
+        return tot
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------------
 # CPU baseline: the oracle's port of the reference training iteration (kind = "port")
 # ------------------------------------------------------------------------------------------------
@@ -164,7 +178,7 @@ def run_product(args):
     model = resnet20_quant(8, 8, "second").to(dev).train()
     if world > 1 and args.sync_bn:
         model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
-    step = QATStep(model, lr=0.04, momentum=0.9, weight_decay=1e-4, world_size=world)
+    step = QATStep(model, lr=0.04, momentum=0.9, weight_decay=1e-4, world_size=world, channels_last=not args.nchw)
 
     g = torch.Generator().manual_seed(1234 + rank)         # each rank its own shard of the synthetic batch
     n_host = 8
@@ -258,7 +272,9 @@ def run_product(args):
         peak, how = peaks()
         achieved = 20.0 * n / ((tf + tb) * 1e-3) / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": how,
+                    "traffic": ncu_traffic_bytes(), "traffic_source": "profiles/r01_ncu_full_act_kernels.json "
+                    "(dram__bytes_read.sum + dram__bytes_write.sum of one fwd + one bwd launch on this input; "
+                    "algorithmic = 5.369e9 B)", "peak_source": how,
                     "kernel": "act_fwd_vec_kernel + act_bwd_vec_kernel (CDF quantizer fwd + fused STE bwd)",
                     "algorithmic_bytes_per_elem": 20, "elems_per_launch": n,
                     "fwd": {"ms": tf, "gbs": 8.0 * n / (tf * 1e-3) / 1e9, "frac": 8.0 * n / (tf * 1e-3) / 1e9 / peak},

@@ -129,7 +129,8 @@ int alignq_admm_zu_update(float* Z, float* U, const float* D, int B, int dim, in
                           float mu, float rho, alignq_stream_t stream);
 
 /* ---- multi-tensor SGD with the quantization-aware gradient surrogate --------------------------
- * SGD.step(idx, w_cdf, w_pdf, lam, lam2) (OPT:196-262): d_p = g + wd p (in place on g);
+ * SGD.step(idx, w_cdf, w_pdf, lam, lam2) (OPT:196-262): d_p = grad_scale g + wd p (in place on g;
+ * grad_scale = 1 reproduces the reference, 1/world_size averages a summed data-parallel gradient);
  * buf = mom buf + (1-damp) d_p (first step: buf = d_p); d_p = nesterov ? d_p + mom buf : buf;
  * p -= lr d_p; g <- d_p, or for tensors with w_cdf != NULL:
  * g <- d_p * sigmoid'(((w_cdf+0.5)(2^bitW-1) mod 1) 2 lam2) lam * w_pdf (OPT:6-13, 232-249).
@@ -147,7 +148,7 @@ typedef struct alignq_sgd_tensor {
 } alignq_sgd_tensor_t;
 int alignq_sgd_step(const alignq_sgd_tensor_t* tensors, const int32_t* chunk_tensor,
                     const int32_t* tensor_chunk0, int ntensors, int64_t nchunks,
-                    float lam, float lam2, int bitW, alignq_stream_t stream);
+                    float lam, float lam2, int bitW, float grad_scale, alignq_stream_t stream);
 
 /* ---- bf16 Gram on the tensor cores (TMA + tcgen05, split-K) ---------------------------------------
  * G = X X^T (divided by F if divide_by_F) for X [B <= 256, F] bf16 row-major, F % 8 == 0, 16-byte
@@ -164,7 +165,8 @@ int alignq_gram_bf16(const void* x_bf16, int B, int64_t F, int divide_by_F, floa
  * `self.relu(self.act_q0(self.bn1(x)))` (cdf_alignment/dense-cifar-10/model/densenet.py:32-34).
  * x, y, gy, gx: [rows = B*H*W, C] fp32 with C contiguous (channels_last), 16-byte aligned, C % 4 == 0,
  * C <= 1024.  training != 0: batch statistics (biased variance), running_mean/var updated with
- * `momentum` (unbiased variance) unless NULL; training == 0: running statistics.  save_mean /
+ * `momentum` (unbiased variance) unless NULL, *num_batches_tracked += 1 unless NULL; training == 0:
+ * running statistics.  save_mean /
  * save_invstd: [C] out (forward) / in (backward).  ws: alignq_bn_act_ws_doubles(C) doubles and
  * counter: one uint32 -- both must be ZERO before the first call (the kernels re-arm them).
  * Backward: g_z = gy [y > 0 if relu] * 2 ar phi(z) (z = BN output), then the BatchNorm backward;
@@ -173,7 +175,8 @@ size_t alignq_bn_act_ws_doubles(int C);
 int alignq_bn_act_fwd(const float* x, int64_t rows, int C, const float* gamma, const float* beta,
                       float* running_mean, float* running_var, float momentum, float bn_eps, int training,
                       int a_bit, float act_range, int variant, int relu, float* y, float* save_mean,
-                      float* save_invstd, double* ws, uint32_t* counter, alignq_stream_t stream);
+                      float* save_invstd, double* ws, uint32_t* counter, int64_t* num_batches_tracked,
+                      alignq_stream_t stream);
 int alignq_bn_act_bwd(const float* x, const float* y, const float* gy, int64_t rows, int C,
                       const float* gamma, const float* beta, const float* save_mean, const float* save_invstd,
                       int training, int a_bit, float act_range, int variant, int relu, float* gx,

@@ -12,7 +12,7 @@ torch.backends.cudnn.benchmark = True
 aq.set_args(variant="A", bitW=8, abitW=8, act_range=2, train_batch_size=128, fuse_bn_act=fuse)
 torch.manual_seed(0)
 model = resnet20_quant(8, 8, "second").to(dev).train()
-step = QATStep(model)
+step = QATStep(model, channels_last=True)
 x = torch.randn(128, 3, 32, 32, device=dev).contiguous(memory_format=torch.channels_last)
 t = torch.randint(0, 10, (128,), device=dev)
 for _ in range(5): step.step(x, t)

@@ -175,15 +175,33 @@ def run_product(args):
     aq.set_args(variant="A", bitW=8, abitW=8, act_range=2, lam=1.0, lam2=4.0, method="ours", train_batch_size=BATCH,
                 fuse_bn_act=fuse)
     torch.manual_seed(0)                                   # identical replicas on every rank
-    model = resnet20_quant(8, 8, "second").to(dev).train()
+    batch = BATCH
+    if args.workload == "resnet20":
+        model = resnet20_quant(8, 8, "second")
+    elif args.workload == "resnet56_admm":                 # configs[1]: QB, W8A8 + ADMM correlation preservation
+        from alignq_b200.model.resnet import resnet56_quant
+        aq.set_args(variant="B", gram_mode=args.gram_mode, fuse_bn_act=False)
+        model = resnet56_quant(8, 8, "second")
+        CONFIG.update(workload=f"resnet56_quant W8A8 (QB) + ADMM, gram_mode={args.gram_mode}, CIFAR-10 synthetic, QAT step", variant="B")
+    elif args.workload == "mobilenetv2":                   # configs[2]: W4A4, depthwise convs, batch 256
+        from alignq_b200.model.mobilenetV2 import mobile_v2
+        batch = 256
+        aq.set_args(bitW=4, abitW=4, train_batch_size=batch, fuse_bn_act=False)
+        model = mobile_v2(4, 4, "second")
+        CONFIG.update(workload="mobile_v2 W4A4 (QA) SVHN synthetic 32x32, QAT step", bitW=4, abitW=4, per_gpu_batch=batch)
+    else:                                                  # configs[3]: DenseNet-40 (k=12) W8A8
+        from alignq_b200.model.densenet import densenet_40_quant
+        model = densenet_40_quant(8, 8, "second")
+        CONFIG.update(workload="densenet_40_quant W8A8 (QA) CIFAR-10 synthetic, QAT step")
+    model = model.to(dev).train()
     if world > 1 and args.sync_bn:
         model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
     step = QATStep(model, lr=0.04, momentum=0.9, weight_decay=1e-4, world_size=world, channels_last=not args.nchw)
 
     g = torch.Generator().manual_seed(1234 + rank)         # each rank its own shard of the synthetic batch
     n_host = 8
-    host_x = [torch.randn(BATCH, 3, 32, 32, generator=g).pin_memory() for _ in range(n_host)]
-    host_t = [torch.randint(0, 10, (BATCH,), generator=g).pin_memory() for _ in range(n_host)]
+    host_x = [torch.randn(batch, 3, 32, 32, generator=g).pin_memory() for _ in range(n_host)]
+    host_t = [torch.randint(0, 10, (batch,), generator=g).pin_memory() for _ in range(n_host)]
     fmt = torch.contiguous_format if args.nchw else torch.channels_last
     host_x = [h.contiguous(memory_format=fmt).pin_memory() for h in host_x]
     dev_x = [h.to(dev) for h in host_x]
@@ -246,8 +264,8 @@ def run_product(args):
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(tt[0]), float(tt[1])
-    value = world * BATCH * args.steps / (ms * 1e-3)
-    e2e = world * BATCH * args.steps / (ms_e2e * 1e-3)
+    value = world * batch * args.steps / (ms * 1e-3)
+    e2e = world * batch * args.steps / (ms_e2e * 1e-3)
 
     roofline = cpu = gram = None
     if rank == 0:
@@ -306,7 +324,7 @@ def run_product(args):
             del xg, Gg, wsg
         except Exception as e:                              # pragma: no cover
             gram = {"error": str(e)[:200]}
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.workload == "resnet20":
             cb = cpu_reference_run(3, 1, budget_s=30.0)
             cpu = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
@@ -314,12 +332,12 @@ def run_product(args):
         line = {"metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": dict(CONFIG, global_batch=BATCH * world, parallelism=f"dp{world}", cuda_graph=graphed,
+                "config": dict(CONFIG, global_batch=batch * world, parallelism=f"dp{world}", cuda_graph=graphed,
                                activation_layout="nchw" if args.nchw else "channels_last", fused_bn_act=fuse,
                                sync_bn=bool(args.sync_bn and world > 1),
                                l2="flushed between timed steps (256 MiB memset, outside the event pairs)"),
                 "e2e": {"value": e2e, "unit": "img/s", "ms_per_step": ms_e2e / args.steps,
-                        "h2d_bytes_per_step": BATCH * 3 * 32 * 32 * 4 + BATCH * 8, "d2h_bytes_per_step": 4},
+                        "h2d_bytes_per_step": batch * 3 * 32 * 32 * 4 + batch * 8, "d2h_bytes_per_step": 4},
                 "gpu_launches": int(launches_per_step) * args.steps,
                 "gpu_launches_per_step": int(launches_per_step),
                 "clocks": clocks, "roofline": roofline, "gram_tensor_roofline": gram, "cpu_baseline": cpu}
@@ -340,6 +358,10 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", type=str, default="resnet20", choices=["resnet20", "resnet56_admm", "mobilenetv2", "densenet40"],
+                    help="default resnet20 = BASELINE.json configs[0] (the metric's workload); the others are configs[1..3], "
+                    "for the record only (their JSON line says so in config.workload)")
+    ap.add_argument("--gram-mode", type=str, default="tf32x3", choices=["fp32", "tf32x3", "bf16"])
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--sync-bn", action="store_true", help="N>1: SyncBatchNorm (global-batch BN statistics)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -237,7 +237,7 @@ class _ActAdmmFn(torch.autograd.Function):
     """y, trans_loss, D = fused activation quantizer + corr(x) / corr(t) + ADMM loss."""
 
     @staticmethod
-    def forward(ctx, x, alterD, gamma, a_bit, act_range, eps, mu, rho, gram_mode):
+    def forward(ctx, x, alterD, gamma, a_bit, act_range, eps, mu, rho, gram_mode, variant_id=1):
         xc = L.dev_f32_dense(x, "activation")      # per-sample feature order is irrelevant to the Gram
         Z = L.dev_f32(alterD, "alterD")
         U = L.dev_f32(gamma, "gamma")
@@ -257,35 +257,47 @@ class _ActAdmmFn(torch.autograd.Function):
                 y.data_ptr(), D.data_ptr(), loss.data_ptr(), dLdD.data_ptr(), ws.data_ptr(), ws.numel(),
                 gram_mode, L.stream_ptr()), "alignq_act_admm_fwd")
         ctx.save_for_backward(xc, dLdD, D, Z, U)
-        ctx.cfg = (a_bit, act_range, eps, mu, rho, gram_mode)
+        ctx.cfg = (a_bit, act_range, eps, mu, rho, gram_mode, variant_id)
         ctx.mark_non_differentiable(D)
+        ctx.set_materialize_grads(False)       # a backward pass that does not reach trans_loss skips the Gram backward
         return y, loss, D
 
     @staticmethod
     def backward(ctx, gy, gloss, _gD):
         xc, dLdD, D, Z, U = ctx.saved_tensors
-        a_bit, act_range, eps, mu, rho, gram_mode = ctx.cfg
+        a_bit, act_range, eps, mu, rho, gram_mode, variant_id = ctx.cfg
         B = xc.shape[0]
         Fdim = xc.numel() // B
         dim = Z.shape[0]
         lib = L.load()
         gx = gZ = gU = None
-        gl = L.dev_f32(gloss.reshape(1), "grad of trans_loss")
         with torch.cuda.device_of(xc):
+            if gloss is None:
+                # this backward pass does not involve trans_loss (e.g. CE.backward(retain_graph=True) in
+                # cdf_alignment_admm/.../main.py:300): only the straight-through quantizer backward remains
+                if gy is not None and ctx.needs_input_grad[0]:
+                    gyc = L.like_layout(gy, xc, "grad of quantized activation")
+                    gx = torch.empty_like(xc)
+                    L.check(lib.alignq_act_bwd(xc.data_ptr(), gyc.data_ptr(), gx.data_ptr(), xc.numel(), a_bit,
+                                               act_range, variant_id, 0, L.stream_ptr()), "alignq_act_bwd")
+                return gx, None, None, None, None, None, None, None, None, None
+            gl = L.dev_f32(gloss.reshape(1), "grad of trans_loss")
             if ctx.needs_input_grad[0]:
-                gyc = L.like_layout(gy, xc, "grad of quantized activation")
+                gyc = None if gy is None else L.like_layout(gy, xc, "grad of quantized activation")
                 gx = torch.empty_like(xc)
                 ws = _gram_ws(B, Fdim, xc.device)
                 L.check(lib.alignq_act_admm_bwd(
-                    xc.data_ptr(), gyc.data_ptr(), dLdD.data_ptr(), gl.data_ptr(), B, Fdim, a_bit, act_range, eps,
+                    xc.data_ptr(), L.ptr(gyc), dLdD.data_ptr(), gl.data_ptr(), B, Fdim, a_bit, act_range, eps,
                     gx.data_ptr(), ws.data_ptr(), ws.numel(), gram_mode, L.stream_ptr()), "alignq_act_admm_bwd")
-            if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
-                gZ = torch.empty_like(Z) if ctx.needs_input_grad[1] else None
-                gU = torch.empty_like(U) if ctx.needs_input_grad[2] else None
+            want_z = ctx.needs_input_grad[1] and args.admm_param_grads
+            want_u = ctx.needs_input_grad[2] and args.admm_param_grads
+            if want_z or want_u:
+                gZ = torch.empty_like(Z) if want_z else None
+                gU = torch.empty_like(U) if want_u else None
                 L.check(lib.alignq_admm_loss(D.data_ptr(), B, Z.data_ptr(), U.data_ptr(), dim, 1, mu, rho,
                                              gl.data_ptr(), 0, 0, 0, L.ptr(gZ), L.ptr(gU), L.stream_ptr()),
                         "alignq_admm_loss (parameter grads)")
-        return gx, gZ, gU, None, None, None, None, None, None
+        return gx, gZ, gU, None, None, None, None, None, None, None
 
 
 class activation_quantize_fn(nn.Module):
@@ -316,7 +328,7 @@ class activation_quantize_fn(nn.Module):
             eps = 0.0 if self.variant == "B" else 1e-5
             y, loss, D = _ActAdmmFn.apply(x, self.opt.alterD, self.opt.gamma, self.a_bit, float(args.act_range),
                                           eps, float(self.opt.mu), float(self.opt.rho),
-                                          L.GRAM_MODE_ID[args.gram_mode])
+                                          L.GRAM_MODE_ID[args.gram_mode], L.VARIANT_ID[self.variant])
             self.opt.D = D
             return y, loss
         y = self._plain(x)

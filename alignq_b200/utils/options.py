@@ -10,7 +10,9 @@ Extra fields (no reference counterpart): ``variant`` selects which of the three 
 variants the math follows ('A' = cdf_alignment/*, 'B' = cdf_alignment_admm/resnet-*,
 'C' = cdf_alignment_admm/{dann,dsan}_office); ``gram_mode`` picks the Gram numerics
 ('fp32' FFMA parity mode, 'tf32x3' / 'bf16' tcgen05 modes); ``fuse_bn_act`` lets the model files run
-BatchNorm -> activation quantizer -> ReLU as one fused kernel pair on channels_last inputs.
+BatchNorm -> activation quantizer -> ReLU as one fused kernel pair on channels_last inputs;
+``admm_param_grads=False`` skips d trans_loss / d(alterD, gamma), which ``ADMM_OPT`` never reads
+(it applies closed-form Z/U updates, optimizer.py:97-124).
 """
 from __future__ import annotations
 
@@ -20,7 +22,7 @@ from types import SimpleNamespace
 _DEFAULTS = dict(
     gpus=[0], bitW=2, abitW=2, act_range=2, lam=1.0, lam2=4.0, method="ours", stage="second",
     train_batch_size=128, eval_batch_size=100, lr=0.04, momentum=0.9, weight_decay=1e-4,
-    variant="A", gram_mode="fp32", store_weight_attrs=True, fuse_bn_act=False,
+    variant="A", gram_mode="fp32", store_weight_attrs=True, fuse_bn_act=False, admm_param_grads=True,
 )
 
 args = SimpleNamespace(**_DEFAULTS)

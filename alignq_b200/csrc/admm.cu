@@ -3,16 +3,23 @@
 //
 // Replaces ADMM.forward (utils/admm.py:24-33) and the alterD/gamma branches of ADMM_OPT.step
 // (utils/optimizer.py:97-124; the reference evaluates `if torch.norm(V, 2) > mu/rho` on the host).
-// All matrices are [B, B] with B <= dim; a single 1024-thread CTA per ADMM module keeps every
-// reduction in one SM -- these are latency-bound O(B^2) kernels (<= 256 KB), batched over modules
-// through gridDim.x.
+// All matrices are [B, B] with B <= dim (<= 256 KB): latency-bound O(B^2) work, but one SM's L2
+// bandwidth (~120 GB/s) would make a single CTA take ~15 us.  Each ADMM module is therefore handled
+// by one thread-block CLUSTER of 8 CTAs (8 SMs): every CTA reduces its slice, the partial sums are
+// exchanged through distributed shared memory (cluster.map_shared_rank + cluster.sync), and every CTA
+// then applies the second pass to its slice.  Modules are batched through gridDim.x (= 8 * nmod).
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "gram_common.cuh"
 #include "../../include/alignq_b200.h"
 
 namespace alignq {
 
-constexpr int AT = 1024;
+namespace cg = cooperative_groups;
+
+constexpr int AT = 512;           // threads per CTA
+constexpr int ACL = 8;            // CTAs per cluster (one cluster per ADMM module)
 
 template <typename T>
 __device__ __forceinline__ T block_sum1(T v, T* scratch) {
@@ -23,6 +30,30 @@ __device__ __forceinline__ T block_sum1(T v, T* scratch) {
   __syncthreads();
   v = (lane < nw) ? scratch[lane] : T(0);
   return warp_sum(v);
+}
+
+// Cluster-wide sum of NV doubles: block reduce, deposit into rank 0's shared array through DSMEM,
+// cluster.sync, everyone reads the totals back from rank 0.  part: __shared__ double[ACL * NV] per CTA.
+template <int NV>
+__device__ __forceinline__ void cluster_sum(double (&v)[NV], double* part, double* scratch) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned rank = cluster.block_rank();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = block_sum1(v[i], scratch);
+  cluster.sync();                        // every CTA of the cluster is resident before remote smem is touched
+  double* root = cluster.map_shared_rank(part, 0);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) root[rank * NV + i] = v[i];
+  }
+  cluster.sync();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    double t = 0.0;
+    for (int r = 0; r < ACL; ++r) t += root[r * NV + i];
+    v[i] = t;
+  }
+  cluster.sync();                        // rank 0's array may be reused after everyone has read it
 }
 
 // G = sum_slab P / F   (fused: D = G_t - G_x as two separately rounded fp32 results, QB:118-122)
@@ -51,35 +82,36 @@ wsym_kernel(const float* __restrict__ dLdD, int B, int Bp, float* __restrict__ W
   W[e] = (i < B && j < B) ? dLdD[(size_t)i * B + j] + dLdD[(size_t)j * B + i] : 0.f;
 }
 
-__global__ void __launch_bounds__(AT)
+__global__ void __cluster_dims__(ACL, 1, 1) __launch_bounds__(AT)
 admm_loss_kernel(const float* __restrict__ D, int B, const float* __restrict__ Z, const float* __restrict__ U, int dim,
                  float mu, float rho, const float* __restrict__ gloss, int gloss_per_module,
                  float* __restrict__ loss, float* __restrict__ dLdD, float* __restrict__ dLdZ, float* __restrict__ dLdU) {
   __shared__ double scratch[32];
-  const int m = blockIdx.x;
+  __shared__ double part[ACL * 3];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int m = blockIdx.x / ACL;
   const float* Dm = D + (size_t)m * B * B;
   const float* Zm = Z + (size_t)m * dim * dim;
   const float* Um = U + (size_t)m * dim * dim;
   const int bb = B * B;
-  double sz = 0.0, sr2 = 0.0, sur = 0.0;
-  for (int e = threadIdx.x; e < bb; e += AT) {
+  double s[3] = {0.0, 0.0, 0.0};                            // sum |Z|, sum R^2, sum U |R| over this CTA's slice
+  for (int e = rank * AT + threadIdx.x; e < bb; e += ACL * AT) {
     const int i = e / B, j = e - i * B;
     const float z = Zm[(size_t)i * dim + j], u = Um[(size_t)i * dim + j];
     const float r = __fsub_rn(Dm[e], z);
-    sz += (double)fabsf(z);
-    sr2 += (double)__fmul_rn(r, r);
-    sur += (double)__fmul_rn(u, fabsf(r));
+    s[0] += (double)fabsf(z);
+    s[1] += (double)__fmul_rn(r, r);
+    s[2] += (double)__fmul_rn(u, fabsf(r));
   }
-  sz = block_sum1(sz, scratch);
-  sr2 = block_sum1(sr2, scratch);
-  sur = block_sum1(sur, scratch);
+  cluster_sum<3>(s, part, scratch);
   const float inv_bb = 1.0f / (float)bb;
-  const float mean_r2 = (float)(sr2 / bb);
+  const float mean_r2 = (float)(s[1] / bb);
   const float rms = sqrtf(mean_r2);                               // mean(...) ** 0.5
-  if (threadIdx.x == 0 && loss) {
-    const float reg = mu * (float)(sz / bb);
+  if (rank == 0 && threadIdx.x == 0 && loss) {
+    const float reg = mu * (float)(s[0] / bb);
     const float con = (rho / 2.0f) * rms;
-    loss[m] = (reg + con) + (float)(sur / bb);
+    loss[m] = (reg + con) + (float)(s[2] / bb);
   }
   if (dLdD || dLdZ || dLdU) {
     // d/dD [rho/2 sqrt(mean R^2)] = rho/2 * R / (B^2 rms);  d/dD mean(U |R|) = U sign(R) / B^2
@@ -89,7 +121,7 @@ admm_loss_kernel(const float* __restrict__ D, int B, const float* __restrict__ Z
     float* GD = dLdD ? dLdD + (size_t)m * bb : nullptr;
     float* GZ = dLdZ ? dLdZ + (size_t)m * dim * dim : nullptr;
     float* GU = dLdU ? dLdU + (size_t)m * dim * dim : nullptr;
-    for (int e = threadIdx.x; e < dim * dim; e += AT) {
+    for (int e = rank * AT + threadIdx.x; e < dim * dim; e += ACL * AT) {
       const int i = e / dim, j = e - i * dim;
       if (i < B && j < B) {
         const float z = Zm[e], u = Um[e];
@@ -107,27 +139,30 @@ admm_loss_kernel(const float* __restrict__ D, int B, const float* __restrict__ Z
   }
 }
 
-__global__ void __launch_bounds__(AT)
+__global__ void __cluster_dims__(ACL, 1, 1) __launch_bounds__(AT)
 admm_zu_kernel(float* __restrict__ Z, float* __restrict__ U, const float* __restrict__ D, int B, int dim,
                float mu_over_rho, float inv_rho, float rho) {
   __shared__ double scratch[32];
-  const int m = blockIdx.x;
+  __shared__ double part[ACL];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int m = blockIdx.x / ACL;
   float* Zm = Z + (size_t)m * dim * dim;
   float* Um = U + (size_t)m * dim * dim;
   const float* Dm = D + (size_t)m * B * B;
   const int dd = dim * dim;
-  double ss = 0.0;
-  for (int e = threadIdx.x; e < dd; e += AT) {
+  double ss[1] = {0.0};
+  for (int e = rank * AT + threadIdx.x; e < dd; e += ACL * AT) {
     const int i = e / dim, j = e - i * dim;
     const float d = (i < B && j < B) ? Dm[(size_t)i * B + j] : 0.f;
     const float v = __fadd_rn(d, __fmul_rn(inv_rho, Um[e]));       // V = D_ + 1/rho * gamma
-    ss += (double)v * (double)v;
+    ss[0] += (double)v * (double)v;
   }
-  ss = block_sum1(ss, scratch);
-  const float nv = (float)sqrt(ss);                               // torch.norm(V, 2): Frobenius
+  cluster_sum<1>(ss, part, scratch);
+  const float nv = (float)sqrt(ss[0]);                            // torch.norm(V, 2): Frobenius
   const bool shrink = nv > mu_over_rho;
   const float coef = __fsub_rn(1.0f, __fmul_rn(__frcp_rn(nv), mu_over_rho));   // 1 - mu/rho / ||V||
-  for (int e = threadIdx.x; e < dd; e += AT) {
+  for (int e = rank * AT + threadIdx.x; e < dd; e += ACL * AT) {
     const int i = e / dim, j = e - i * dim;
     const float d = (i < B && j < B) ? Dm[(size_t)i * B + j] : 0.f;
     const float u = Um[e];
@@ -162,7 +197,7 @@ extern "C" int alignq_admm_loss(const float* D, int B, const float* Z, const flo
   if (B < 1 || dim < B || nmod < 0 || dim > 4096) return ALIGNQ_EINVAL;
   if (nmod == 0) return ALIGNQ_OK;
   if (!D || !Z || !U) return ALIGNQ_EINVAL;
-  admm_loss_kernel<<<nmod, AT, 0, reinterpret_cast<cudaStream_t>(stream)>>>(D, B, Z, U, dim, mu, rho, gloss,
+  admm_loss_kernel<<<nmod * ACL, AT, 0, reinterpret_cast<cudaStream_t>(stream)>>>(D, B, Z, U, dim, mu, rho, gloss,
                                                                            gloss_per_module, loss, dLdD, dLdZ, dLdU);
   ALIGNQ_LAUNCH_CHECK();
   return ALIGNQ_OK;
@@ -176,7 +211,7 @@ extern "C" int alignq_admm_zu_update(float* Z, float* U, const float* D, int B, 
   // python: mu / rho and 1 / rho are evaluated in double, then become fp32 scalars of the tensor ops
   const float mu_over_rho = (float)((double)mu / (double)rho);
   const float inv_rho = (float)(1.0 / (double)rho);
-  admm_zu_kernel<<<nmod, AT, 0, reinterpret_cast<cudaStream_t>(stream)>>>(Z, U, D, B, dim, mu_over_rho, inv_rho, rho);
+  admm_zu_kernel<<<nmod * ACL, AT, 0, reinterpret_cast<cudaStream_t>(stream)>>>(Z, U, D, B, dim, mu_over_rho, inv_rho, rho);
   ALIGNQ_LAUNCH_CHECK();
   return ALIGNQ_OK;
 }

@@ -237,7 +237,7 @@ class _ActAdmmFn(torch.autograd.Function):
     """y, trans_loss, D = fused activation quantizer + corr(x) / corr(t) + ADMM loss."""
 
     @staticmethod
-    def forward(ctx, x, alterD, gamma, a_bit, act_range, eps, mu, rho, gram_mode, variant_id=1):
+    def forward(ctx, x, alterD, gamma, a_bit, act_range, eps, mu, rho, gram_mode, variant_id=1, d_out=None):
         xc = L.dev_f32_dense(x, "activation")      # per-sample feature order is irrelevant to the Gram
         Z = L.dev_f32(alterD, "alterD")
         U = L.dev_f32(gamma, "gamma")
@@ -247,7 +247,8 @@ class _ActAdmmFn(torch.autograd.Function):
         if Z.shape != (dim, dim) or U.shape != (dim, dim) or dim < B:
             raise L.AlignQError(f"ADMM dim {tuple(Z.shape)} must be square and >= batch {B}")
         y = torch.empty_like(xc)
-        D = torch.empty(B, B, dtype=torch.float32, device=xc.device)
+        D = d_out if (d_out is not None and d_out.shape == (B, B) and d_out.is_contiguous()) \
+            else torch.empty(B, B, dtype=torch.float32, device=xc.device)
         dLdD = torch.empty_like(D)
         loss = torch.empty((), dtype=torch.float32, device=xc.device)
         ws = _gram_ws(B, Fdim, xc.device)
@@ -280,7 +281,7 @@ class _ActAdmmFn(torch.autograd.Function):
                     gx = torch.empty_like(xc)
                     L.check(lib.alignq_act_bwd(xc.data_ptr(), gyc.data_ptr(), gx.data_ptr(), xc.numel(), a_bit,
                                                act_range, variant_id, 0, L.stream_ptr()), "alignq_act_bwd")
-                return gx, None, None, None, None, None, None, None, None, None
+                return gx, None, None, None, None, None, None, None, None, None, None
             gl = L.dev_f32(gloss.reshape(1), "grad of trans_loss")
             if ctx.needs_input_grad[0]:
                 gyc = None if gy is None else L.like_layout(gy, xc, "grad of quantized activation")
@@ -297,7 +298,7 @@ class _ActAdmmFn(torch.autograd.Function):
                 L.check(lib.alignq_admm_loss(D.data_ptr(), B, Z.data_ptr(), U.data_ptr(), dim, 1, mu, rho,
                                              gl.data_ptr(), 0, 0, 0, L.ptr(gZ), L.ptr(gU), L.stream_ptr()),
                         "alignq_admm_loss (parameter grads)")
-        return gx, gZ, gU, None, None, None, None, None, None, None
+        return gx, gZ, gU, None, None, None, None, None, None, None, None
 
 
 class activation_quantize_fn(nn.Module):
@@ -328,7 +329,8 @@ class activation_quantize_fn(nn.Module):
             eps = 0.0 if self.variant == "B" else 1e-5
             y, loss, D = _ActAdmmFn.apply(x, self.opt.alterD, self.opt.gamma, self.a_bit, float(args.act_range),
                                           eps, float(self.opt.mu), float(self.opt.rho),
-                                          L.GRAM_MODE_ID[args.gram_mode], L.VARIANT_ID[self.variant])
+                                          L.GRAM_MODE_ID[args.gram_mode], L.VARIANT_ID[self.variant],
+                                          getattr(self.opt, "_D_slot", None))
             self.opt.D = D
             return y, loss
         y = self._plain(x)

@@ -61,7 +61,7 @@ class QATStep:
 
     def __init__(self, model, lr=0.04, momentum=0.9, weight_decay=1e-4, lam=None, lam2=None,
                  trans_loss_offset=0.5, process_group=None, world_size=1, bank_weights=True,
-                 channels_last=False):
+                 channels_last=False, fast_admm=True):
         self.model = model
         if channels_last:                      # NHWC weights: cuDNN needs no layout conversion kernels
             for p in model.parameters():
@@ -79,6 +79,14 @@ class QATStep:
         self.admm_params = [p for n, p in named if "alterD" in n or "gamma" in n]
         self.opt = SGD(self.params, lr=lr, momentum=momentum, weight_decay=weight_decay)
         self.opt_admm = ADMM_OPT(self.admm_params) if self.admm_params else None
+        self.admm_bank = None
+        if self.admm_params and fast_admm:     # batched Z/U update; d loss / d(Z, U) is never read by ADMM_OPT
+            from .admm_bank import AdmmBank
+            try:
+                self.admm_bank = AdmmBank(model, args.train_batch_size)
+                args.admm_param_grads = False
+            except Exception:
+                self.admm_bank = None
         self.lam = args.lam if lam is None else lam
         self.lam2 = args.lam2 if lam2 is None else lam2
         self.offset = trans_loss_offset
@@ -122,7 +130,9 @@ class QATStep:
             scale = 1.0 / self.world                               # the mean is folded into the SGD kernel
         idx, w_cdf, w_pdf = collect_sgd_args(self.model, self.params)
         self.opt.step(idx, w_cdf, w_pdf, self.lam, self.lam2, grad_scale=scale)
-        if self.opt_admm is not None:
+        if self.admm_bank is not None and self.admm_bank.ready():
+            self.admm_bank.update()                                # all modules, one launch
+        elif self.opt_admm is not None:
             self.opt_admm.step(*collect_admm_args(self.model, self.admm_params))
         if self.bank is not None:
             self.bank.fresh = False                                # weights changed: slices are stale

@@ -67,9 +67,11 @@ extern "C" int alignq_act_admm_bwd(const float* x, const float* gy, const float*
   if (!x || !dLdD || !gx || !ws) return ALIGNQ_EINVAL;
   if (ws_bytes < gram_wsym_floats(B) * sizeof(float)) return ALIGNQ_ENOSPACE;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  (void)gram_mode;      // the backward products run on the fp32 path in every mode
   float* Wsym = reinterpret_cast<float*>(ws);
   int rc = launch_wsym(dLdD, B, Wsym, s);
   if (rc) return rc;
+  if (gram_mode != ALIGNQ_GRAM_FP32 && B <= 128 && aligned16(x) && (F % 4) == 0)      // tensor-core products
+    return gram_tc_backward(x, gy, Wsym, gram_bp(B), gloss, B, F, act_range, eps, gx,
+                            gram_mode == ALIGNQ_GRAM_TF32X3 ? 1 : 0, s);
   return gram_ffma_backward(x, gy, Wsym, gram_bp(B), gloss, B, F, act_range, eps, gx, s);
 }

@@ -487,8 +487,17 @@ def test_tc_fused_forward_vs_fp32_mode_and_oracle(mode, variant, B, shape):
     assert dl <= (1e-5 if mode == "tf32x3" else 2e-2)
     _, lo, Do = O.activation_quantize_admm(x0, 8, admm.alterD.detach(), admm.gamma.detach(), "second", variant, 2.0)
     assert float((res[mode][2] - Do).abs().max()) / gmax <= 2 * TC_TOL[mode]
+    # backward: tcgen05 products with bf16 H+L operands (16 mantissa bits) in tf32x3 mode, bf16 in bf16 mode,
+    # against the fp32 FFMA backward; also against the oracle's autograd (tf32x3: the 1e-4 bar of the fp32 path)
     if mode == "tf32x3":
-        rel_close(res[mode][3], res["fp32"][3], rtol=1e-3, atol_frac=1e-4, what="gx (dLdD from the tf32x3 forward)")
+        rel_close(res[mode][3], res["fp32"][3], rtol=1e-4, atol_frac=2e-5, what="gx tcgen05 backward vs fp32 backward")
+        xo = x0.clone().requires_grad_(True)
+        yo, lo2, _ = O.activation_quantize_admm(xo, 8, admm.alterD.detach(), admm.gamma.detach(), "second", variant, 2.0)
+        ((yo * gy).sum() + lo2).backward()
+        rel_close(res[mode][3], xo.grad, rtol=1e-4, atol_frac=2e-5, what="gx tcgen05 backward vs oracle autograd")
+    else:
+        e = float((res[mode][3] - res["fp32"][3]).norm() / res["fp32"][3].norm())
+        assert e <= 1e-2, f"gx bf16 backward rel-norm err {e:.2e}"
 
 
 def test_channels_last_activations_need_no_layout_copy():
@@ -541,3 +550,25 @@ def test_gram_bf16_tma_tcgen05_vs_fp64(B, F):
     L.check(lib.alignq_gram_bf16(x.data_ptr(), B, F, 0, G.data_ptr(), ws.data_ptr(), ws.numel(), L.stream_ptr()), "gram_bf16")
     assert float((G.double() - ref * F).abs().max()) <= 1e-5 * float((ref * F).abs().max())
     assert lib.alignq_gram_bf16(x.data_ptr(), B, F - 1, 0, G.data_ptr(), ws.data_ptr(), ws.numel(), L.stream_ptr()) == -2   # F % 8
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", 2e-4), ("tf32x3", 5e-4), ("bf16", 3e-2)])
+@pytest.mark.parametrize("variant,B,shape", [("B", 128, (16, 16, 16)), ("C", 28, (32, 14, 14)), ("B", 100, (3, 11, 12))])
+def test_pure_admm_gradient_vs_oracle_autograd(mode, tol, variant, B, shape):
+    """d trans_loss / d x alone (no gradient through y): isolates the Gram backward -- the two [B,B]x[B,F]
+    products, the standardise backward and the chain through the CDF map -- from the much larger STE term."""
+    torch.manual_seed(15)
+    aq.set_args(variant=variant, act_range=2, method="ours", gram_mode=mode)
+    admm = aq.ADMM(128).to(DEV)
+    x0 = torch.randn(B, *shape, device=DEV)
+    Fn = aq.activation_quantize_fn if variant == "B" else aq.activation_quantize_fn2
+    x = x0.clone().requires_grad_(True)
+    _, loss = Fn(8, "second", admm)(x)
+    loss.backward()
+    xo = x0.double().clone().requires_grad_(True)
+    _, lo, _ = O.activation_quantize_admm(xo, 8, admm.alterD.detach().double(), admm.gamma.detach().double(),
+                                          "second", variant, 2.0)
+    lo.backward()
+    e = float((x.grad.double() - xo.grad).norm() / xo.grad.norm())
+    print(f"pure ADMM gradient {mode} {variant} B={B}: rel-norm err vs fp64 autograd {e:.2e}")
+    assert e <= tol

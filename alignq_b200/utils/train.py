@@ -61,7 +61,7 @@ class QATStep:
 
     def __init__(self, model, lr=0.04, momentum=0.9, weight_decay=1e-4, lam=None, lam2=None,
                  trans_loss_offset=0.5, process_group=None, world_size=1, bank_weights=True,
-                 channels_last=False, fast_admm=True):
+                 channels_last=False, fast_admm=True, single_backward=False):
         self.model = model
         if channels_last:                      # NHWC weights: cuDNN needs no layout conversion kernels
             for p in model.parameters():
@@ -90,6 +90,9 @@ class QATStep:
         self.lam = args.lam if lam is None else lam
         self.lam2 = args.lam2 if lam2 is None else lam2
         self.offset = trans_loss_offset
+        # reference: CE.backward(retain_graph=True) then trans_loss.backward() (resnet-56 main.py:300-307);
+        # cdf_alignment_admm/resnet-20-cifar-10/main.py:297-300 does ONE (CE + trans_loss).backward(): same sums
+        self.single_backward = single_backward
         self.pg, self.world = process_group, world_size
         self.all_params = self.params + self.admm_params
         dev = self.params[0].device
@@ -107,7 +110,9 @@ class QATStep:
         if isinstance(out, tuple):
             logits, trans_loss = out
             ce = F.cross_entropy(logits, t)
-            if torch.is_tensor(trans_loss):
+            if torch.is_tensor(trans_loss) and self.single_backward:
+                (ce + trans_loss + self.offset).backward()
+            elif torch.is_tensor(trans_loss):
                 ce.backward(retain_graph=True)                     # .../main.py:300-307
                 (trans_loss + self.offset).backward()
             else:

@@ -196,7 +196,8 @@ def run_product(args):
     model = model.to(dev).train()
     if world > 1 and args.sync_bn:
         model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
-    step = QATStep(model, lr=0.04, momentum=0.9, weight_decay=1e-4, world_size=world, channels_last=not args.nchw)
+    step = QATStep(model, lr=0.04, momentum=0.9, weight_decay=1e-4, world_size=world, channels_last=not args.nchw,
+                   single_backward=True)
 
     g = torch.Generator().manual_seed(1234 + rank)         # each rank its own shard of the synthetic batch
     n_host = 8

@@ -156,14 +156,19 @@ __device__ __forceinline__ void bwd_terms(float w, float g, float mean, float rs
 }
 
 __global__ void __launch_bounds__(kThreads)
-wq_bwd_partial_kernel(const float* __restrict__ flat, const float* __restrict__ g_wq,
+wq_bwd_partial_kernel(const float* __restrict__ flat, const float* g_wq,
                       const int64_t* __restrict__ seg_off, const int32_t* __restrict__ chunk_seg,
                       const int32_t* __restrict__ seg_chunk0, const float* __restrict__ stats,
-                      double* __restrict__ partials) {
+                      double* __restrict__ partials, const float* const* __restrict__ g_ptrs) {
   __shared__ double scratch[64];
   const ChunkRange r = chunk_range(seg_off, chunk_seg, seg_chunk0);
   const float mean = stats[4 * r.seg], rstd = stats[4 * r.seg + 2];
   double sa = 0.0, saz = 0.0;
+  if (g_ptrs) {                                   // per-segment upstream gradients (NULL = segment not in this pass)
+    const float* gp = g_ptrs[r.seg];
+    if (!gp) return;
+    g_wq = gp - seg_off[r.seg];
+  }
   for_each_2(flat, g_wq, r, [&](int64_t, float w, float g) {
     float a, z;
     bwd_terms(w, g, mean, rstd, a, z);
@@ -175,13 +180,19 @@ wq_bwd_partial_kernel(const float* __restrict__ flat, const float* __restrict__ 
 }
 
 __global__ void __launch_bounds__(kThreads)
-wq_bwd_apply_kernel(const float* __restrict__ flat, const float* __restrict__ g_wq,
+wq_bwd_apply_kernel(const float* __restrict__ flat, const float* g_wq,
                     const int64_t* __restrict__ seg_off, const int32_t* __restrict__ chunk_seg,
                     const int32_t* __restrict__ seg_chunk0, const float* __restrict__ stats,
-                    const double* __restrict__ partials, float* __restrict__ g_w) {
+                    const double* __restrict__ partials, float* __restrict__ g_w,
+                    const float* const* __restrict__ g_ptrs, int accumulate) {
   __shared__ double scratch[64];
   const ChunkRange r = chunk_range(seg_off, chunk_seg, seg_chunk0);
   const float mean = stats[4 * r.seg], rstd = stats[4 * r.seg + 2];
+  if (g_ptrs) {
+    const float* gp = g_ptrs[r.seg];
+    if (!gp) return;
+    g_wq = gp - seg_off[r.seg];
+  }
   double sa, saz;
   segment_totals(partials, r, sa, saz, scratch);
   const float mean_a = (float)(sa / (double)r.seg_numel);
@@ -189,7 +200,8 @@ wq_bwd_apply_kernel(const float* __restrict__ flat, const float* __restrict__ g_
   for_each_2(flat, g_wq, r, [&](int64_t i, float w, float g) {
     float a, z;
     bwd_terms(w, g, mean, rstd, a, z);
-    g_w[i] = rstd * (a - mean_a - z * kz);
+    const float gw = rstd * (a - mean_a - z * kz);
+    g_w[i] = accumulate ? g_w[i] + gw : gw;
   });
 }
 
@@ -235,16 +247,18 @@ extern "C" int alignq_wq_forward(const float* flat, const int64_t* seg_off, cons
   return ALIGNQ_OK;
 }
 
-extern "C" int alignq_wq_backward(const float* flat, const float* g_wq, const int64_t* seg_off,
-                                  const int32_t* chunk_seg, const int32_t* seg_chunk0, int nseg, int64_t nchunks,
-                                  int w_bit, const float* stats, float* g_w, double* ws, alignq_stream_t stream) {
+extern "C" int alignq_wq_backward(const float* flat, const float* g_wq, const float* const* g_ptrs,
+                                  const int64_t* seg_off, const int32_t* chunk_seg, const int32_t* seg_chunk0,
+                                  int nseg, int64_t nchunks, int w_bit, const float* stats, float* g_w,
+                                  int accumulate, double* ws, alignq_stream_t stream) {
   if (nseg < 0 || nchunks < 0 || w_bit < 1 || w_bit >= 32) return ALIGNQ_EINVAL;
   if (nseg == 0 || nchunks == 0) return ALIGNQ_OK;
-  if (!flat || !g_wq || !seg_off || !chunk_seg || !seg_chunk0 || !stats || !g_w || !ws) return ALIGNQ_EINVAL;
+  if (!flat || (!g_wq && !g_ptrs) || !seg_off || !chunk_seg || !seg_chunk0 || !stats || !g_w || !ws) return ALIGNQ_EINVAL;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  wq_bwd_partial_kernel<<<(unsigned)nchunks, kThreads, 0, s>>>(flat, g_wq, seg_off, chunk_seg, seg_chunk0, stats, ws);
+  wq_bwd_partial_kernel<<<(unsigned)nchunks, kThreads, 0, s>>>(flat, g_wq, seg_off, chunk_seg, seg_chunk0, stats, ws, g_ptrs);
   ALIGNQ_LAUNCH_CHECK();
-  wq_bwd_apply_kernel<<<(unsigned)nchunks, kThreads, 0, s>>>(flat, g_wq, seg_off, chunk_seg, seg_chunk0, stats, ws, g_w);
+  wq_bwd_apply_kernel<<<(unsigned)nchunks, kThreads, 0, s>>>(flat, g_wq, seg_off, chunk_seg, seg_chunk0, stats, ws, g_w,
+                                                             g_ptrs, accumulate);
   ALIGNQ_LAUNCH_CHECK();
   return ALIGNQ_OK;
 }

@@ -162,8 +162,8 @@ class _WeightQuantFn(torch.autograd.Function):
         ws = torch.empty(2 * max(nchunks, 1), dtype=torch.float64, device=wc.device)
         with torch.cuda.device_of(wc):
             L.check(L.load().alignq_wq_backward(
-                wc.data_ptr(), g.data_ptr(), seg_off.data_ptr(), chunk_seg.data_ptr(), seg_chunk0.data_ptr(), 1,
-                nchunks, ctx.w_bit, stats.data_ptr(), gw.data_ptr(), ws.data_ptr(), L.stream_ptr()),
+                wc.data_ptr(), g.data_ptr(), 0, seg_off.data_ptr(), chunk_seg.data_ptr(), seg_chunk0.data_ptr(), 1,
+                nchunks, ctx.w_bit, stats.data_ptr(), gw.data_ptr(), 0, ws.data_ptr(), L.stream_ptr()),
                 "alignq_wq_backward")
         return gw, None, None, None
 

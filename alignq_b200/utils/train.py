@@ -72,6 +72,7 @@ class QATStep:
             from .weight_bank import WeightBank
             try:
                 self.bank = WeightBank(model)
+                self.bank.batched_backward = True
             except Exception:
                 self.bank = None
         named = list(model.named_parameters())
@@ -111,15 +112,15 @@ class QATStep:
             logits, trans_loss = out
             ce = F.cross_entropy(logits, t)
             if torch.is_tensor(trans_loss) and self.single_backward:
-                (ce + trans_loss + self.offset).backward()
+                self._backward(ce + trans_loss + self.offset)
             elif torch.is_tensor(trans_loss):
-                ce.backward(retain_graph=True)                     # .../main.py:300-307
-                (trans_loss + self.offset).backward()
+                self._backward(ce, retain_graph=True)              # .../main.py:300-307
+                self._backward(trans_loss + self.offset)
             else:
-                ce.backward()
+                self._backward(ce)
         else:
             ce = F.cross_entropy(out, t)
-            ce.backward()
+            self._backward(ce)
         scale = 1.0
         if self.world > 1:                                         # ONE collective per step over NVLink:
             owners = [p for p in self.params if p.grad is not None]
@@ -143,6 +144,11 @@ class QATStep:
             self.bank.fresh = False                                # weights changed: slices are stale
         self.loss.copy_(ce.detach())
         return self.loss
+
+    def _backward(self, loss, retain_graph=False):
+        loss.backward(retain_graph=retain_graph)
+        if self.bank is not None:
+            self.bank.flush_backward()                             # all weight-quantizer backwards, one launch pair
 
     def step(self, x, t):
         if self.graph is None:

@@ -35,13 +35,16 @@ class _BankSliceFn(torch.autograd.Function):
         (w,) = ctx.saved_tensors
         bank, i = ctx.bank, ctx.i
         g = L.like_layout(g, w, "grad of quantized weight")
+        if bank.batched_backward:                 # deposit; WeightBank.flush_backward() runs ONE launch pair
+            bank.pending[i] = g
+            return None, None, None
         seg_off, chunk_seg, seg_chunk0, nchunks = _single_plan(w.numel(), w.device)
         gw = torch.empty_like(w)
         ws = torch.empty(2 * max(nchunks, 1), dtype=torch.float64, device=w.device)
         with torch.cuda.device_of(w):
             L.check(L.load().alignq_wq_backward(
-                w.data_ptr(), g.data_ptr(), seg_off.data_ptr(), chunk_seg.data_ptr(), seg_chunk0.data_ptr(), 1,
-                nchunks, bank.w_bit, bank.stats[4 * i: 4 * i + 4].data_ptr(), gw.data_ptr(), ws.data_ptr(),
+                w.data_ptr(), g.data_ptr(), 0, seg_off.data_ptr(), chunk_seg.data_ptr(), seg_chunk0.data_ptr(), 1,
+                nchunks, bank.w_bit, bank.stats[4 * i: 4 * i + 4].data_ptr(), gw.data_ptr(), 0, ws.data_ptr(),
                 L.stream_ptr()), "alignq_wq_backward")
         return gw, None, None
 
@@ -87,6 +90,14 @@ class WeightBank:
         view = lambda flat: [torch.as_strided(flat, p.shape, p.stride(), seg_off[i]) for i, p in enumerate(params)]
         self.wq, self.cdf, self.pdf = view(self.wq_flat), view(self.cdf_flat), view(self.pdf_flat)
         self.fresh = False
+        # batched backward: layers deposit their upstream gradients, flush_backward() runs one launch pair
+        self.batched_backward = False
+        self.pending = [None] * len(params)
+        self.gw_flat = torch.zeros_like(self.flat)
+        self.gw = view(self.gw_flat)
+        self.bwd_ws = torch.empty(2 * self.nchunks, dtype=torch.float64, device=dev)
+        self._gptr_dev = torch.zeros(len(params), dtype=torch.int64, device=dev)
+        self._gptr_last, self._pinned = None, []
         for i, q in enumerate(self.fns):
             q._bank = (self, i)
 
@@ -100,6 +111,31 @@ class WeightBank:
                 self.cdf_flat.data_ptr() if want else 0, self.pdf_flat.data_ptr() if want else 0, 0,
                 self.stats.data_ptr(), self.ws.data_ptr(), L.stream_ptr()), "alignq_wq_forward (bank)")
         self.fresh = True
+        if self.batched_backward:
+            self.gw_flat.zero_()                           # flush_backward() always accumulates
+
+    @torch.no_grad()
+    def flush_backward(self):
+        """After a ``.backward()`` call: weight gradients of every layer that received one, in ONE
+        multi-tensor launch pair, accumulated into the bank's gradient buffer (the ``p.grad`` views)."""
+        if not self.batched_backward or not any(g is not None for g in self.pending):
+            return
+        ptrs = [0 if g is None else g.data_ptr() for g in self.pending]
+        if ptrs != self._gptr_last:                        # pinned staging: capturable, kept alive
+            host = torch.tensor(ptrs, dtype=torch.int64).pin_memory()
+            self._pinned.append(host)
+            self._gptr_dev.copy_(host, non_blocking=True)
+            self._gptr_last = ptrs
+        with torch.cuda.device_of(self.flat):
+            L.check(L.load().alignq_wq_backward(
+                self.flat.data_ptr(), 0, self._gptr_dev.data_ptr(), self.seg_off.data_ptr(), self.chunk_seg.data_ptr(),
+                self.seg_chunk0.data_ptr(), len(self.params), self.nchunks, self.w_bit, self.stats.data_ptr(),
+                self.gw_flat.data_ptr(), 1, self.bwd_ws.data_ptr(), L.stream_ptr()), "alignq_wq_backward (bank)")
+        for i, g in enumerate(self.pending):
+            if g is not None:
+                self.params[i].grad = self.gw[i]
+        self._keep = self.pending                          # upstream gradients stay alive until the next flush
+        self.pending = [None] * len(self.params)
 
     def lookup(self, i, w):
         """Called from weight_quantize_fn.forward: the layer's slice, linked into the autograd graph."""

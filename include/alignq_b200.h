@@ -82,15 +82,19 @@ int alignq_cdf_bwd(const float* x, const float* m, const float* s, int variant, 
  * seg_chunk0 passed to the launch functions are DEVICE copies of those tables.
  * ws: nchunks*2 doubles of scratch.  stats: nseg*4 floats out = {mean, std, 1/std, numel}.
  * Backward (autograd through mean and std):
- *   gw_j = (1/s) [a_j - sum(a)/N - z_j sum(a z)/(N-1)],  a = 2 g phi(z).                       */
+ *   gw_j = (1/s) [a_j - sum(a)/N - z_j sum(a z)/(N-1)],  a = 2 g phi(z).
+ * Upstream gradients: either flat `g_wq` (same segmentation as `flat`) or `g_ptrs`, a DEVICE array of nseg
+ * pointers to per-tensor gradients (NULL entry = tensor not in this backward pass, left untouched);
+ * accumulate != 0 adds into g_w.                                                                  */
 int64_t alignq_wq_plan(const int64_t* seg_off_host, int nseg, int32_t* chunk_seg_host, int32_t* seg_chunk0_host);
 int alignq_wq_forward(const float* flat, const int64_t* seg_off, const int32_t* chunk_seg,
                       const int32_t* seg_chunk0, int nseg, int64_t nchunks, int w_bit, int variant,
                       float* wq, float* w_cdf, float* w_pdf, int16_t* codes, float* stats, double* ws,
                       alignq_stream_t stream);
-int alignq_wq_backward(const float* flat, const float* g_wq, const int64_t* seg_off, const int32_t* chunk_seg,
-                       const int32_t* seg_chunk0, int nseg, int64_t nchunks, int w_bit, const float* stats,
-                       float* g_w, double* ws, alignq_stream_t stream);
+int alignq_wq_backward(const float* flat, const float* g_wq, const float* const* g_ptrs,
+                       const int64_t* seg_off, const int32_t* chunk_seg, const int32_t* seg_chunk0,
+                       int nseg, int64_t nchunks, int w_bit, const float* stats, float* g_w,
+                       int accumulate, double* ws, alignq_stream_t stream);
 
 /* ---- correlation / Gram ----------------------------------------------------------------------
  * corr(x, y) (QB:134-137 eps = 0; QC:158-161 eps = 1e-5): standardise every feature column over

@@ -243,9 +243,22 @@ def test_weight_multi_tensor_launch_matches_single():
     L.check(lib.alignq_wq_forward(flat.data_ptr(), d_off.data_ptr(), d_cs.data_ptr(), d_c0.data_ptr(), len(sizes),
                                   nchunks, 8, 1, wq.data_ptr(), 0, 0, 0, stats.data_ptr(), ws.data_ptr(),
                                   L.stream_ptr()), "wq_forward")
-    L.check(lib.alignq_wq_backward(flat.data_ptr(), gq.data_ptr(), d_off.data_ptr(), d_cs.data_ptr(), d_c0.data_ptr(),
-                                   len(sizes), nchunks, 8, stats.data_ptr(), gw.data_ptr(), ws.data_ptr(),
+    L.check(lib.alignq_wq_backward(flat.data_ptr(), gq.data_ptr(), 0, d_off.data_ptr(), d_cs.data_ptr(), d_c0.data_ptr(),
+                                   len(sizes), nchunks, 8, stats.data_ptr(), gw.data_ptr(), 0, ws.data_ptr(),
                                    L.stream_ptr()), "wq_backward")
+    # the same through per-segment gradient pointers, with one segment absent and accumulation on top
+    parts = [gq[seg_off[i]: seg_off[i + 1]].clone() for i in range(len(sizes))]
+    ptrs = torch.tensor([0 if i == 3 else p.data_ptr() for i, p in enumerate(parts)], dtype=torch.int64, device=DEV)
+    gw2 = torch.full_like(flat, 7.0)
+    L.check(lib.alignq_wq_backward(flat.data_ptr(), 0, ptrs.data_ptr(), d_off.data_ptr(), d_cs.data_ptr(), d_c0.data_ptr(),
+                                   len(sizes), nchunks, 8, stats.data_ptr(), gw2.data_ptr(), 1, ws.data_ptr(),
+                                   L.stream_ptr()), "wq_backward ptrs")
+    for i in range(len(sizes)):
+        a, b = seg_off[i], seg_off[i + 1]
+        if i == 3:
+            assert bool((gw2[a:b] == 7.0).all())
+        else:
+            assert torch.allclose(gw2[a:b], gw[a:b] + 7.0, rtol=1e-6, atol=1e-6)
     aq.set_args(variant="B", bitW=8)
     for i, n in enumerate(sizes):
         a, b = seg_off[i], seg_off[i + 1]

@@ -101,6 +101,11 @@ wq_stats_kernel(const float* __restrict__ flat, const int64_t* __restrict__ seg_
 
 struct SegStats { float mean, std, rstd, var; };
 
+// per-segment upstream-gradient pointers, passed BY VALUE as a kernel parameter (no table upload, and
+// therefore nothing but kernel nodes when the step is captured in a CUDA graph)
+constexpr int kMaxPtrs = 128;
+struct GPtrTable { const float* p[kMaxPtrs]; };
+
 __device__ __forceinline__ SegStats finalize_stats(double s, double ss, int64_t N) {
   SegStats st;
   const double mean = s / (double)N;
@@ -159,13 +164,14 @@ __global__ void __launch_bounds__(kThreads)
 wq_bwd_partial_kernel(const float* __restrict__ flat, const float* g_wq,
                       const int64_t* __restrict__ seg_off, const int32_t* __restrict__ chunk_seg,
                       const int32_t* __restrict__ seg_chunk0, const float* __restrict__ stats,
-                      double* __restrict__ partials, const float* const* __restrict__ g_ptrs) {
+                      double* __restrict__ partials, const __grid_constant__ GPtrTable gt, int use_gt, int seg_base) {
   __shared__ double scratch[64];
   const ChunkRange r = chunk_range(seg_off, chunk_seg, seg_chunk0);
   const float mean = stats[4 * r.seg], rstd = stats[4 * r.seg + 2];
   double sa = 0.0, saz = 0.0;
-  if (g_ptrs) {                                   // per-segment upstream gradients (NULL = segment not in this pass)
-    const float* gp = g_ptrs[r.seg];
+  if (use_gt) {                                   // per-segment upstream gradients (NULL = segment not in this pass)
+    if (r.seg < seg_base || r.seg >= seg_base + kMaxPtrs) return;
+    const float* gp = gt.p[r.seg - seg_base];
     if (!gp) return;
     g_wq = gp - seg_off[r.seg];
   }
@@ -184,12 +190,13 @@ wq_bwd_apply_kernel(const float* __restrict__ flat, const float* g_wq,
                     const int64_t* __restrict__ seg_off, const int32_t* __restrict__ chunk_seg,
                     const int32_t* __restrict__ seg_chunk0, const float* __restrict__ stats,
                     const double* __restrict__ partials, float* __restrict__ g_w,
-                    const float* const* __restrict__ g_ptrs, int accumulate) {
+                    const __grid_constant__ GPtrTable gt, int use_gt, int seg_base, int accumulate) {
   __shared__ double scratch[64];
   const ChunkRange r = chunk_range(seg_off, chunk_seg, seg_chunk0);
   const float mean = stats[4 * r.seg], rstd = stats[4 * r.seg + 2];
-  if (g_ptrs) {
-    const float* gp = g_ptrs[r.seg];
+  if (use_gt) {
+    if (r.seg < seg_base || r.seg >= seg_base + kMaxPtrs) return;
+    const float* gp = gt.p[r.seg - seg_base];
     if (!gp) return;
     g_wq = gp - seg_off[r.seg];
   }
@@ -255,10 +262,15 @@ extern "C" int alignq_wq_backward(const float* flat, const float* g_wq, const fl
   if (nseg == 0 || nchunks == 0) return ALIGNQ_OK;
   if (!flat || (!g_wq && !g_ptrs) || !seg_off || !chunk_seg || !seg_chunk0 || !stats || !g_w || !ws) return ALIGNQ_EINVAL;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  wq_bwd_partial_kernel<<<(unsigned)nchunks, kThreads, 0, s>>>(flat, g_wq, seg_off, chunk_seg, seg_chunk0, stats, ws, g_ptrs);
-  ALIGNQ_LAUNCH_CHECK();
-  wq_bwd_apply_kernel<<<(unsigned)nchunks, kThreads, 0, s>>>(flat, g_wq, seg_off, chunk_seg, seg_chunk0, stats, ws, g_w,
-                                                             g_ptrs, accumulate);
-  ALIGNQ_LAUNCH_CHECK();
+  GPtrTable gt;
+  for (int base = 0; base < (g_ptrs ? nseg : 1); base += kMaxPtrs) {
+    for (int i = 0; i < kMaxPtrs; ++i) gt.p[i] = (g_ptrs && base + i < nseg) ? g_ptrs[base + i] : nullptr;
+    wq_bwd_partial_kernel<<<(unsigned)nchunks, kThreads, 0, s>>>(flat, g_wq, seg_off, chunk_seg, seg_chunk0, stats, ws, gt,
+                                                                 g_ptrs ? 1 : 0, base);
+    ALIGNQ_LAUNCH_CHECK();
+    wq_bwd_apply_kernel<<<(unsigned)nchunks, kThreads, 0, s>>>(flat, g_wq, seg_off, chunk_seg, seg_chunk0, stats, ws, g_w, gt,
+                                                               g_ptrs ? 1 : 0, base, accumulate);
+    ALIGNQ_LAUNCH_CHECK();
+  }
   return ALIGNQ_OK;
 }

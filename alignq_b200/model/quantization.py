@@ -186,11 +186,12 @@ class weight_quantize_fn(nn.Module):
             return x
         want = bool(args.store_weight_attrs)
         outs = _WeightQuantFn.apply(x, self.w_bit, L.VARIANT_ID[self.variant], want)
-        if want:
-            self.weight_q, self.weight_cdf, self.weight_pdf = outs
-        else:
-            self.weight_q, self.weight_cdf, self.weight_pdf = outs[0], None, None
-        return self.weight_q
+        # The attributes are detached copies of the handles: holding the graph-attached output across
+        # iterations would keep the parameter's AccumulateGrad node (and the stream it was created on)
+        # alive, which breaks CUDA-graph capture after a side-stream warm-up.
+        self.weight_q = outs[0].detach()
+        self.weight_cdf, self.weight_pdf = (outs[1], outs[2]) if want else (None, None)
+        return outs[0]
 
 
 # ------------------------------------------------------------------------------------------------

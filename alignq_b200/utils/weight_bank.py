@@ -96,8 +96,6 @@ class WeightBank:
         self.gw_flat = torch.zeros_like(self.flat)
         self.gw = view(self.gw_flat)
         self.bwd_ws = torch.empty(2 * self.nchunks, dtype=torch.float64, device=dev)
-        self._gptr_dev = torch.zeros(len(params), dtype=torch.int64, device=dev)
-        self._gptr_last, self._pinned = None, []
         for i, q in enumerate(self.fns):
             q._bank = (self, i)
 
@@ -120,15 +118,11 @@ class WeightBank:
         multi-tensor launch pair, accumulated into the bank's gradient buffer (the ``p.grad`` views)."""
         if not self.batched_backward or not any(g is not None for g in self.pending):
             return
-        ptrs = [0 if g is None else g.data_ptr() for g in self.pending]
-        if ptrs != self._gptr_last:                        # pinned staging: capturable, kept alive
-            host = torch.tensor(ptrs, dtype=torch.int64).pin_memory()
-            self._pinned.append(host)
-            self._gptr_dev.copy_(host, non_blocking=True)
-            self._gptr_last = ptrs
-        with torch.cuda.device_of(self.flat):
+        import ctypes
+        ptrs = (ctypes.c_void_p * len(self.pending))(*[None if g is None else g.data_ptr() for g in self.pending])
+        with torch.cuda.device_of(self.flat):              # pointers travel as kernel arguments: nothing to upload
             L.check(L.load().alignq_wq_backward(
-                self.flat.data_ptr(), 0, self._gptr_dev.data_ptr(), self.seg_off.data_ptr(), self.chunk_seg.data_ptr(),
+                self.flat.data_ptr(), 0, ptrs, self.seg_off.data_ptr(), self.chunk_seg.data_ptr(),
                 self.seg_chunk0.data_ptr(), len(self.params), self.nchunks, self.w_bit, self.stats.data_ptr(),
                 self.gw_flat.data_ptr(), 1, self.bwd_ws.data_ptr(), L.stream_ptr()), "alignq_wq_backward (bank)")
         for i, g in enumerate(self.pending):
@@ -141,7 +135,7 @@ class WeightBank:
         """Called from weight_quantize_fn.forward: the layer's slice, linked into the autograd graph."""
         q = self.fns[i]
         wq = _BankSliceFn.apply(w, self, i)
-        q.weight_q = wq
+        q.weight_q = wq.detach()
         q.weight_cdf = self.cdf[i] if args.store_weight_attrs else None
         q.weight_pdf = self.pdf[i] if args.store_weight_attrs else None
         return wq

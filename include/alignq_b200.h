@@ -83,8 +83,8 @@ int alignq_cdf_bwd(const float* x, const float* m, const float* s, int variant, 
  * ws: nchunks*2 doubles of scratch.  stats: nseg*4 floats out = {mean, std, 1/std, numel}.
  * Backward (autograd through mean and std):
  *   gw_j = (1/s) [a_j - sum(a)/N - z_j sum(a z)/(N-1)],  a = 2 g phi(z).
- * Upstream gradients: either flat `g_wq` (same segmentation as `flat`) or `g_ptrs`, a DEVICE array of nseg
- * pointers to per-tensor gradients (NULL entry = tensor not in this backward pass, left untouched);
+ * Upstream gradients: either flat `g_wq` (same segmentation as `flat`) or `g_ptrs`, a HOST array of nseg
+ * device pointers to per-tensor gradients, handed to the kernels by value (no table upload) (NULL entry = tensor not in this backward pass, left untouched);
  * accumulate != 0 adds into g_w.                                                                  */
 int64_t alignq_wq_plan(const int64_t* seg_off_host, int nseg, int32_t* chunk_seg_host, int32_t* seg_chunk0_host);
 int alignq_wq_forward(const float* flat, const int64_t* seg_off, const int32_t* chunk_seg,

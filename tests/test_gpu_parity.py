@@ -248,9 +248,10 @@ def test_weight_multi_tensor_launch_matches_single():
                                    L.stream_ptr()), "wq_backward")
     # the same through per-segment gradient pointers, with one segment absent and accumulation on top
     parts = [gq[seg_off[i]: seg_off[i + 1]].clone() for i in range(len(sizes))]
-    ptrs = torch.tensor([0 if i == 3 else p.data_ptr() for i, p in enumerate(parts)], dtype=torch.int64, device=DEV)
+    import ctypes
+    ptrs = (ctypes.c_void_p * len(parts))(*[None if i == 3 else p.data_ptr() for i, p in enumerate(parts)])
     gw2 = torch.full_like(flat, 7.0)
-    L.check(lib.alignq_wq_backward(flat.data_ptr(), 0, ptrs.data_ptr(), d_off.data_ptr(), d_cs.data_ptr(), d_c0.data_ptr(),
+    L.check(lib.alignq_wq_backward(flat.data_ptr(), 0, ptrs, d_off.data_ptr(), d_cs.data_ptr(), d_c0.data_ptr(),
                                    len(sizes), nchunks, 8, stats.data_ptr(), gw2.data_ptr(), 1, ws.data_ptr(),
                                    L.stream_ptr()), "wq_backward ptrs")
     for i in range(len(sizes)):

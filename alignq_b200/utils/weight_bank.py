@@ -26,7 +26,9 @@ class _BankSliceFn(torch.autograd.Function):
         ctx.bank, ctx.i = bank, i
         ctx.save_for_backward(w)
         ctx.set_materialize_grads(False)
-        return bank.wq[i]
+        # a fresh alias: autograd attaches grad_fn to the returned object, and attaching it to the bank's
+        # persistent view would keep every iteration's graph (and its AccumulateGrad nodes) alive
+        return bank.wq[i].detach()
 
     @staticmethod
     def backward(ctx, g):

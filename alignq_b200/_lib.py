@@ -54,8 +54,8 @@ SIGNATURES = {
     "alignq_gram_bf16_ws_bytes": (_Z, [_I]),
     "alignq_gram_bf16": (_I, [_P, _I, _L, _I, _P, _P, _Z, _P]),
     "alignq_bn_act_ws_doubles": (_Z, [_I]),
-    "alignq_bn_act_fwd": (_I, [_P, _L, _I, _P, _P, _P, _P, _F, _F, _I, _I, _F, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
-    "alignq_bn_act_bwd": (_I, [_P, _P, _P, _L, _I, _P, _P, _P, _P, _I, _I, _F, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "alignq_bn_act_fwd": (_I, [_P, _L, _I, _P, _P, _P, _P, _F, _F, _I, _I, _F, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "alignq_bn_act_bwd": (_I, [_P, _P, _P, _L, _I, _P, _P, _P, _P, _I, _I, _F, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "alignq_sgd_step": (_I, [_P, _P, _P, _I, _L, _F, _F, _I, _F, _P]),
 }
 

@@ -31,6 +31,10 @@ __device__ __forceinline__ float bnq_quant(float z, const BnQ& q) {
   if (q.a_bit == 1) v = (c > 0.f) ? 1.f : ((c < 0.f) ? -1.f : c);
   else v = __fmul_rn(rintf(__fmul_rn(c, q.n)), q.inv_n);
   if (q.variant == 0) v = __fmul_rn(sym_map(v), q.ar);
+  return v;
+}
+__device__ __forceinline__ float bnq_finish(float v, float res, const BnQ& q) {       // (+ shortcut) -> ReLU
+  v += res;
   return (q.relu && v < 0.f) ? 0.f : v;
 }
 
@@ -136,7 +140,7 @@ __global__ void bnq_eval_stats_kernel(const float* __restrict__ running_mean, co
 __global__ void __launch_bounds__(BN_MAX_THREADS)
 bnq_apply_kernel(const float* __restrict__ x, int64_t R, int C, const float* __restrict__ gamma,
                  const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ invstd,
-                 BnQ q, float* __restrict__ y) {
+                 BnQ q, const float* __restrict__ residual, float* __restrict__ y) {
   const int C4 = C >> 2, k = blockDim.x / C4;
   const int c4 = threadIdx.x % C4, rsub = threadIdx.x / C4;
   float m[4], is[4], g[4], b[4];
@@ -147,9 +151,11 @@ bnq_apply_kernel(const float* __restrict__ x, int64_t R, int C, const float* __r
   }
   for (int64_t r = (int64_t)blockIdx.x * k + rsub; r < R; r += (int64_t)gridDim.x * k) {
     const Lane4 v = ld4(x + r * C + 4 * c4);
+    Lane4 rs = {{0.f, 0.f, 0.f, 0.f}};
+    if (residual) rs = ld4(residual + r * C + 4 * c4);
     float o[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) o[j] = bnq_quant(fmaf((v.v[j] - m[j]) * is[j], g[j], b[j]), q);
+    for (int j = 0; j < 4; ++j) o[j] = bnq_finish(bnq_quant(fmaf((v.v[j] - m[j]) * is[j], g[j], b[j]), q), rs.v[j], q);
     *reinterpret_cast<float4*>(y + r * C + 4 * c4) = make_float4(o[0], o[1], o[2], o[3]);
   }
 }
@@ -225,7 +231,7 @@ __global__ void __launch_bounds__(BN_MAX_THREADS)
 bnq_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ gy, int64_t R,
                      int C, const float* __restrict__ gamma, const float* __restrict__ beta,
                      const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ coef,
-                     int training, BnQ q, float* __restrict__ gx) {
+                     int training, BnQ q, float* __restrict__ gx, float* __restrict__ g_residual) {
   const int C4 = C >> 2, k = blockDim.x / C4;
   const int c4 = threadIdx.x % C4, rsub = threadIdx.x / C4;
   float m[4], is[4], g[4], b[4], k1[4], k2[4];
@@ -248,6 +254,12 @@ bnq_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ y, c
       out[j] = g[j] * is[j] * (gz - k1[j] - xh * k2[j]);
     }
     *reinterpret_cast<float4*>(gx + o) = make_float4(out[0], out[1], out[2], out[3]);
+    if (g_residual) {                                       // the shortcut sees the ReLU-masked upstream gradient
+      float gr[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) gr[j] = (q.relu && !(yv.v[j] > 0.f)) ? 0.f : gv.v[j];
+      *reinterpret_cast<float4*>(g_residual + o) = make_float4(gr[0], gr[1], gr[2], gr[3]);
+    }
   }
 }
 
@@ -291,10 +303,10 @@ extern "C" size_t alignq_bn_act_ws_doubles(int C) {
 
 extern "C" int alignq_bn_act_fwd(const float* x, int64_t rows, int C, const float* gamma, const float* beta,
                                  float* running_mean, float* running_var, float momentum, float bn_eps, int training,
-                                 int a_bit, float act_range, int variant, int relu, float* y, float* save_mean,
-                                 float* save_invstd, double* ws, uint32_t* counter, int64_t* num_batches_tracked,
-                                 alignq_stream_t stream) {
-  int rc = bn_check(rows, C, a_bit, variant, x, y, nullptr);
+                                 int a_bit, float act_range, int variant, int relu, const float* residual, float* y,
+                                 float* save_mean, float* save_invstd, double* ws, uint32_t* counter,
+                                 int64_t* num_batches_tracked, alignq_stream_t stream) {
+  int rc = bn_check(rows, C, a_bit, variant, x, y, residual);
   if (rc) return rc;
   if (!x || !y || !save_mean || !save_invstd || !ws || !counter) return ALIGNQ_EINVAL;
   if (!training && (!running_mean || !running_var)) return ALIGNQ_EINVAL;
@@ -309,7 +321,7 @@ extern "C" int alignq_bn_act_fwd(const float* x, int64_t rows, int C, const floa
   }
   ALIGNQ_LAUNCH_CHECK();
   bnq_apply_kernel<<<L.grid * 2, L.threads, 0, s>>>(x, rows, C, gamma, beta, save_mean, save_invstd,
-                                                    make_bnq(a_bit, act_range, variant, relu), y);
+                                                    make_bnq(a_bit, act_range, variant, relu), residual, y);
   ALIGNQ_LAUNCH_CHECK();
   return ALIGNQ_OK;
 }
@@ -317,12 +329,12 @@ extern "C" int alignq_bn_act_fwd(const float* x, int64_t rows, int C, const floa
 extern "C" int alignq_bn_act_bwd(const float* x, const float* y, const float* gy, int64_t rows, int C,
                                  const float* gamma, const float* beta, const float* save_mean,
                                  const float* save_invstd, int training, int a_bit, float act_range, int variant,
-                                 int relu, float* gx, float* ggamma, float* gbeta, double* ws, uint32_t* counter,
-                                 alignq_stream_t stream) {
+                                 int relu, float* gx, float* g_residual, float* ggamma, float* gbeta, double* ws,
+                                 uint32_t* counter, alignq_stream_t stream) {
   int rc = bn_check(rows, C, a_bit, variant, x, gy, gx);
   if (rc) return rc;
   if (!x || !gy || !gx || !save_mean || !save_invstd || !ws || !counter || (relu && !y)) return ALIGNQ_EINVAL;
-  if (relu && !aligned16(y)) return ALIGNQ_EALIGN;
+  if ((relu && !aligned16(y)) || (g_residual && !aligned16(g_residual))) return ALIGNQ_EALIGN;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const BnLaunch L = bn_launch(rows, C);
   const BnQ q = make_bnq(a_bit, act_range, variant, relu);
@@ -331,7 +343,7 @@ extern "C" int alignq_bn_act_bwd(const float* x, const float* y, const float* gy
                                                           ggamma, gbeta, coef, ws, counter);
   ALIGNQ_LAUNCH_CHECK();
   bnq_bwd_apply_kernel<<<L.grid * 2, L.threads, 0, s>>>(x, y, gy, rows, C, gamma, beta, save_mean, save_invstd, coef,
-                                                        training, q, gx);
+                                                        training, q, gx, g_residual);
   ALIGNQ_LAUNCH_CHECK();
   return ALIGNQ_OK;
 }

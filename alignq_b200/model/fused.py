@@ -33,7 +33,7 @@ def _bn_ws(C: int, device):
 
 class _BnActFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, bn, a_bit, act_range, variant, relu):
+    def forward(ctx, x, weight, bias, bn, a_bit, act_range, variant, relu, residual=None):
         B, C, H, W = x.shape
         rows = B * H * W
         training = bool(bn.training or bn.running_mean is None)
@@ -45,29 +45,30 @@ class _BnActFn(torch.autograd.Function):
             L.check(L.load().alignq_bn_act_fwd(
                 x.data_ptr(), rows, C, L.ptr(weight), L.ptr(bias), L.ptr(bn.running_mean), L.ptr(bn.running_var),
                 float(bn.momentum), float(bn.eps), int(training), a_bit, act_range, variant, int(relu),
-                y.data_ptr(), mean.data_ptr(), invstd.data_ptr(), ws.data_ptr(), counter.data_ptr(),
+                L.ptr(residual), y.data_ptr(), mean.data_ptr(), invstd.data_ptr(), ws.data_ptr(), counter.data_ptr(),
                 L.ptr(bn.num_batches_tracked) if training else 0, L.stream_ptr()), "alignq_bn_act_fwd")
         # y is only needed for the ReLU mask; without ReLU the model files go on to modify it in place
         # (`out += shortcut`, resnet.py:77), so it must not be saved
         ctx.save_for_backward(x, y if relu else None, weight, bias, mean, invstd)
-        ctx.cfg = (rows, C, training, a_bit, act_range, variant, relu)
+        ctx.cfg = (rows, C, training, a_bit, act_range, variant, relu, residual is not None)
         return y
 
     @staticmethod
     def backward(ctx, gy):
         x, y, weight, bias, mean, invstd = ctx.saved_tensors
-        rows, C, training, a_bit, act_range, variant, relu = ctx.cfg
+        rows, C, training, a_bit, act_range, variant, relu, has_res = ctx.cfg
         gy = L.like_layout(gy, x, "grad of fused bn-act output")
         gx = torch.empty_like(x)
+        gr = torch.empty_like(x) if (has_res and ctx.needs_input_grad[8]) else None
         gw = torch.empty(C, dtype=torch.float32, device=x.device) if weight is not None else None
         gb = torch.empty(C, dtype=torch.float32, device=x.device) if bias is not None else None
         ws, counter = _bn_ws(C, x.device)
         with torch.cuda.device_of(x):
             L.check(L.load().alignq_bn_act_bwd(
                 x.data_ptr(), L.ptr(y), gy.data_ptr(), rows, C, L.ptr(weight), L.ptr(bias), mean.data_ptr(),
-                invstd.data_ptr(), int(training), a_bit, act_range, variant, int(relu), gx.data_ptr(), L.ptr(gw),
-                L.ptr(gb), ws.data_ptr(), counter.data_ptr(), L.stream_ptr()), "alignq_bn_act_bwd")
-        return gx, gw, gb, None, None, None, None, None
+                invstd.data_ptr(), int(training), a_bit, act_range, variant, int(relu), gx.data_ptr(), L.ptr(gr),
+                L.ptr(gw), L.ptr(gb), ws.data_ptr(), counter.data_ptr(), L.stream_ptr()), "alignq_bn_act_bwd")
+        return gx, gw, gb, None, None, None, None, None, gr
 
 
 def can_fuse(bn, actq, x) -> bool:
@@ -79,10 +80,15 @@ def can_fuse(bn, actq, x) -> bool:
             and x.is_contiguous(memory_format=torch.channels_last) and x.data_ptr() % 16 == 0)
 
 
-def bn_act(bn, actq, x, relu: bool):
-    """``relu(actq(bn(x)))`` (or without the ReLU), fused when possible."""
-    if can_fuse(bn, actq, x):
+def bn_act(bn, actq, x, relu: bool, residual=None):
+    """``relu(actq(bn(x)) [+ residual])`` (or without the ReLU), fused when possible.  ``residual`` is the
+    block shortcut of ``out += shortcut; out = F.relu(out)`` (resnet.py:77-78)."""
+    if can_fuse(bn, actq, x) and (residual is None or (residual.shape == x.shape and residual.stride() == x.stride()
+                                                       and residual.dtype == torch.float32
+                                                       and residual.data_ptr() % 16 == 0)):
         return _BnActFn.apply(x, bn.weight, bn.bias, bn, actq.a_bit, float(args.act_range),
-                              L.VARIANT_ID[actq.variant], relu)
+                              L.VARIANT_ID[actq.variant], relu, residual)
     y = actq(bn(x))
+    if residual is not None:
+        y = y + residual
     return F.relu(y) if relu else y

@@ -4,6 +4,8 @@ from __future__ import annotations
 
 import torch.nn as nn
 
+from ..utils.options import args
+from .fused import bn_act
 from .quantization import activation_quantize_fn, conv2d_Q_fn
 
 
@@ -33,9 +35,13 @@ class Block(nn.Module):
                 nn.BatchNorm2d(out_planes), self.act_skip, nn.ReLU(inplace=True))
 
     def forward(self, x):
-        out = self.relu(self.act_q1(self.bn1(self.conv1(x))))
-        out = self.relu(self.act_q2(self.bn2(self.conv2(out))))
-        out = self.act_q3(self.bn3(self.conv3(out)))
+        if args.act_range <= 6:          # |act_q| <= act_range: ReLU6 == ReLU on the quantizer's output
+            out = bn_act(self.bn1, self.act_q1, self.conv1(x), True)
+            out = bn_act(self.bn2, self.act_q2, self.conv2(out), True)
+        else:
+            out = self.relu(self.act_q1(self.bn1(self.conv1(x))))
+            out = self.relu(self.act_q2(self.bn2(self.conv2(out))))
+        out = bn_act(self.bn3, self.act_q3, self.conv3(out), False)
         if self.stride == 1:
             out += self.shortcut(x)
         return out
@@ -64,9 +70,9 @@ class MobileNetV2(nn.Module):
         self.avg_pool2d = nn.AvgPool2d(4)
 
     def forward(self, x):
-        out = self.relu(self.act_q1(self.bn1(self.conv1(x))))
+        out = bn_act(self.bn1, self.act_q1, self.conv1(x), True)
         out = self.layers(out)
-        out = self.relu(self.act_q2(self.bn2(self.conv2(out))))
+        out = bn_act(self.bn2, self.act_q2, self.conv2(out), True)
         self.out = self.avg_pool2d(out)
         return self.linear(self.out.view(self.out.size(0), -1))
 

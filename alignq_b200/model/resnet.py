@@ -52,9 +52,7 @@ class PreActBlock_conv_Q(nn.Module):
         if not self.with_admm:
             shortcut = x if self.skip_conv is None else bn_act(self.skip_bn, self.act_skip_q, self.skip_conv(x), False)
             out = bn_act(self.bn0, self.act_q0, self.conv0(x), True)       # relu(act_q0(bn0(.)))
-            out = bn_act(self.bn1, self.act_q1, self.conv1(out), False)
-            out += shortcut
-            return F.relu(out)
+            return bn_act(self.bn1, self.act_q1, self.conv1(out), True, residual=shortcut)   # relu(act_q1(.) + shortcut)
         trans_loss = 0.
         shortcut = x
         if self.skip_conv is not None:

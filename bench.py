@@ -186,7 +186,7 @@ def run_product(args):
     elif args.workload == "mobilenetv2":                   # configs[2]: W4A4, depthwise convs, batch 256
         from alignq_b200.model.mobilenetV2 import mobile_v2
         batch = 256
-        aq.set_args(bitW=4, abitW=4, train_batch_size=batch, fuse_bn_act=False)
+        aq.set_args(bitW=4, abitW=4, train_batch_size=batch)
         model = mobile_v2(4, 4, "second")
         CONFIG.update(workload="mobile_v2 W4A4 (QA) SVHN synthetic 32x32, QAT step", bitW=4, abitW=4, per_gpu_batch=batch)
     else:                                                  # configs[3]: DenseNet-40 (k=12) W8A8

@@ -173,18 +173,21 @@ int alignq_gram_bf16(const void* x_bf16, int B, int64_t F, int divide_by_F, floa
  * running statistics.  save_mean /
  * save_invstd: [C] out (forward) / in (backward).  ws: alignq_bn_act_ws_doubles(C) doubles and
  * counter: one uint32 -- both must be ZERO before the first call (the kernels re-arm them).
+ * `residual` (nullable, same layout): y = relu(q(bn(x)) + residual), the block tail `out += shortcut;
+ * F.relu(out)` (resnet.py:77-78); g_residual (nullable) receives its gradient.
  * Backward: g_z = gy [y > 0 if relu] * 2 ar phi(z) (z = BN output), then the BatchNorm backward;
  * ggamma / gbeta ([C], nullable) receive the affine gradients.                                      */
 size_t alignq_bn_act_ws_doubles(int C);
 int alignq_bn_act_fwd(const float* x, int64_t rows, int C, const float* gamma, const float* beta,
                       float* running_mean, float* running_var, float momentum, float bn_eps, int training,
-                      int a_bit, float act_range, int variant, int relu, float* y, float* save_mean,
-                      float* save_invstd, double* ws, uint32_t* counter, int64_t* num_batches_tracked,
-                      alignq_stream_t stream);
+                      int a_bit, float act_range, int variant, int relu, const float* residual, float* y,
+                      float* save_mean, float* save_invstd, double* ws, uint32_t* counter,
+                      int64_t* num_batches_tracked, alignq_stream_t stream);
 int alignq_bn_act_bwd(const float* x, const float* y, const float* gy, int64_t rows, int C,
                       const float* gamma, const float* beta, const float* save_mean, const float* save_invstd,
                       int training, int a_bit, float act_range, int variant, int relu, float* gx,
-                      float* ggamma, float* gbeta, double* ws, uint32_t* counter, alignq_stream_t stream);
+                      float* g_residual, float* ggamma, float* gbeta, double* ws, uint32_t* counter,
+                      alignq_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -104,3 +104,27 @@ def test_resnet20_fused_equals_unfused_within_band():
     assert rel(outs[1][0], outs[0][0]) <= 2e-2
     assert rel(outs[1][1], outs[0][1]) <= 5e-2
     assert torch.allclose(outs[1][2], outs[0][2], rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("relu", [True, False])
+def test_fused_bn_act_with_residual(relu):
+    """Block tail `out = act_q1(bn1(conv1(out))); out += shortcut; out = F.relu(out)` (resnet.py:74-78) in one pass."""
+    torch.manual_seed(3)
+    aq.set_args(variant="A", act_range=2, abitW=8, fuse_bn_act=True)
+    shape = (32, 32, 16, 16)
+    cl = lambda t_: t_.contiguous(memory_format=torch.channels_last)
+    x0, r0, gy = cl(torch.randn(shape, device=DEV)), cl(torch.randn(shape, device=DEV)), cl(torch.randn(shape, device=DEV))
+    bn = nn.BatchNorm2d(shape[1]).to(DEV).train()
+    bn_ref = copy.deepcopy(bn)
+    actq = aq.activation_quantize_fn(8, "second")
+    x, r = x0.clone().requires_grad_(True), r0.clone().requires_grad_(True)
+    y = bn_act(bn, actq, x, relu, residual=r)
+    (y * gy).sum().backward()
+    xr, rr = x0.clone().requires_grad_(True), r0.clone().requires_grad_(True)
+    yr = O.activation_quantize(bn_ref(xr), 8, "second", "A", 2.0) + rr
+    yr = F.relu(yr) if relu else yr
+    (yr * gy).sum().backward()
+    d = (y - yr).abs()
+    assert float(d.max()) <= 4.0 / 255 * 1.001 and int((d > 1e-6).sum()) <= max(1, int(1e-4 * y.numel()))
+    assert rel(x.grad, xr.grad) <= 2e-3 and rel(r.grad, rr.grad) <= 2e-3
+    assert rel(bn.weight.grad, bn_ref.weight.grad) <= 2e-3

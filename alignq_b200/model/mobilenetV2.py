@@ -35,7 +35,7 @@ class Block(nn.Module):
                 nn.BatchNorm2d(out_planes), self.act_skip, nn.ReLU(inplace=True))
 
     def forward(self, x):
-        if args.act_range <= 6:          # |act_q| <= act_range: ReLU6 == ReLU on the quantizer's output
+        if args.act_range <= 6 and self.act_q1.a_bit < 32:   # |act_q| <= act_range: ReLU6 == ReLU on the quantizer's output
             out = bn_act(self.bn1, self.act_q1, self.conv1(x), True)
             out = bn_act(self.bn2, self.act_q2, self.conv2(out), True)
         else:

@@ -10,8 +10,9 @@
 //   warp 0   TMA producer: one cp.async.bulk.tensor box [256 rows x 64 cols] (32 KB, SWIZZLE_128B) per
 //            stage into a 6-stage ring, mbarrier expect_tx / complete_tx
 //   warp 1   MMA issuer: per 16-column k-step two tcgen05.mma.cta_group::1.kind::f16 (M = 128, N = 256):
-//            A = rows [0,128) resp. [128,256) of the stage, B = all 256 rows of the SAME stage (K-major,
-//            128B-swizzled descriptors); accumulators = the whole TMEM (2 x 256 fp32 columns);
+//            rows [0,128) x all 256 rows (N = 256) and rows [128,256) x rows [128,256) (N = 128; the missing
+//            block is the transpose of one already computed) -- A and B descriptors point into the SAME stage
+//            (K-major, 128B-swizzled); accumulators in TMEM (256 + 128 fp32 columns);
 //            tcgen05.commit releases the stage to the producer
 //   warps 2-5 epilogue: tcgen05.ld 32x32b -> smem transpose -> coalesced fp32 partial [256 x 256]
 // followed by gram_bf16_reduce_kernel (sum of the per-CTA partials, deterministic).
@@ -79,6 +80,7 @@ gram_bf16_kernel(const __grid_constant__ CUtensorMap tmap, int B, int64_t ktiles
   } else if (warp == 1 && lane == 0) {
     // ---------------- MMA issuer ----------------
     constexpr uint32_t IDESC = make_idesc(1u /*bf16*/, 128u, 256u);
+    constexpr uint32_t IDESC_SYM = make_idesc(1u, 128u, 128u);   // lower row half: only its diagonal block (G is symmetric)
     for (int64_t i = 0; i < my_tiles; ++i) {
       const int s = (int)(i % STAGES);
       mbar_wait(&full[s], (uint32_t)((i / STAGES) & 1));
@@ -90,8 +92,8 @@ gram_bf16_kernel(const __grid_constant__ CUtensorMap tmap, int B, int64_t ktiles
         const uint64_t db = desc_sw128(sb + ks * 32);                       // all 256 rows: N = 256
         const uint64_t da0 = db;                                            // rows   0..127
         const uint64_t da1 = desc_sw128(sb + 128 * 128 + ks * 32);          // rows 128..255
-        umma<false>(tmem_base, da0, db, IDESC, acc);
-        umma<false>(tmem_base + 256, da1, db, IDESC, acc);
+        umma<false>(tmem_base, da0, db, IDESC, acc);                        // G[0:128, 0:256]
+        umma<false>(tmem_base + 256, da1, da1, IDESC_SYM, acc);             // G[128:256, 128:256]; the rest is G[0:128, 128:256]^T
       }
       umma_commit(&empty[s]);
     }
@@ -109,9 +111,9 @@ gram_bf16_kernel(const __grid_constant__ CUtensorMap tmap, int B, int64_t ktiles
       const int row0 = half * 128 + qd * 32;
       if (row0 >= B) continue;
 #pragma unroll 1
-      for (int col0 = 0; col0 < B; col0 += 32) {
+      for (int col0 = half * 128; col0 < B; col0 += 32) {
         uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + half * 256 + col0, v);
+        tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + half * 256 + (col0 - half * 128), v);
 #pragma unroll
         for (int j = 0; j < 32; ++j) tr[lane * 33 + j] = __uint_as_float(v[j]);
         __syncwarp();
@@ -135,9 +137,11 @@ gram_bf16_reduce_kernel(const float* __restrict__ partials, int nparts, int B, f
   const size_t bb = (size_t)B * B;
   const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= bb) return;
+  const int i = (int)(e / B), j = (int)(e - (size_t)i * B);
+  const size_t src = (i >= 128 && j < 128) ? (size_t)j * B + i : e;        // lower-left block = transpose of upper-right
   float acc = 0.f;
 #pragma unroll 4
-  for (int p = 0; p < nparts; ++p) acc += partials[(size_t)p * bb + e];
+  for (int p = 0; p < nparts; ++p) acc += partials[(size_t)p * bb + src];
   G[e] = acc * scale;
 }
 

@@ -356,8 +356,8 @@ def run_product(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", type=str, default="resnet20", choices=["resnet20", "resnet56_admm", "mobilenetv2", "densenet40"],
                     help="default resnet20 = BASELINE.json configs[0] (the metric's workload); the others are configs[1..3], "

@@ -132,17 +132,45 @@ gram_bf16_kernel(const __grid_constant__ CUtensorMap tmap, int B, int64_t ktiles
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-__global__ void __launch_bounds__(256)
+// Sum of the per-CTA partials.  32 consecutive elements per block; the block's 4 warps each sum a
+// quarter of the parts (coalesced 128-byte rows, 4 loads in flight per thread) and warp 0 combines the
+// four sums in fixed order (deterministic).  Elements of the never-computed lower-left block
+// (i >= 128, j < 128) are skipped here and mirrored from the upper-right block afterwards.
+__global__ void __launch_bounds__(128)
 gram_bf16_reduce_kernel(const float* __restrict__ partials, int nparts, int B, float scale, float* __restrict__ G) {
+  __shared__ float part[4][32];
   const size_t bb = (size_t)B * B;
-  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= bb) return;
+  const size_t e = (size_t)blockIdx.x * 32 + (threadIdx.x & 31);
+  const int w = threadIdx.x >> 5;
   const int i = (int)(e / B), j = (int)(e - (size_t)i * B);
-  const size_t src = (i >= 128 && j < 128) ? (size_t)j * B + i : e;        // lower-left block = transpose of upper-right
+  const bool live = e < bb && !(i >= 128 && j < 128);
   float acc = 0.f;
+  if (live) {
 #pragma unroll 4
-  for (int p = 0; p < nparts; ++p) acc += partials[(size_t)p * bb + src];
-  G[e] = acc * scale;
+    for (int p = w; p < nparts; p += 4) acc += partials[(size_t)p * bb + e];
+  }
+  part[w][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (w == 0 && live) G[e] = (((part[0][threadIdx.x] + part[1][threadIdx.x]) + part[2][threadIdx.x]) + part[3][threadIdx.x]) * scale;
+}
+
+// G[i][j] = G[j][i] for i >= 128, j < 128 (32 x 32 tiles through shared memory, coalesced both ways)
+__global__ void __launch_bounds__(256)
+gram_bf16_mirror_kernel(float* __restrict__ G, int B) {
+  __shared__ float tile[32][33];
+  const int ti = 4 + blockIdx.y, tj = blockIdx.x;                        // destination tile (rows >= 128, cols < 128)
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int row = tj * 32 + ty + 8 * r, col = ti * 32 + tx;            // source element
+    tile[ty + 8 * r][tx] = (row < B && col < B) ? G[(size_t)row * B + col] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int row = ti * 32 + ty + 8 * r, col = tj * 32 + tx;
+    if (row < B && col < B) G[(size_t)row * B + col] = tile[tx][ty + 8 * r];
+  }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -197,9 +225,13 @@ extern "C" int alignq_gram_bf16(const void* x_bf16, int B, int64_t F, int divide
   if (e != cudaSuccess) return (int)e;
   gram_bf16_kernel<<<(unsigned)grid, NTHREADS, SMEM_BYTES, s>>>(tmap, B, ktiles, reinterpret_cast<float*>(ws));
   ALIGNQ_LAUNCH_CHECK();
-  const int bb = B * B;
-  gram_bf16_reduce_kernel<<<(bb + 255) / 256, 256, 0, s>>>(reinterpret_cast<float*>(ws), (int)grid, B,
-                                                           divide_by_F ? 1.0f / (float)F : 1.0f, G);
+  const size_t bb = (size_t)B * B;
+  gram_bf16_reduce_kernel<<<(unsigned)((bb + 31) / 32), 128, 0, s>>>(reinterpret_cast<float*>(ws), (int)grid, B,
+                                                                     divide_by_F ? 1.0f / (float)F : 1.0f, G);
+  if (B > 128) {
+    ALIGNQ_LAUNCH_CHECK();
+    gram_bf16_mirror_kernel<<<dim3(4, (B - 128 + 31) / 32), 256, 0, s>>>(G, B);
+  }
   ALIGNQ_LAUNCH_CHECK();
   return ALIGNQ_OK;
 }

@@ -1,4 +1,4 @@
-"""Minimal driver for ncu: a few launches of the tcgen05 Gram kernels."""
+"""Minimal driver for ncu: the tcgen05 kernels (fused forward, backward, bf16 Gram) once each per mode."""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -6,15 +6,19 @@ from alignq_b200 import _lib as L
 lib = L.load()
 dev = "cuda"
 B, Fd = 128, 262144
-x = torch.randn(B, Fd, device=dev)
-y = torch.empty_like(x); D = torch.empty(B, B, device=dev); dL = torch.empty(B, B, device=dev); loss = torch.empty((), device=dev)
-G = torch.empty(B, B, device=dev)
+x = torch.randn(B, Fd, device=dev); gy = torch.randn(B, Fd, device=dev)
+y = torch.empty_like(x); gx = torch.empty_like(x)
+D = torch.empty(B, B, device=dev); dL = torch.empty(B, B, device=dev); loss = torch.empty((), device=dev); gl = torch.ones(1, device=dev)
 Z = torch.rand(B, B, device=dev); U = torch.rand(B, B, device=dev)
 ws = torch.empty(int(lib.alignq_gram_ws_bytes(B, Fd)), dtype=torch.uint8, device=dev)
-for rep in range(3):
+xb = torch.randn(256, 1 << 20, device=dev).to(torch.bfloat16); G = torch.empty(256, 256, device=dev)
+ws2 = torch.empty(int(lib.alignq_gram_bf16_ws_bytes(256)), dtype=torch.uint8, device=dev)
+for rep in range(2):
     for mid in (1, 2):
         L.check(lib.alignq_act_admm_fwd(x.data_ptr(), B, Fd, 8, 2.0, 0.0, Z.data_ptr(), U.data_ptr(), B, 0.2, 0.3, y.data_ptr(), D.data_ptr(),
                                         loss.data_ptr(), dL.data_ptr(), ws.data_ptr(), ws.numel(), mid, L.stream_ptr()), "fused")
-        L.check(lib.alignq_corr_fwd(x.data_ptr(), x.data_ptr(), B, Fd, 0.0, G.data_ptr(), ws.data_ptr(), ws.numel(), mid, L.stream_ptr()), "corr")
+        L.check(lib.alignq_act_admm_bwd(x.data_ptr(), gy.data_ptr(), dL.data_ptr(), gl.data_ptr(), B, Fd, 8, 2.0, 0.0, gx.data_ptr(),
+                                        ws.data_ptr(), ws.numel(), mid, L.stream_ptr()), "bwd")
+    L.check(lib.alignq_gram_bf16(xb.data_ptr(), 256, 1 << 20, 1, G.data_ptr(), ws2.data_ptr(), ws2.numel(), L.stream_ptr()), "g16")
 torch.cuda.synchronize()
 print("ok", float(loss))

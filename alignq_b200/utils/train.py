@@ -61,7 +61,7 @@ class QATStep:
 
     def __init__(self, model, lr=0.04, momentum=0.9, weight_decay=1e-4, lam=None, lam2=None,
                  trans_loss_offset=0.5, process_group=None, world_size=1, bank_weights=True,
-                 channels_last=False, fast_admm=True, single_backward=False):
+                 channels_last=False, fast_admm=True, single_backward=False, forward_loss=None):
         self.model = model
         if channels_last:                      # NHWC weights: cuDNN needs no layout conversion kernels
             for p in model.parameters():
@@ -94,6 +94,9 @@ class QATStep:
         # reference: CE.backward(retain_graph=True) then trans_loss.backward() (resnet-56 main.py:300-307);
         # cdf_alignment_admm/resnet-20-cifar-10/main.py:297-300 does ONE (CE + trans_loss).backward(): same sums
         self.single_backward = single_backward
+        # optional custom forward: (model, x, t) -> (task_loss, trans_loss | None), e.g. the two DANN passes of
+        # cdf_alignment_admm/dann_office/main.py:372-385
+        self.forward_loss = forward_loss
         self.pg, self.world = process_group, world_size
         self.all_params = self.params + self.admm_params
         dev = self.params[0].device
@@ -107,19 +110,18 @@ class QATStep:
             p.grad = None                                          # over its gradient buffers without an add
         if self.bank is not None:
             self.bank.quantize_all()
-        out = self.model(x)
-        if isinstance(out, tuple):
-            logits, trans_loss = out
-            ce = F.cross_entropy(logits, t)
-            if torch.is_tensor(trans_loss) and self.single_backward:
-                self._backward(ce + trans_loss + self.offset)
-            elif torch.is_tensor(trans_loss):
-                self._backward(ce, retain_graph=True)              # .../main.py:300-307
-                self._backward(trans_loss + self.offset)
-            else:
-                self._backward(ce)
+        if self.forward_loss is not None:
+            ce, trans_loss = self.forward_loss(self.model, x, t)
         else:
-            ce = F.cross_entropy(out, t)
+            out = self.model(x)
+            logits, trans_loss = out if isinstance(out, tuple) else (out, None)
+            ce = F.cross_entropy(logits, t)
+        if torch.is_tensor(trans_loss) and self.single_backward:
+            self._backward(ce + trans_loss + self.offset)
+        elif torch.is_tensor(trans_loss):
+            self._backward(ce, retain_graph=True)                  # .../main.py:300-307
+            self._backward(trans_loss + self.offset)
+        else:
             self._backward(ce)
         scale = 1.0
         if self.world > 1:                                         # ONE collective per step over NVLink:

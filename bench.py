@@ -175,7 +175,7 @@ def run_product(args):
     aq.set_args(variant="A", bitW=8, abitW=8, act_range=2, lam=1.0, lam2=4.0, method="ours", train_batch_size=BATCH,
                 fuse_bn_act=fuse)
     torch.manual_seed(0)                                   # identical replicas on every rank
-    batch = BATCH
+    batch, img_hw, ncls, forward_loss = BATCH, 32, 10, None
     if args.workload == "resnet20":
         model = resnet20_quant(8, 8, "second")
     elif args.workload == "resnet56_admm":                 # configs[1]: QB, W8A8 + ADMM correlation preservation
@@ -189,6 +189,22 @@ def run_product(args):
         aq.set_args(bitW=4, abitW=4, train_batch_size=batch)
         model = mobile_v2(4, 4, "second")
         CONFIG.update(workload="mobile_v2 W4A4 (QA) SVHN synthetic 32x32, QAT step", bitW=4, abitW=4, per_gpu_batch=batch)
+    elif args.workload == "resnet50_dann":                 # configs[4]: QC, Office-31 shaped 224x224, batch 28 per GPU,
+        from alignq_b200.model.dann import resnet50_dann   # source + target forward per iteration (main.py:372-385)
+        batch = 28
+        aq.set_args(variant="C", gram_mode=args.gram_mode, fuse_bn_act=False, train_batch_size=batch)
+        model = resnet50_dann(8, 8, "second")
+        CONFIG.update(workload=f"resnet50_dann W8A8 (QC) + ADMM, gram_mode={args.gram_mode}, Office-31 synthetic 224x224, "
+                               "source+target forward, QAT step", variant="C", per_gpu_batch=batch)
+        img_hw, ncls = 224, 31
+
+        def forward_loss(m, x, t):
+            b = x.shape[0] // 2
+            cls_s, dom_s, tl_s = m(x[:b], 0.5)
+            _, dom_t, tl_t = m(x[b:], 0.5)
+            zeros, ones = torch.zeros_like(t), torch.ones_like(t)
+            F_ = torch.nn.functional
+            return F_.cross_entropy(cls_s, t) + F_.cross_entropy(dom_s, zeros) + F_.cross_entropy(dom_t, ones), tl_s + tl_t
     else:                                                  # configs[3]: DenseNet-40 (k=12) W8A8
         from alignq_b200.model.densenet import densenet_40_quant
         model = densenet_40_quant(8, 8, "second")
@@ -197,12 +213,14 @@ def run_product(args):
     if world > 1 and args.sync_bn:
         model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
     step = QATStep(model, lr=0.04, momentum=0.9, weight_decay=1e-4, world_size=world, channels_last=not args.nchw,
-                   single_backward=True)
+                   single_backward=True, forward_loss=forward_loss)
 
     g = torch.Generator().manual_seed(1234 + rank)         # each rank its own shard of the synthetic batch
     n_host = 8
-    host_x = [torch.randn(batch, 3, 32, 32, generator=g).pin_memory() for _ in range(n_host)]
-    host_t = [torch.randint(0, 10, (batch,), generator=g).pin_memory() for _ in range(n_host)]
+    nimg = batch * (2 if forward_loss is not None else 1)      # DANN: source + target images per step
+    n_host = 8 if img_hw == 32 else 2
+    host_x = [torch.randn(nimg, 3, img_hw, img_hw, generator=g).pin_memory() for _ in range(n_host)]
+    host_t = [torch.randint(0, ncls, (batch,), generator=g).pin_memory() for _ in range(n_host)]
     fmt = torch.contiguous_format if args.nchw else torch.channels_last
     host_x = [h.contiguous(memory_format=fmt).pin_memory() for h in host_x]
     dev_x = [h.to(dev) for h in host_x]
@@ -338,7 +356,7 @@ def run_product(args):
                                sync_bn=bool(args.sync_bn and world > 1),
                                l2="flushed between timed steps (256 MiB memset, outside the event pairs)"),
                 "e2e": {"value": e2e, "unit": "img/s", "ms_per_step": ms_e2e / args.steps,
-                        "h2d_bytes_per_step": batch * 3 * 32 * 32 * 4 + batch * 8, "d2h_bytes_per_step": 4},
+                        "h2d_bytes_per_step": nimg * 3 * img_hw * img_hw * 4 + batch * 8, "d2h_bytes_per_step": 4},
                 "gpu_launches": int(launches_per_step) * args.steps,
                 "gpu_launches_per_step": int(launches_per_step),
                 "clocks": clocks, "roofline": roofline, "gram_tensor_roofline": gram, "cpu_baseline": cpu}
@@ -359,7 +377,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", type=str, default="resnet20", choices=["resnet20", "resnet56_admm", "mobilenetv2", "densenet40"],
+    ap.add_argument("--workload", type=str, default="resnet20", choices=["resnet20", "resnet56_admm", "mobilenetv2", "densenet40", "resnet50_dann"],
                     help="default resnet20 = BASELINE.json configs[0] (the metric's workload); the others are configs[1..3], "
                     "for the record only (their JSON line says so in config.workload)")
     ap.add_argument("--gram-mode", type=str, default="tf32x3", choices=["fp32", "tf32x3", "bf16"])

@@ -17,7 +17,8 @@
 namespace alignq {
 
 constexpr int BN_MAX_THREADS = 256;
-constexpr int BN_MAX_GRID = 2 * ALIGNQ_NUM_SMS;
+constexpr int BN_MAX_GRID = 4 * ALIGNQ_NUM_SMS;
+constexpr int BN_SLOTS = 16;      // accumulator copies: same-address fp64 atomics serialise in L2 (~15 ns each)
 
 struct BnQ {
   float n, inv_n, ar, gscale;
@@ -74,7 +75,7 @@ __device__ __forceinline__ void block_accumulate(const float (&a)[4], const floa
     double v = 0.0;
 #pragma unroll 8
     for (int r = 0; r < k; ++r) v += (double)sh[(r * C4 + c4) * 8 + j];
-    atomicAdd(acc + (c4 * 4 + (j & 3)) * 2 + (j >> 2), v);
+    atomicAdd(acc + ((size_t)(blockIdx.x % BN_SLOTS) * 4 * C4 + c4 * 4 + (j & 3)) * 2 + (j >> 2), v);
   }
 }
 
@@ -91,26 +92,26 @@ bnq_stats_kernel(const float* __restrict__ x, int64_t R, int C, float* __restric
   const int c4 = threadIdx.x % C4, rsub = threadIdx.x / C4;
   float s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
   const int64_t stride = (int64_t)gridDim.x * k;
-  int64_t r = (int64_t)blockIdx.x * k + rsub;
-  for (; r + 3 * stride < R; r += 4 * stride) {             // 4 independent 128-bit loads in flight
-    Lane4 v[4];
+  const Lane4 zero4 = {{0.f, 0.f, 0.f, 0.f}};
+  for (int64_t r = (int64_t)blockIdx.x * k + rsub; r < R; r += 4 * stride) {   // 4 predicated 128-bit loads in flight,
+    Lane4 v[4];                                                                // no serial tail
 #pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = ld4(x + (r + u * stride) * C + 4 * c4);
+    for (int u = 0; u < 4; ++u) v[u] = (r + u * stride < R) ? ld4(x + (r + u * stride) * C + 4 * c4) : zero4;
 #pragma unroll
     for (int u = 0; u < 4; ++u)
 #pragma unroll
       for (int j = 0; j < 4; ++j) { s[j] += v[u].v[j]; ss[j] = fmaf(v[u].v[j], v[u].v[j], ss[j]); }
   }
-  for (; r < R; r += stride) {
-    const Lane4 v = ld4(x + r * C + 4 * c4);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { s[j] += v.v[j]; ss[j] = fmaf(v.v[j], v.v[j], ss[j]); }
-  }
   block_accumulate(s, ss, C4, k, sh, ws);
   if (last_block(counter, &flag)) {
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      const double S = __ldcg(ws + 2 * c), SS = __ldcg(ws + 2 * c + 1);
-      ws[2 * c] = 0.0; ws[2 * c + 1] = 0.0;                  // re-arm the accumulators
+      double S = 0.0, SS = 0.0;
+#pragma unroll
+      for (int sl = 0; sl < BN_SLOTS; ++sl) {                // fixed order over the accumulator copies
+        double* a = ws + ((size_t)sl * C + c) * 2;
+        S += __ldcg(a); SS += __ldcg(a + 1);
+        a[0] = 0.0; a[1] = 0.0;                              // re-arm the accumulators
+      }
       const double mean = S / (double)R;
       double var = SS / (double)R - mean * mean;            // biased: what BN normalises with
       var = var < 0.0 ? 0.0 : var;
@@ -198,24 +199,31 @@ bnq_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ y, 
     }
   };
   const Lane4 ones = {{1.f, 1.f, 1.f, 1.f}};
-  for (; r + stride < R; r += 2 * stride) {                 // 2 rows x 3 tensors = 6 loads in flight
-    const int64_t o0 = r * C + 4 * c4, o1 = (r + stride) * C + 4 * c4;
-    const Lane4 x0 = ld4(x + o0), g0 = ld4(gy + o0), x1 = ld4(x + o1), g1 = ld4(gy + o1);
-    const Lane4 y0 = q.relu ? ld4(y + o0) : ones, y1 = q.relu ? ld4(y + o1) : ones;
-    body(x0, g0, y0);
-    body(x1, g1, y1);
-  }
-  for (; r < R; r += stride) {
-    const int64_t o = r * C + 4 * c4;
-    const Lane4 xv = ld4(x + o), gv = ld4(gy + o);
-    const Lane4 yv = q.relu ? ld4(y + o) : ones;
-    body(xv, gv, yv);
+  for (; r < R; r += 4 * stride) {                          // 4 rows x 3 tensors = 12 predicated loads in flight
+    Lane4 xs_[4], gs_[4], ys_[4];
+    bool ok[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      ok[u] = r + u * stride < R;
+      const int64_t o = (r + u * stride) * C + 4 * c4;
+      xs_[u] = ok[u] ? ld4(x + o) : ones;
+      gs_[u] = ok[u] ? ld4(gy + o) : ones;
+      ys_[u] = (ok[u] && q.relu) ? ld4(y + o) : ones;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (ok[u]) body(xs_[u], gs_[u], ys_[u]);
   }
   block_accumulate(db, dg, C4, k, sh, ws);
   if (last_block(counter, &flag)) {
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      const double S = __ldcg(ws + 2 * c), SS = __ldcg(ws + 2 * c + 1);
-      ws[2 * c] = 0.0; ws[2 * c + 1] = 0.0;                  // re-arm the accumulators
+      double S = 0.0, SS = 0.0;
+#pragma unroll
+      for (int sl = 0; sl < BN_SLOTS; ++sl) {                // fixed order over the accumulator copies
+        double* a = ws + ((size_t)sl * C + c) * 2;
+        S += __ldcg(a); SS += __ldcg(a + 1);
+        a[0] = 0.0; a[1] = 0.0;                              // re-arm the accumulators
+      }
       if (gbeta) gbeta[c] = (float)S;
       if (ggamma) ggamma[c] = (float)SS;
       coef[2 * c] = (float)(S / (double)R);
@@ -298,7 +306,7 @@ using namespace alignq;
 
 extern "C" size_t alignq_bn_act_ws_doubles(int C) {
   if (C <= 0) return 0;
-  return (size_t)C * 2 + (size_t)C;        // fp64 accumulators [C][2] (ZERO before first use) + [C][2] float coefficients
+  return (size_t)BN_SLOTS * C * 2 + (size_t)C;   // fp64 accumulators [slots][C][2] (ZERO before first use) + [C][2] float coefficients
 }
 
 extern "C" int alignq_bn_act_fwd(const float* x, int64_t rows, int C, const float* gamma, const float* beta,
@@ -338,7 +346,7 @@ extern "C" int alignq_bn_act_bwd(const float* x, const float* y, const float* gy
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const BnLaunch L = bn_launch(rows, C);
   const BnQ q = make_bnq(a_bit, act_range, variant, relu);
-  float* coef = reinterpret_cast<float*>(ws + (size_t)C * 2);       // [C][2] floats after the accumulators
+  float* coef = reinterpret_cast<float*>(ws + (size_t)BN_SLOTS * C * 2);       // [C][2] floats after the accumulators
   bnq_bwd_reduce_kernel<<<L.grid, L.threads, L.smem, s>>>(x, y, gy, rows, C, gamma, beta, save_mean, save_invstd, q,
                                                           ggamma, gbeta, coef, ws, counter);
   ALIGNQ_LAUNCH_CHECK();

@@ -29,6 +29,9 @@
 #include "../../include/alignq_b200.h"
 
 namespace alignq {
+int gram_tc_small_partials(const float* x, int B, int64_t F, float eps, ActQ q, int fused, float* y, float* partials,
+                           int64_t cap, int gram_mode, int* nparts, cudaStream_t s);
+
 namespace tc {
 
 constexpr int KB = 32;            // feature columns per tile
@@ -336,6 +339,21 @@ template <int MODE, bool FUSED>
 static int launch(const float* x, int B, int64_t F, float eps, ActQ q, float* y, float* G, float* D, void* ws,
                   size_t ws_bytes, cudaStream_t s) {
   const bool staged = aligned16(x) && (F % 4 == 0);          // cp.async needs 16-byte aligned row segments
+  if (staged && B <= 32) {                                   // gram_tc_small.cu: M = 64 MMA, 64-column tiles
+    constexpr int NACC = FUSED ? 2 : 1;
+    float* partials = reinterpret_cast<float*>(ws) + gram_wsym_floats(B);
+    const size_t head = gram_wsym_floats(B) * sizeof(float);
+    if (ws_bytes <= head) return ALIGNQ_ENOSPACE;
+    const int64_t cap = (int64_t)((ws_bytes - head) / ((size_t)NACC * B * B * sizeof(float)));
+    if (cap < 1) return ALIGNQ_ENOSPACE;
+    int nparts = 0;
+    const int rc = gram_tc_small_partials(x, B, F, eps, q, FUSED ? 1 : 0, y, partials, cap, MODE, &nparts, s);
+    if (rc != ALIGNQ_OK) return rc;
+    const int bb = B * B;
+    gram_reduce_tc_kernel<<<(bb + 255) / 256, 256, 0, s>>>(partials, nparts, B, 1.0f / (float)F, NACC, FUSED ? 1 : 0, G, D);
+    ALIGNQ_LAUNCH_CHECK();
+    return ALIGNQ_OK;
+  }
   return staged ? launch_impl<MODE, FUSED, true>(x, B, F, eps, q, y, G, D, ws, ws_bytes, s)
                 : launch_impl<MODE, FUSED, false>(x, B, F, eps, q, y, G, D, ws, ws_bytes, s);
 }

@@ -267,10 +267,14 @@ gram_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gy, co
 
 }  // namespace tcb
 
+int gram_tc_backward_small(const float* x, const float* gy, const float* Wsym, int Bp, const float* gloss, int B,
+                           int64_t F, float ar, float eps, float* gx, int split, cudaStream_t s);
+
 int gram_tc_backward(const float* x, const float* gy, const float* Wsym, int Bp, const float* gloss, int B, int64_t F,
                      float ar, float eps, float* gx, int split, cudaStream_t s) {
   using namespace tcb;
   if (B > 128 || B < 2) return ALIGNQ_ERANGE;
+  if (B <= 32) return gram_tc_backward_small(x, gy, Wsym, Bp, gloss, B, F, ar, eps, gx, split, s);   // thread-per-column variant
   if (!aligned16(x) || (F % 4) != 0) return ALIGNQ_EALIGN;       // cp.async row segments
   const int64_t ntiles = (F + KB - 1) / KB;
   int64_t grid = (ntiles + 1) / 2;                               // >= 2 tiles per CTA amortise the Wsym split

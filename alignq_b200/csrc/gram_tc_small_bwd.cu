@@ -1,0 +1,256 @@
+// Small-batch (B <= 32) tcgen05 backward of the fused activation quantizer + ADMM correlation term -- config 5
+// of BASELINE.json (ResNet-50 DANN, 28 images per GPU, F up to 802 816).  Same math as gram_tc_bwd.cu
+// (autograd backward of cdf_alignment_admm/resnet-56-cifar-10/model/quantization.py:109-123 through corr()
+// :134-137 and the straight-through rounding :33-36); what changes is who owns what:
+//
+//   * ONE THREAD OWNS ONE FEATURE COLUMN (all B <= 32 batch rows in registers).  Column statistics, the
+//     reductions of gS and gS*c, and the final combine are thread-local: no cross-warp reduction, one
+//     __syncthreads per tile.  Global loads/stores are coalesced across the warp (consecutive columns).
+//   * the per-tile product is flipped so the feature columns are the MMA's M dimension:
+//         D[n, i] = sum_j XsT[n, j] * Wsym[i, j]        M = 128 columns, N = 32 (i), K = 32 (batch j)
+//     A = the standardised tile transposed (thread n writes row n: 4 x 16-byte core-matrix rows, bf16 H + L),
+//     B = Wsym (symmetric; split once per CTA).  The accumulator row n lands in TMEM lane n, so
+//     tcgen05.ld hands thread n exactly its own column of W Xs: no shared-memory transpose.
+//   * 128 threads per CTA, three CTAs per SM (37 KB smem, 64 TMEM columns each) overlap each other's
+//     load -> convert -> MMA -> combine phases.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "gram_common.cuh"
+#include "tc_common.cuh"
+#include "../../include/alignq_b200.h"
+
+namespace alignq {
+namespace tcsb {
+
+using namespace tc;
+
+constexpr int NT = 128;                 // threads = columns per tile = MMA M
+constexpr int RB = 32;                  // batch rows: MMA N and K
+constexpr int LBO = 128;                // K-adjacent core matrices, dense
+constexpr int SBO = 4 * LBO;            // 8-row groups: K = 32 bf16 = 4 core matrices
+constexpr int A_TILE = 16 * SBO;        // XsT operand: 128 rows x 64 B            8 KB
+constexpr int W_TILE = 4 * SBO;         // Wsym operand: 32 rows x 64 B             2 KB
+constexpr int OFF_W = 0;                // [H, L]
+constexpr int OFF_A = OFF_W + 2 * W_TILE;          // [xH, xL, tH, tL]
+constexpr int OFF_BAR = OFF_A + 4 * A_TILE;
+constexpr int SMEM_BYTES = OFF_BAR + 64;
+constexpr int CTAS_PER_SM = 3;
+
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& h, __nv_bfloat16& l) {
+  h = __float2bfloat16_rn(v);
+  l = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+__device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+__device__ __forceinline__ float ld_once(const float* p) {        // read-once stream: do not keep the line in L1
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// one 16-byte core-matrix row (8 consecutive batch rows of this thread's column) of the H and L operands
+template <bool SPLIT>
+__device__ __forceinline__ void store_chunk(uint8_t* dst, const float (&c)[8]) {
+  __nv_bfloat16 h[8], l[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) split_bf16(c[k], h[k], l[k]);
+  *reinterpret_cast<uint4*>(dst) = make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
+  if (SPLIT)
+    *reinterpret_cast<uint4*>(dst + A_TILE) = make_uint4(pack2(l[0], l[1]), pack2(l[2], l[3]), pack2(l[4], l[5]), pack2(l[6], l[7]));
+}
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(NT, CTAS_PER_SM)
+gram_tc_bwd_small_kernel(const float* __restrict__ x, const float* __restrict__ gy, const float* __restrict__ Wsym, int Bp,
+                         const float* __restrict__ gloss, int B, int64_t F, float ar, float eps, int64_t ntiles,
+                         float* __restrict__ gx) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n = threadIdx.x;
+
+  // ---- setup: clear operands, split Wsym (B operand, row i = output batch index, K = j), barrier, TMEM ----
+  for (int i = threadIdx.x; i < OFF_BAR / 16; i += NT) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  {
+    const int i = n >> 2, ch = n & 3;                          // 32 rows x 4 chunks of 8 consecutive j
+    if (i < B && 8 * ch < B) {
+      const float* src = Wsym + (size_t)i * Bp + 8 * ch;
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = (8 * ch + k < B) ? __ldg(src + k) : 0.f;
+      __nv_bfloat16 h[8], l[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) split_bf16(v[k], h[k], l[k]);
+      uint8_t* dst = smem + OFF_W + (i >> 3) * SBO + (i & 7) * 16 + ch * LBO;
+      *reinterpret_cast<uint4*>(dst) = make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
+      if (SPLIT)
+        *reinterpret_cast<uint4*>(dst + W_TILE) = make_uint4(pack2(l[0], l[1]), pack2(l[2], l[3]), pack2(l[4], l[5]), pack2(l[6], l[7]));
+    }
+  }
+  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(tmem_slot, 64);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const float gl = gloss ? __ldg(gloss) : 1.0f;
+  const float sx = -gl / (float)F, st = gl / (float)F;           // corr_bwd(X, -dD), corr_bwd(T, +dD)
+  const float invB = 1.0f / (float)B, invBm1 = 1.0f / (float)(B - 1);
+  const float gscale = 2.0f * ar * kInvSqrt2Pi;
+  constexpr uint32_t IDESC = make_idesc(1u /*bf16*/, 128u, 32u);
+  uint8_t* arow = smem + OFF_A + (n >> 3) * SBO + (n & 7) * 16;  // this column's row of the A operands
+
+  int it = 0;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int64_t f = tile * NT + n;
+    const bool colv = f < F;
+    {                                                            // next tile's lines -> L2 (lane r: row r of x and gy)
+      const int64_t fn = (tile + gridDim.x) * NT + warp * 32;
+      if (lane < B && fn < F) {
+        prefetch_l2(x + (int64_t)lane * F + fn);
+        if (gy) prefetch_l2(gy + (int64_t)lane * F + fn);
+      }
+    }
+    // ---- 1. the column: values, map, statistics (all thread-local) -------------------------------------
+    float xv[RB], tv[RB];
+#pragma unroll
+    for (int r = 0; r < RB; ++r) xv[r] = (colv && r < B) ? ld_once(x + (int64_t)r * F + f) : 0.f;
+    const float px = xv[0], pt = act_map_t(px, ar);
+    float s1 = 0.f, s2 = 0.f, u1 = 0.f, u2 = 0.f;
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+      tv[r] = act_map_t(xv[r], ar);
+      if (r < B) {
+        const float d = xv[r] - px, e = tv[r] - pt;
+        s1 += d;  s2 = fmaf(d, d, s2);
+        u1 += e;  u2 = fmaf(e, e, u2);
+      }
+    }
+    float vx = (s2 - s1 * s1 * invB) * invBm1;  vx = vx < 0.f ? 0.f : vx;
+    float vt = (u2 - u1 * u1 * invB) * invBm1;  vt = vt < 0.f ? 0.f : vt;
+    const float sdx = sqrtf(vx), sdt = sqrtf(vt);
+    const float mx = px + s1 * invB, mt = pt + u1 * invB;
+    const float rx = 1.0f / (sdx + eps), rt = 1.0f / (sdt + eps);
+    // ---- 2. A operands: row n = this column, K = batch (4 core-matrix rows of 8) --------------------------
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float cx[8], ct[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int r = 8 * c + k;
+        const bool v = colv && r < B;
+        cx[k] = v ? (xv[r] - mx) * rx : 0.f;
+        ct[k] = v ? (tv[r] - mt) * rt : 0.f;
+      }
+      store_chunk<SPLIT>(arow + c * LBO, cx);
+      store_chunk<SPLIT>(arow + c * LBO + 2 * A_TILE, ct);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    // ---- 3. MMAs ---------------------------------------------------------------------------------------
+    if (threadIdx.x == 0) {
+      tc_fence_after();
+      const uint32_t sw = smem_u32(smem + OFF_W), sa = smem_u32(smem + OFF_A);
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const uint32_t koff = ks * 2 * LBO;
+        const uint64_t wh = make_desc(sw + koff, LBO, SBO), wl = make_desc(sw + W_TILE + koff, LBO, SBO);
+#pragma unroll
+        for (int src = 0; src < 2; ++src) {
+          const uint64_t ah = make_desc(sa + (2 * src) * A_TILE + koff, LBO, SBO);
+          const uint64_t al = make_desc(sa + (2 * src + 1) * A_TILE + koff, LBO, SBO);
+          umma<false>(tmem_base + 32 * src, ah, wh, IDESC, ks > 0 ? 1u : 0u);
+          if (SPLIT) {
+            umma<false>(tmem_base + 32 * src, ah, wl, IDESC, 1u);
+            umma<false>(tmem_base + 32 * src, al, wh, IDESC, 1u);
+          }
+        }
+      }
+      umma_commit(bar);
+    }
+    mbar_wait(bar, (uint32_t)(it & 1));
+    tc_fence_after();
+    // ---- 4. x source: gS = -g W Xs / F, its two column sums, the corr_bwd(x) part of gx ---------------------
+    float o[RB];
+    {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16), v);
+      float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        o[r] = (r < B) ? sx * __uint_as_float(v[r]) : 0.f;
+        a1 += o[r];
+        a2 = fmaf(o[r], xv[r] - mx, a2);
+      }
+      // the std term is masked at sd == 0 as torch's std_backward does
+      const float kx = (sdx > 0.f) ? -a2 * rx * rx * invBm1 / sdx : 0.f;
+      const float mg = a1 * invB;
+#pragma unroll
+      for (int r = 0; r < RB; ++r) o[r] = (o[r] - mg) * rx + kx * (xv[r] - mx);
+    }
+    // ---- 5. t source, straight-through factor, store ---------------------------------------------------------
+    {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + 32, v);
+      tc_fence_before();
+      float b1 = 0.f, b2 = 0.f;
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        const float g = (r < B) ? st * __uint_as_float(v[r]) : 0.f;
+        v[r] = __float_as_uint(g);
+        b1 += g;
+        b2 = fmaf(g, tv[r] - mt, b2);
+      }
+      const float kt = (sdt > 0.f) ? -b2 * rt * rt * invBm1 / sdt : 0.f;
+      const float mg = b1 * invB;
+      if (colv) {
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+          if (r < B) {
+            const float gv = gy ? ld_once(gy + (int64_t)r * F + f) : 0.f;
+            const float bt = (__uint_as_float(v[r]) - mg) * rt + kt * (tv[r] - mt);
+            const float vv = __fmul_rn(xv[r], kInvSqrt2);
+            const float dphi = gscale * gauss_kernel_from_v(vv);
+            gx[(int64_t)r * F + f] = o[r] + (bt + gv) * dphi;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 64);
+}
+
+}  // namespace tcsb
+
+int gram_tc_backward_small(const float* x, const float* gy, const float* Wsym, int Bp, const float* gloss, int B,
+                           int64_t F, float ar, float eps, float* gx, int split, cudaStream_t s) {
+  using namespace tcsb;
+  if (B > RB || B < 2) return ALIGNQ_ERANGE;
+  const int64_t ntiles = (F + NT - 1) / NT;
+  int64_t grid = ntiles;
+  if (grid > (int64_t)ALIGNQ_NUM_SMS * CTAS_PER_SM) grid = (int64_t)ALIGNQ_NUM_SMS * CTAS_PER_SM;
+  if (grid < 1) grid = 1;
+  cudaError_t e;
+  if (split) {
+    e = cudaFuncSetAttribute(gram_tc_bwd_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    gram_tc_bwd_small_kernel<true><<<(unsigned)grid, NT, SMEM_BYTES, s>>>(x, gy, Wsym, Bp, gloss, B, F, ar, eps, ntiles, gx);
+  } else {
+    e = cudaFuncSetAttribute(gram_tc_bwd_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    gram_tc_bwd_small_kernel<false><<<(unsigned)grid, NT, SMEM_BYTES, s>>>(x, gy, Wsym, Bp, gloss, B, F, ar, eps, ntiles, gx);
+  }
+  ALIGNQ_LAUNCH_CHECK();
+  return ALIGNQ_OK;
+}
+
+}  // namespace alignq

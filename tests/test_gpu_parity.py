@@ -462,7 +462,8 @@ TC_TOL = {"tf32x3": 1e-5, "bf16": 1e-2}
 
 
 @pytest.mark.parametrize("mode", ["tf32x3", "bf16"])
-@pytest.mark.parametrize("B,F,eps", [(128, 4096, 0.0), (128, 16384, 0.0), (28, 3000, 1e-5), (100, 1027, 0.0), (8, 96, 0.0)])
+@pytest.mark.parametrize("B,F,eps", [(128, 4096, 0.0), (128, 16384, 0.0), (28, 3000, 1e-5), (100, 1027, 0.0), (8, 96, 0.0),
+                                     (32, 8192, 0.0), (2, 64, 0.0), (17, 4100, 1e-5)])
 def test_tc_corr_vs_oracle(mode, B, F, eps):
     torch.manual_seed(11)
     aq.set_args(gram_mode=mode)
@@ -476,7 +477,8 @@ def test_tc_corr_vs_oracle(mode, B, F, eps):
 
 @pytest.mark.parametrize("mode", ["tf32x3", "bf16"])
 @pytest.mark.parametrize("variant,B,shape", [("B", 128, (16, 32, 32)), ("B", 128, (64, 8, 8)), ("C", 28, (64, 14, 14)),
-                                             ("B", 100, (3, 11, 13))])
+                                             ("B", 100, (3, 11, 13)), ("C", 28, (256, 14, 14)), ("B", 32, (5, 9, 4)),
+                                             ("C", 5, (3, 7, 5))])
 def test_tc_fused_forward_vs_fp32_mode_and_oracle(mode, variant, B, shape):
     torch.manual_seed(12)
     dim = 128

@@ -291,21 +291,40 @@ gram_tc_kernel(const float* __restrict__ x, int B, int64_t F, float eps, ActQ q,
   if (warp == 0) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
-// G = (1/F) sum_cta acc;  fused: D = G_t - G_x (two separately rounded Grams, as quantization.py:118-122)
-__global__ void __launch_bounds__(256)
+// G = (1/F) sum_cta acc;  fused: D = G_t - G_x (two separately rounded Grams, as quantization.py:118-122).
+// Block (32 elements, 32 part lanes): lane pl sums parts pl, pl + 32, ... of its element (coalesced 128-byte rows),
+// then the 32 lane sums are added in a fixed order, so the result does not depend on scheduling.
+__global__ void __launch_bounds__(1024)
 gram_reduce_tc_kernel(const float* __restrict__ partials, int nparts, int B, float invF, int nacc, int fused,
                       float* __restrict__ G, float* __restrict__ D) {
+  __shared__ float sm[2][32][33];
   const size_t bb = (size_t)B * B;
-  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= bb) return;
+  const size_t e = (size_t)blockIdx.x * 32 + threadIdx.x;
+  const int pl = threadIdx.y;
+  for (int a = 0; a < nacc; ++a) {
+    float acc = 0.f;
+    if (e < bb)
+      for (int p = pl; p < nparts; p += 32) acc += partials[((size_t)p * nacc + a) * bb + e];
+    sm[a][pl][threadIdx.x] = acc;
+  }
+  __syncthreads();
+  if (pl != 0 || e >= bb) return;
   float gx = 0.f, gt = 0.f;
-  for (int p = 0; p < nparts; ++p) gx += partials[(size_t)p * nacc * bb + e];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) gx += sm[0][k][threadIdx.x];
   gx = __fmul_rn(gx, invF);
   if (G) G[e] = gx;
   if (fused) {
-    for (int p = 0; p < nparts; ++p) gt += partials[((size_t)p * nacc + 1) * bb + e];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) gt += sm[1][k][threadIdx.x];
     D[e] = __fsub_rn(__fmul_rn(gt, invF), gx);
   }
+}
+
+static void launch_reduce_tc(const float* partials, int nparts, int B, int64_t F, int nacc, int fused, float* G, float* D,
+                             cudaStream_t s) {
+  const int bb = B * B;
+  gram_reduce_tc_kernel<<<(bb + 31) / 32, dim3(32, 32), 0, s>>>(partials, nparts, B, 1.0f / (float)F, nacc, fused, G, D);
 }
 
 template <int MODE, bool FUSED, bool STAGED>
@@ -328,9 +347,7 @@ static int launch_impl(const float* x, int B, int64_t F, float eps, ActQ q, floa
   if (e != cudaSuccess) return (int)e;
   gram_tc_kernel<MODE, FUSED, STAGED><<<(unsigned)grid, NT, C::SMEM_BYTES, s>>>(x, B, F, eps, q, y, partials, ntiles);
   ALIGNQ_LAUNCH_CHECK();
-  const int bb = B * B;
-  gram_reduce_tc_kernel<<<(bb + 255) / 256, 256, 0, s>>>(partials, (int)grid, B, 1.0f / (float)F, C::NACC,
-                                                         FUSED ? 1 : 0, G, D);
+  launch_reduce_tc(partials, (int)grid, B, F, C::NACC, FUSED ? 1 : 0, G, D, s);
   ALIGNQ_LAUNCH_CHECK();
   return ALIGNQ_OK;
 }
@@ -339,7 +356,7 @@ template <int MODE, bool FUSED>
 static int launch(const float* x, int B, int64_t F, float eps, ActQ q, float* y, float* G, float* D, void* ws,
                   size_t ws_bytes, cudaStream_t s) {
   const bool staged = aligned16(x) && (F % 4 == 0);          // cp.async needs 16-byte aligned row segments
-  if (staged && B <= 32) {                                   // gram_tc_small.cu: M = 64 MMA, 64-column tiles
+  if (B <= 32) {                                             // gram_tc_small.cu: thread-per-column variant
     constexpr int NACC = FUSED ? 2 : 1;
     float* partials = reinterpret_cast<float*>(ws) + gram_wsym_floats(B);
     const size_t head = gram_wsym_floats(B) * sizeof(float);
@@ -349,8 +366,7 @@ static int launch(const float* x, int B, int64_t F, float eps, ActQ q, float* y,
     int nparts = 0;
     const int rc = gram_tc_small_partials(x, B, F, eps, q, FUSED ? 1 : 0, y, partials, cap, MODE, &nparts, s);
     if (rc != ALIGNQ_OK) return rc;
-    const int bb = B * B;
-    gram_reduce_tc_kernel<<<(bb + 255) / 256, 256, 0, s>>>(partials, nparts, B, 1.0f / (float)F, NACC, FUSED ? 1 : 0, G, D);
+    launch_reduce_tc(partials, nparts, B, F, NACC, FUSED ? 1 : 0, G, D, s);
     ALIGNQ_LAUNCH_CHECK();
     return ALIGNQ_OK;
   }

@@ -18,12 +18,14 @@
 #include "common.cuh"
 #include "gram_common.cuh"
 #include "tc_common.cuh"
+#include "tc_small_common.cuh"
 #include "../../include/alignq_b200.h"
 
 namespace alignq {
 namespace tcsb {
 
 using namespace tc;
+using namespace tcsmall;
 
 constexpr int NT = 128;                 // threads = columns per tile = MMA M
 constexpr int RB = 32;                  // batch rows: MMA N and K
@@ -33,34 +35,11 @@ constexpr int A_TILE = 16 * SBO;        // XsT operand: 128 rows x 64 B         
 constexpr int W_TILE = 4 * SBO;         // Wsym operand: 32 rows x 64 B             2 KB
 constexpr int OFF_W = 0;                // [H, L]
 constexpr int OFF_A = OFF_W + 2 * W_TILE;          // [xH, xL, tH, tL]
-constexpr int OFF_BAR = OFF_A + 4 * A_TILE;
+constexpr int OFF_XS = OFF_A + 4 * A_TILE;         // x of the NEXT tile, [32][128] floats (own column per thread)
+constexpr int OFF_GY = OFF_XS + RB * NT * 4;       // gy of THIS tile, same shape
+constexpr int OFF_BAR = OFF_GY + RB * NT * 4;
 constexpr int SMEM_BYTES = OFF_BAR + 64;
 constexpr int CTAS_PER_SM = 3;
-
-__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& h, __nv_bfloat16& l) {
-  h = __float2bfloat16_rn(v);
-  l = __float2bfloat16_rn(v - __bfloat162float(h));
-}
-__device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
-  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
-}
-__device__ __forceinline__ float ld_once(const float* p) {        // read-once stream: do not keep the line in L1
-  float v;
-  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
-// one 16-byte core-matrix row (8 consecutive batch rows of this thread's column) of the H and L operands
-template <bool SPLIT>
-__device__ __forceinline__ void store_chunk(uint8_t* dst, const float (&c)[8]) {
-  __nv_bfloat16 h[8], l[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) split_bf16(c[k], h[k], l[k]);
-  *reinterpret_cast<uint4*>(dst) = make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
-  if (SPLIT)
-    *reinterpret_cast<uint4*>(dst + A_TILE) = make_uint4(pack2(l[0], l[1]), pack2(l[2], l[3]), pack2(l[4], l[5]), pack2(l[6], l[7]));
-}
 
 template <bool SPLIT>
 __global__ void __launch_bounds__(NT, CTAS_PER_SM)
@@ -82,13 +61,7 @@ gram_tc_bwd_small_kernel(const float* __restrict__ x, const float* __restrict__ 
       float v[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) v[k] = (8 * ch + k < B) ? __ldg(src + k) : 0.f;
-      __nv_bfloat16 h[8], l[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) split_bf16(v[k], h[k], l[k]);
-      uint8_t* dst = smem + OFF_W + (i >> 3) * SBO + (i & 7) * 16 + ch * LBO;
-      *reinterpret_cast<uint4*>(dst) = make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
-      if (SPLIT)
-        *reinterpret_cast<uint4*>(dst + W_TILE) = make_uint4(pack2(l[0], l[1]), pack2(l[2], l[3]), pack2(l[4], l[5]), pack2(l[6], l[7]));
+      store_chunk<SPLIT>(smem + OFF_W + (i >> 3) * SBO + (i & 7) * 16 + ch * LBO, W_TILE, v);
     }
   }
   if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
@@ -106,50 +79,63 @@ gram_tc_bwd_small_kernel(const float* __restrict__ x, const float* __restrict__ 
   constexpr uint32_t IDESC = make_idesc(1u /*bf16*/, 128u, 32u);
   uint8_t* arow = smem + OFF_A + (n >> 3) * SBO + (n & 7) * 16;  // this column's row of the A operands
 
+  // Asynchronous, register-free prefetch: thread n copies ITS OWN column (4 bytes per row) of the next tile's x and
+  // of this tile's gy into shared memory and later reads back only what it copied, so no barrier is involved.
+  const uint32_t xs_u32 = smem_u32(smem + OFF_XS) + n * 4, gs_u32 = smem_u32(smem + OFF_GY) + n * 4;
+  const float* xs = reinterpret_cast<const float*>(smem + OFF_XS) + n;
+  const float* gs = reinterpret_cast<const float*>(smem + OFF_GY) + n;
+  // rows r >= B re-read row 0 (the pivot of the statistics): always a valid address, no per-row predicate
+  auto fetch_col = [&](uint32_t dst, const float* src, int64_t tile) {
+    const int64_t f = tile * NT + n;
+    if (src != nullptr && tile < ntiles && f < F) {
+      const float* p = src + f;
+#pragma unroll
+      for (int r = 0; r < RB; ++r) cp_async4(dst + r * (NT * 4), p + ((r < B) ? (int64_t)r * F : 0), 4u);
+    }
+    cp_async_commit();
+  };
+  fetch_col(xs_u32, x, blockIdx.x);
+
   int it = 0;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
     const int64_t f = tile * NT + n;
     const bool colv = f < F;
-    {                                                            // next tile's lines -> L2 (lane r: row r of x and gy)
-      const int64_t fn = (tile + gridDim.x) * NT + warp * 32;
-      if (lane < B && fn < F) {
-        prefetch_l2(x + (int64_t)lane * F + fn);
-        if (gy) prefetch_l2(gy + (int64_t)lane * F + fn);
-      }
-    }
     // ---- 1. the column: values, map, statistics (all thread-local) -------------------------------------
+    // Rows r >= B carry the pivot (row 0, see fetch_col): they add nothing to the statistics; their operand entries (K index
+    // j >= B) meet the zero rows/columns of Wsym, and accumulator entries i >= B come out exactly 0, so nothing
+    // below is predicated per element except the global stores.
+    cp_async_wait_all();
     float xv[RB], tv[RB];
 #pragma unroll
-    for (int r = 0; r < RB; ++r) xv[r] = (colv && r < B) ? ld_once(x + (int64_t)r * F + f) : 0.f;
-    const float px = xv[0], pt = act_map_t(px, ar);
-    float s1 = 0.f, s2 = 0.f, u1 = 0.f, u2 = 0.f;
+    for (int r = 0; r < RB; ++r) xv[r] = xs[r * NT];
+    const float px = xv[0];
+    fetch_col(xs_u32, x, tile + gridDim.x);                      // next tile's x (this buffer is in registers now)
+    fetch_col(gs_u32, gy, tile);                                 // this tile's gy, read in step 5
+    float s1 = 0.f, s2 = 0.f, u1 = 0.f, u2 = 0.f, pt = 0.f;
 #pragma unroll
     for (int r = 0; r < RB; ++r) {
       tv[r] = act_map_t(xv[r], ar);
-      if (r < B) {
-        const float d = xv[r] - px, e = tv[r] - pt;
-        s1 += d;  s2 = fmaf(d, d, s2);
-        u1 += e;  u2 = fmaf(e, e, u2);
-      }
+      if (r == 0) pt = tv[0];
+      const float d = xv[r] - px, e = tv[r] - pt;
+      s1 += d;  s2 = fmaf(d, d, s2);
+      u1 += e;  u2 = fmaf(e, e, u2);
     }
     float vx = (s2 - s1 * s1 * invB) * invBm1;  vx = vx < 0.f ? 0.f : vx;
     float vt = (u2 - u1 * u1 * invB) * invBm1;  vt = vt < 0.f ? 0.f : vt;
     const float sdx = sqrtf(vx), sdt = sqrtf(vt);
     const float mx = px + s1 * invB, mt = pt + u1 * invB;
-    const float rx = 1.0f / (sdx + eps), rt = 1.0f / (sdt + eps);
+    const float rx = colv ? 1.0f / (sdx + eps) : 0.f, rt = colv ? 1.0f / (sdt + eps) : 0.f;   // columns >= F: zero rows
     // ---- 2. A operands: row n = this column, K = batch (4 core-matrix rows of 8) --------------------------
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       float cx[8], ct[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        const int r = 8 * c + k;
-        const bool v = colv && r < B;
-        cx[k] = v ? (xv[r] - mx) * rx : 0.f;
-        ct[k] = v ? (tv[r] - mt) * rt : 0.f;
+        cx[k] = (xv[8 * c + k] - mx) * rx;
+        ct[k] = (tv[8 * c + k] - mt) * rt;
       }
-      store_chunk<SPLIT>(arow + c * LBO, cx);
-      store_chunk<SPLIT>(arow + c * LBO + 2 * A_TILE, ct);
+      store_chunk<SPLIT>(arow + c * LBO, A_TILE, cx);
+      store_chunk<SPLIT>(arow + c * LBO + 2 * A_TILE, A_TILE, ct);
     }
     fence_proxy_async();
     tc_fence_before();
@@ -185,7 +171,7 @@ gram_tc_bwd_small_kernel(const float* __restrict__ x, const float* __restrict__ 
       float a1 = 0.f, a2 = 0.f;
 #pragma unroll
       for (int r = 0; r < RB; ++r) {
-        o[r] = (r < B) ? sx * __uint_as_float(v[r]) : 0.f;
+        o[r] = sx * __uint_as_float(v[r]);
         a1 += o[r];
         a2 = fmaf(o[r], xv[r] - mx, a2);
       }
@@ -203,24 +189,22 @@ gram_tc_bwd_small_kernel(const float* __restrict__ x, const float* __restrict__ 
       float b1 = 0.f, b2 = 0.f;
 #pragma unroll
       for (int r = 0; r < RB; ++r) {
-        const float g = (r < B) ? st * __uint_as_float(v[r]) : 0.f;
+        const float g = st * __uint_as_float(v[r]);
         v[r] = __float_as_uint(g);
         b1 += g;
         b2 = fmaf(g, tv[r] - mt, b2);
       }
       const float kt = (sdt > 0.f) ? -b2 * rt * rt * invBm1 / sdt : 0.f;
       const float mg = b1 * invB;
-      if (colv) {
+      cp_async_wait_all();
+      float* gp = gx + f;
 #pragma unroll
-        for (int r = 0; r < RB; ++r) {
-          if (r < B) {
-            const float gv = gy ? ld_once(gy + (int64_t)r * F + f) : 0.f;
-            const float bt = (__uint_as_float(v[r]) - mg) * rt + kt * (tv[r] - mt);
-            const float vv = __fmul_rn(xv[r], kInvSqrt2);
-            const float dphi = gscale * gauss_kernel_from_v(vv);
-            gx[(int64_t)r * F + f] = o[r] + (bt + gv) * dphi;
-          }
-        }
+      for (int r = 0; r < RB; ++r) {
+        const float gv = gs[r * NT];
+        const float bt = (__uint_as_float(v[r]) - mg) * rt + kt * (tv[r] - mt);
+        const float vv = __fmul_rn(xv[r], kInvSqrt2);
+        const float dphi = gscale * gauss_kernel_from_v(vv);
+        st_if(gp + (int64_t)r * F, o[r] + (bt + gv) * dphi, colv && r < B);
       }
     }
   }

@@ -55,7 +55,15 @@ struct Cfg {
   static constexpr int NACC = NSRC;                        // one fp32 accumulator [128 x 128] per source
   static constexpr int UMMA_K = 32 / ESZ;
   static constexpr int KSTEPS = KB / UMMA_K;
-  static constexpr int TMEM_COLS = NACC * 128;             // 128 / 256: powers of two
+  // tf32x3: the small cross products (H L^T + L H^T) get their own accumulator, so only ONE large accumulate per
+  // k-step hits the main accumulator (see FLUSH_TILES)
+  static constexpr int ACC_COLS = TF32 ? 256 : 128;        // TMEM columns per source
+  static constexpr int TMEM_COLS = NACC * ACC_COLS;        // 128 .. 512: powers of two
+  // The tensor core TRUNCATES when it adds into the fp32 accumulator (measured: ~4.6e-8 relative drift per
+  // accumulate, 3.5e-5 at B = 128, F = 262144 with one long chain).  tf32x3 therefore caps the chain: every
+  // FLUSH_TILES tiles (64 large accumulates) the accumulators are added into the CTA's fp32 partials with
+  // round-to-nearest and restarted.  bf16 mode (tolerance 1e-2) never flushes.
+  static constexpr int FLUSH_TILES = TF32 ? 16 : 0;
   static constexpr int STAGE_BYTES = NOPER * TILE_BYTES;
   static constexpr int RED_BYTES = (NW + 1) * KB * 4 * (int)sizeof(float);   // per-warp partials + finished column stats
   static constexpr int EPI_BYTES = NW * 32 * 33 * (int)sizeof(float);    // per-warp transpose tiles of the epilogue
@@ -141,10 +149,57 @@ gram_tc_kernel(const float* __restrict__ x, int B, int64_t F, float eps, ActQ q,
   } else {
     fetch_regs(blockIdx.x);
   }
+  // Accumulators -> this CTA's fp32 partials (add = false: store, true: read-modify-write of the CTA's own slot).
+  // TMEM (lane = row, 32 consecutive columns per thread) -> per-warp smem transpose -> 128-byte row stores.
+  int nflush = 0;
+  auto dump = [&](bool add) {
+    const int qd = warp & 3, cb = warp >> 2;                       // lane quarter, 32-column block
+    float* tr = reinterpret_cast<float*>(smem) + warp * (32 * 33);       // the operand stages are idle when this runs
+    float* out = partials + (size_t)blockIdx.x * C::NACC * B * B;
+#pragma unroll 1
+    for (int a = 0; a < C::NACC; ++a) {
+#pragma unroll 1
+      for (int col0 = cb * 32; col0 < 128; col0 += (NW / 4) * 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + a * C::ACC_COLS + col0, v);
+        if (C::TF32) {
+          uint32_t w[32];
+          tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + a * C::ACC_COLS + 128 + col0, w);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) tr[lane * 33 + j] = __uint_as_float(v[j]) + __uint_as_float(w[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) tr[lane * 33 + j] = __uint_as_float(v[j]);
+        }
+        __syncwarp();
+        if (col0 + lane < B) {
+          float* o = out + ((size_t)a * B + qd * 32) * B + col0 + lane;
+          const int nrow = (B - qd * 32) < 32 ? (B - qd * 32) : 32;
+          float prev[32];                                          // all loads in flight before the first store
+#pragma unroll
+          for (int r = 0; r < 32; ++r) prev[r] = (add && r < nrow) ? __ldcg(o + (size_t)r * B) : 0.f;
+#pragma unroll
+          for (int r = 0; r < 32; ++r)
+            if (r < nrow) o[(size_t)r * B] = prev[r] + tr[r * 33 + lane];
+        }
+        __syncwarp();
+      }
+    }
+  };
   int it = 0;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
     const int s = it & 1;
     uint8_t* st = stage_base + s * C::STAGE_BYTES;
+    if (C::FLUSH_TILES > 0 && it > 0 && (it % (C::FLUSH_TILES > 0 ? C::FLUSH_TILES : 1)) == 0) {
+      // every MMA issued so far has to retire before the accumulators are read; the operand stages are idle then,
+      // so the transpose scratch may use them, and the two barriers of step 2 separate it from the next operand stores
+      if (threadIdx.x == 0) umma_commit(&bars[2]);
+      mbar_wait(&bars[2], (uint32_t)(nflush & 1));
+      tc_fence_after();
+      dump(nflush > 0);
+      ++nflush;
+      tc_fence_before();
+    }
 
     // ---- 1. take the prefetched column, start the next fetch, map + quantise ---------------------
     const int64_t f = tile * KB + lane;
@@ -238,19 +293,20 @@ gram_tc_kernel(const float* __restrict__ x, int B, int64_t F, float eps, ActQ q,
       const uint32_t sb = smem_u32(st);
 #pragma unroll
       for (int ks = 0; ks < C::KSTEPS; ++ks) {
-        const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
+        const bool fresh = (C::FLUSH_TILES > 0) ? (it % (C::FLUSH_TILES > 0 ? C::FLUSH_TILES : 1)) == 0 : it == 0;
+        const uint32_t acc = (!fresh || ks > 0) ? 1u : 0u;
         const uint32_t koff = ks * 2 * LBO;
 #pragma unroll
         for (int src = 0; src < C::NSRC; ++src) {
           if (C::TF32) {
             const uint64_t dh = make_desc(sb + (2 * src) * C::TILE_BYTES + koff, LBO, C::SBO);
             const uint64_t dl = make_desc(sb + (2 * src + 1) * C::TILE_BYTES + koff, LBO, C::SBO);
-            umma<true>(tmem_base + src * 128, dh, dh, C::IDESC, acc);      // H H^T
-            umma<true>(tmem_base + src * 128, dh, dl, C::IDESC, 1u);       // H L^T
-            umma<true>(tmem_base + src * 128, dl, dh, C::IDESC, 1u);       // L H^T
+            umma<true>(tmem_base + src * C::ACC_COLS, dh, dh, C::IDESC, acc);            // H H^T -> main
+            umma<true>(tmem_base + src * C::ACC_COLS + 128, dh, dl, C::IDESC, acc);      // H L^T -> cross
+            umma<true>(tmem_base + src * C::ACC_COLS + 128, dl, dh, C::IDESC, 1u);       // L H^T -> cross
           } else {
             const uint64_t d = make_desc(sb + src * C::TILE_BYTES + koff, LBO, C::SBO);
-            umma<false>(tmem_base + src * 128, d, d, C::IDESC, acc);
+            umma<false>(tmem_base + src * C::ACC_COLS, d, d, C::IDESC, acc);
           }
         }
       }
@@ -259,33 +315,9 @@ gram_tc_kernel(const float* __restrict__ x, int B, int64_t F, float eps, ActQ q,
   }
   // ---- epilogue: TMEM -> registers -> fp32 partials -----------------------------------------------
   if (threadIdx.x == 0) umma_commit(&bars[2]);
-  mbar_wait(&bars[2], 0);
+  mbar_wait(&bars[2], (uint32_t)(nflush & 1));
   tc_fence_after();
-  {
-    // TMEM (lane = row, 32 consecutive columns per thread) -> per-warp smem transpose -> 128-byte row stores
-    const int qd = warp & 3, cb = warp >> 2;                       // lane quarter, 32-column block
-    float* tr = reinterpret_cast<float*>(smem) + warp * (32 * 33);       // operand stages are free now
-    float* out = partials + (size_t)blockIdx.x * C::NACC * B * B;
-#pragma unroll 1
-    for (int a = 0; a < C::NACC; ++a) {
-#pragma unroll 1
-      for (int col0 = cb * 32; col0 < 128; col0 += (NW / 4) * 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + a * 128 + col0, v);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) tr[lane * 33 + j] = __uint_as_float(v[j]);
-        __syncwarp();
-        if (col0 + lane < B) {
-          for (int r = 0; r < 32; ++r) {
-            const int row = qd * 32 + r;
-            if (row >= B) break;
-            out[((size_t)a * B + row) * B + col0 + lane] = tr[r * 33 + lane];
-          }
-        }
-        __syncwarp();
-      }
-    }
-  }
+  dump(nflush > 0);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, C::TMEM_COLS);

@@ -463,7 +463,8 @@ TC_TOL = {"tf32x3": 1e-5, "bf16": 1e-2}
 
 @pytest.mark.parametrize("mode", ["tf32x3", "bf16"])
 @pytest.mark.parametrize("B,F,eps", [(128, 4096, 0.0), (128, 16384, 0.0), (28, 3000, 1e-5), (100, 1027, 0.0), (8, 96, 0.0),
-                                     (32, 8192, 0.0), (2, 64, 0.0), (17, 4100, 1e-5), (28, 100352, 1e-5), (31, 1001, 0.0)])
+                                     (32, 8192, 0.0), (2, 64, 0.0), (17, 4100, 1e-5), (28, 100352, 1e-5), (31, 1001, 0.0),
+                                     (128, 262144, 0.0), (64, 100000, 1e-5)])
 def test_tc_corr_vs_oracle(mode, B, F, eps):
     torch.manual_seed(11)
     aq.set_args(gram_mode=mode)

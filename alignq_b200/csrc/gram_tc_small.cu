@@ -42,7 +42,8 @@ constexpr int SMEM_BYTES = OFF_BAR + 64;
 constexpr int CTAS_PER_SM = 3;
 constexpr int KSTEPS = NT / 16;
 
-template <bool SPLIT, bool FUSED>
+// RBT = batch rows carried per thread (B rounded up to the next instantiated size: rows RBT..31 of the operands stay zero)
+template <bool SPLIT, bool FUSED, int RBT>
 __global__ void __launch_bounds__(NT, CTAS_PER_SM)
 gram_tc_small_kernel(const float* __restrict__ x, int B, int64_t F, float eps, ActQ q, float* __restrict__ y,
                      float* __restrict__ partials, int64_t ntiles) {
@@ -91,20 +92,20 @@ gram_tc_small_kernel(const float* __restrict__ x, int B, int64_t F, float eps, A
     // Rows r >= B carry the pivot value (row 0): they add nothing to the statistics, and whatever they put into
     // operand rows >= B only reaches Gram entries with an index >= B, which are never read -- so nothing below
     // is predicated per element except the global loads and stores.
-    float xv[RB], tv[RB];
+    float xv[RBT], tv[RBT];
     const bool ystore = colv && y != nullptr;
     const float* xp = x + f;
     if (colv) {                                  // rows r >= B re-read row 0: always a valid address
 #pragma unroll
-      for (int r = 0; r < RB; ++r) xv[r] = ld_once(xp + ((r < B) ? (int64_t)r * F : 0));
+      for (int r = 0; r < RBT; ++r) xv[r] = ld_once(xp + ((r < B) ? (int64_t)r * F : 0));
     } else {
 #pragma unroll
-      for (int r = 0; r < RB; ++r) xv[r] = 0.f;
+      for (int r = 0; r < RBT; ++r) xv[r] = 0.f;
     }
     const float px = xv[0];
     float s1 = 0.f, s2 = 0.f, u1 = 0.f, u2 = 0.f, pt = 0.f;
 #pragma unroll
-    for (int r = 0; r < RB; ++r) {
+    for (int r = 0; r < RBT; ++r) {
       const float d = xv[r] - px;
       s1 += d;  s2 = fmaf(d, d, s2);
       if (FUSED) {
@@ -132,12 +133,13 @@ gram_tc_small_kernel(const float* __restrict__ x, int B, int64_t F, float eps, A
     // ---- 2. operands (stage s is free: its MMAs of tile it-2 were waited for in iteration it-1) ---------
     uint8_t* dst = smem + s * STAGE + (n >> 3) * LBO + (n & 7) * 16;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < (RBT + 7) / 8; ++c) {
       float cx[8], ct[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        cx[k] = (xv[8 * c + k] - mx) * rx;
-        ct[k] = FUSED ? (tv[8 * c + k] - mt) * rt : 0.f;
+        const int r = (8 * c + k < RBT) ? 8 * c + k : 0;           // compile-time: rows >= RBT are zeros
+        cx[k] = (8 * c + k < RBT) ? (xv[r] - mx) * rx : 0.f;
+        ct[k] = (FUSED && 8 * c + k < RBT) ? (tv[r] - mt) * rt : 0.f;
       }
       store_chunk<SPLIT>(dst + c * SBO, OP_TILE, cx);
       if (FUSED) store_chunk<SPLIT>(dst + (4 + c) * SBO, OP_TILE, ct);
@@ -189,20 +191,30 @@ gram_tc_small_kernel(const float* __restrict__ x, int B, int64_t F, float eps, A
   if (warp == 0) tmem_dealloc(tmem_base, 2 * NCOLS);
 }
 
-template <bool SPLIT, bool FUSED>
-static int launch(const float* x, int B, int64_t F, float eps, ActQ q, float* y, float* partials, int64_t cap,
+template <bool SPLIT, bool FUSED, int RBT>
+static int launch_rbt(const float* x, int B, int64_t F, float eps, ActQ q, float* y, float* partials, int64_t cap,
                   int* nparts, cudaStream_t s) {
   const int64_t ntiles = (F + NT - 1) / NT;
   int64_t grid = ntiles;
   if (grid > (int64_t)ALIGNQ_NUM_SMS * CTAS_PER_SM) grid = (int64_t)ALIGNQ_NUM_SMS * CTAS_PER_SM;
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
-  cudaError_t e = cudaFuncSetAttribute(gram_tc_small_kernel<SPLIT, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  cudaError_t e = cudaFuncSetAttribute(gram_tc_small_kernel<SPLIT, FUSED, RBT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (e != cudaSuccess) return (int)e;
-  gram_tc_small_kernel<SPLIT, FUSED><<<(unsigned)grid, NT, SMEM_BYTES, s>>>(x, B, F, eps, q, y, partials, ntiles);
+  gram_tc_small_kernel<SPLIT, FUSED, RBT><<<(unsigned)grid, NT, SMEM_BYTES, s>>>(x, B, F, eps, q, y, partials, ntiles);
   ALIGNQ_LAUNCH_CHECK();
   *nparts = (int)grid;
   return ALIGNQ_OK;
+}
+
+template <bool SPLIT, bool FUSED>
+static int launch(const float* x, int B, int64_t F, float eps, ActQ q, float* y, float* partials, int64_t cap,
+                  int* nparts, cudaStream_t s) {
+  if (B <= 8) return launch_rbt<SPLIT, FUSED, 8>(x, B, F, eps, q, y, partials, cap, nparts, s);
+  if (B <= 16) return launch_rbt<SPLIT, FUSED, 16>(x, B, F, eps, q, y, partials, cap, nparts, s);
+  if (B <= 24) return launch_rbt<SPLIT, FUSED, 24>(x, B, F, eps, q, y, partials, cap, nparts, s);
+  if (B <= 28) return launch_rbt<SPLIT, FUSED, 28>(x, B, F, eps, q, y, partials, cap, nparts, s);
+  return launch_rbt<SPLIT, FUSED, 32>(x, B, F, eps, q, y, partials, cap, nparts, s);
 }
 
 }  // namespace tcs

@@ -41,7 +41,8 @@ constexpr int OFF_BAR = OFF_GY + RB * NT * 4;
 constexpr int SMEM_BYTES = OFF_BAR + 64;
 constexpr int CTAS_PER_SM = 3;
 
-template <bool SPLIT>
+// RBT = batch rows carried per thread (B rounded up to the next instantiated size; K entries RBT..31 stay zero)
+template <bool SPLIT, int RBT>
 __global__ void __launch_bounds__(NT, CTAS_PER_SM)
 gram_tc_bwd_small_kernel(const float* __restrict__ x, const float* __restrict__ gy, const float* __restrict__ Wsym, int Bp,
                          const float* __restrict__ gloss, int B, int64_t F, float ar, float eps, int64_t ntiles,
@@ -90,7 +91,7 @@ gram_tc_bwd_small_kernel(const float* __restrict__ x, const float* __restrict__ 
     if (src != nullptr && tile < ntiles && f < F) {
       const float* p = src + f;
 #pragma unroll
-      for (int r = 0; r < RB; ++r) cp_async4(dst + r * (NT * 4), p + ((r < B) ? (int64_t)r * F : 0), 4u);
+      for (int r = 0; r < RBT; ++r) cp_async4(dst + r * (NT * 4), p + ((r < B) ? (int64_t)r * F : 0), 4u);
     }
     cp_async_commit();
   };
@@ -105,15 +106,15 @@ gram_tc_bwd_small_kernel(const float* __restrict__ x, const float* __restrict__ 
     // j >= B) meet the zero rows/columns of Wsym, and accumulator entries i >= B come out exactly 0, so nothing
     // below is predicated per element except the global stores.
     cp_async_wait_all();
-    float xv[RB], tv[RB];
+    float xv[RBT], tv[RBT];
 #pragma unroll
-    for (int r = 0; r < RB; ++r) xv[r] = xs[r * NT];
+    for (int r = 0; r < RBT; ++r) xv[r] = xs[r * NT];
     const float px = xv[0];
     fetch_col(xs_u32, x, tile + gridDim.x);                      // next tile's x (this buffer is in registers now)
     fetch_col(gs_u32, gy, tile);                                 // this tile's gy, read in step 5
     float s1 = 0.f, s2 = 0.f, u1 = 0.f, u2 = 0.f, pt = 0.f;
 #pragma unroll
-    for (int r = 0; r < RB; ++r) {
+    for (int r = 0; r < RBT; ++r) {
       tv[r] = act_map_t(xv[r], ar);
       if (r == 0) pt = tv[0];
       const float d = xv[r] - px, e = tv[r] - pt;
@@ -127,12 +128,13 @@ gram_tc_bwd_small_kernel(const float* __restrict__ x, const float* __restrict__ 
     const float rx = colv ? 1.0f / (sdx + eps) : 0.f, rt = colv ? 1.0f / (sdt + eps) : 0.f;   // columns >= F: zero rows
     // ---- 2. A operands: row n = this column, K = batch (4 core-matrix rows of 8) --------------------------
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < (RBT + 7) / 8; ++c) {
       float cx[8], ct[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        cx[k] = (xv[8 * c + k] - mx) * rx;
-        ct[k] = (tv[8 * c + k] - mt) * rt;
+        const int r = (8 * c + k < RBT) ? 8 * c + k : 0;           // compile-time: K entries >= RBT are zeros
+        cx[k] = (8 * c + k < RBT) ? (xv[r] - mx) * rx : 0.f;
+        ct[k] = (8 * c + k < RBT) ? (tv[r] - mt) * rt : 0.f;
       }
       store_chunk<SPLIT>(arow + c * LBO, A_TILE, cx);
       store_chunk<SPLIT>(arow + c * LBO + 2 * A_TILE, A_TILE, ct);
@@ -164,13 +166,13 @@ gram_tc_bwd_small_kernel(const float* __restrict__ x, const float* __restrict__ 
     mbar_wait(bar, (uint32_t)(it & 1));
     tc_fence_after();
     // ---- 4. x source: gS = -g W Xs / F, its two column sums, the corr_bwd(x) part of gx ---------------------
-    float o[RB];
+    float o[RBT];
     {
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16), v);
       float a1 = 0.f, a2 = 0.f;
 #pragma unroll
-      for (int r = 0; r < RB; ++r) {
+      for (int r = 0; r < RBT; ++r) {
         o[r] = sx * __uint_as_float(v[r]);
         a1 += o[r];
         a2 = fmaf(o[r], xv[r] - mx, a2);
@@ -179,7 +181,7 @@ gram_tc_bwd_small_kernel(const float* __restrict__ x, const float* __restrict__ 
       const float kx = (sdx > 0.f) ? -a2 * rx * rx * invBm1 / sdx : 0.f;
       const float mg = a1 * invB;
 #pragma unroll
-      for (int r = 0; r < RB; ++r) o[r] = (o[r] - mg) * rx + kx * (xv[r] - mx);
+      for (int r = 0; r < RBT; ++r) o[r] = (o[r] - mg) * rx + kx * (xv[r] - mx);
     }
     // ---- 5. t source, straight-through factor, store ---------------------------------------------------------
     {
@@ -188,7 +190,7 @@ gram_tc_bwd_small_kernel(const float* __restrict__ x, const float* __restrict__ 
       tc_fence_before();
       float b1 = 0.f, b2 = 0.f;
 #pragma unroll
-      for (int r = 0; r < RB; ++r) {
+      for (int r = 0; r < RBT; ++r) {
         const float g = st * __uint_as_float(v[r]);
         v[r] = __float_as_uint(g);
         b1 += g;
@@ -199,7 +201,7 @@ gram_tc_bwd_small_kernel(const float* __restrict__ x, const float* __restrict__ 
       cp_async_wait_all();
       float* gp = gx + f;
 #pragma unroll
-      for (int r = 0; r < RB; ++r) {
+      for (int r = 0; r < RBT; ++r) {
         const float gv = gs[r * NT];
         const float bt = (__uint_as_float(v[r]) - mg) * rt + kt * (tv[r] - mt);
         const float vv = __fmul_rn(xv[r], kInvSqrt2);
@@ -215,6 +217,26 @@ gram_tc_bwd_small_kernel(const float* __restrict__ x, const float* __restrict__ 
 
 }  // namespace tcsb
 
+template <bool SPLIT, int RBT>
+static int launch_bwd_small(const float* x, const float* gy, const float* Wsym, int Bp, const float* gloss, int B, int64_t F,
+                            float ar, float eps, float* gx, int64_t ntiles, int64_t grid, cudaStream_t s) {
+  using namespace tcsb;
+  cudaError_t e = cudaFuncSetAttribute(gram_tc_bwd_small_kernel<SPLIT, RBT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (e != cudaSuccess) return (int)e;
+  gram_tc_bwd_small_kernel<SPLIT, RBT><<<(unsigned)grid, NT, SMEM_BYTES, s>>>(x, gy, Wsym, Bp, gloss, B, F, ar, eps, ntiles, gx);
+  ALIGNQ_LAUNCH_CHECK();
+  return ALIGNQ_OK;
+}
+template <bool SPLIT>
+static int launch_bwd_small_b(const float* x, const float* gy, const float* Wsym, int Bp, const float* gloss, int B, int64_t F,
+                              float ar, float eps, float* gx, int64_t ntiles, int64_t grid, cudaStream_t s) {
+  if (B <= 8) return launch_bwd_small<SPLIT, 8>(x, gy, Wsym, Bp, gloss, B, F, ar, eps, gx, ntiles, grid, s);
+  if (B <= 16) return launch_bwd_small<SPLIT, 16>(x, gy, Wsym, Bp, gloss, B, F, ar, eps, gx, ntiles, grid, s);
+  if (B <= 24) return launch_bwd_small<SPLIT, 24>(x, gy, Wsym, Bp, gloss, B, F, ar, eps, gx, ntiles, grid, s);
+  if (B <= 28) return launch_bwd_small<SPLIT, 28>(x, gy, Wsym, Bp, gloss, B, F, ar, eps, gx, ntiles, grid, s);
+  return launch_bwd_small<SPLIT, 32>(x, gy, Wsym, Bp, gloss, B, F, ar, eps, gx, ntiles, grid, s);
+}
+
 int gram_tc_backward_small(const float* x, const float* gy, const float* Wsym, int Bp, const float* gloss, int B,
                            int64_t F, float ar, float eps, float* gx, int split, cudaStream_t s) {
   using namespace tcsb;
@@ -223,18 +245,8 @@ int gram_tc_backward_small(const float* x, const float* gy, const float* Wsym, i
   int64_t grid = ntiles;
   if (grid > (int64_t)ALIGNQ_NUM_SMS * CTAS_PER_SM) grid = (int64_t)ALIGNQ_NUM_SMS * CTAS_PER_SM;
   if (grid < 1) grid = 1;
-  cudaError_t e;
-  if (split) {
-    e = cudaFuncSetAttribute(gram_tc_bwd_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e != cudaSuccess) return (int)e;
-    gram_tc_bwd_small_kernel<true><<<(unsigned)grid, NT, SMEM_BYTES, s>>>(x, gy, Wsym, Bp, gloss, B, F, ar, eps, ntiles, gx);
-  } else {
-    e = cudaFuncSetAttribute(gram_tc_bwd_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e != cudaSuccess) return (int)e;
-    gram_tc_bwd_small_kernel<false><<<(unsigned)grid, NT, SMEM_BYTES, s>>>(x, gy, Wsym, Bp, gloss, B, F, ar, eps, ntiles, gx);
-  }
-  ALIGNQ_LAUNCH_CHECK();
-  return ALIGNQ_OK;
+  return split ? launch_bwd_small_b<true>(x, gy, Wsym, Bp, gloss, B, F, ar, eps, gx, ntiles, grid, s)
+               : launch_bwd_small_b<false>(x, gy, Wsym, Bp, gloss, B, F, ar, eps, gx, ntiles, grid, s);
 }
 
 }  // namespace alignq

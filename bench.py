@@ -324,15 +324,17 @@ def run_product(args):
             xg = torch.randn(Bg, Fg, device=dev).to(torch.bfloat16)
             Gg = torch.empty(Bg, Bg, device=dev)
             wsg = torch.empty(int(lib.alignq_gram_bf16_ws_bytes(Bg)), dtype=torch.uint8, device=dev)
-            tg = 0.0
-            for i in range(3 + reps):
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                L.check(lib.alignq_gram_bf16(xg.data_ptr(), Bg, Fg, 1, Gg.data_ptr(), wsg.data_ptr(), wsg.numel(), s), "gram_bf16")
-                e1.record()
-                torch.cuda.synchronize()
-                if i >= 3:
-                    tg += e0.elapsed_time(e1) / reps
+            call = lambda: L.check(lib.alignq_gram_bf16(xg.data_ptr(), Bg, Fg, 1, Gg.data_ptr(), wsg.data_ptr(), wsg.numel(), s), "gram_bf16")
+            for _ in range(3):
+                call()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(reps):                           # back to back: the 537 MB input cannot stay in the 126 MB L2
+                call()
+            e1.record()
+            torch.cuda.synchronize()
+            tg = e0.elapsed_time(e1) / reps
             pk = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(REPO, "MEASURED_PEAKS.json")) else {}
             tf = 2.0 * Bg * Bg * Fg / (tg * 1e-3) / 1e12
             gram = {"bound": "tensor", "achieved": tf, "unit": "TFLOP/s", "peak": pk.get("bf16_tflops", 1590.0),

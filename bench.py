@@ -227,6 +227,29 @@ def run_product(args):
     dev_t = [h.to(dev) for h in host_t]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
+    if args.kernel_shares:                                 # dev aid: CUPTI kernel-time shares of two eager steps, then exit
+        import collections
+        from torch.profiler import profile, ProfilerActivity
+        for _ in range(4):
+            step.step(dev_x[0], dev_t[0])
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(2):
+                step.step(dev_x[0], dev_t[0])
+            torch.cuda.synchronize()
+        agg = collections.defaultdict(lambda: [0, 0.0])
+        for e in prof.events():
+            if getattr(e.device_type, "name", "") == "CUDA":
+                agg[e.name[:96]][0] += 1
+                agg[e.name[:96]][1] += e.device_time
+        tot = sum(v[1] for v in agg.values())
+        lines = [f"# {args.workload}: kernel time per step {tot / 2:.1f} us over {sum(v[0] for v in agg.values()) // 2} kernels (eager, torch.profiler)"]
+        lines += [f"{d / 2:9.1f} us {100 * d / tot:5.1f}% x{c // 2:4d}  {k}" for k, (c, d) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]]
+        os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)
+        open(os.path.join(REPO, "gpurun_out", f"kernel_shares_{args.workload}.txt"), "w").write("\n".join(lines) + "\n")
+        print("\n".join(lines), file=sys.stderr)
+        os._exit(0)
+
     graphed = not args.no_graph
     launches_per_step = None
     if graphed:
@@ -383,6 +406,7 @@ def main():
                     help="default resnet20 = BASELINE.json configs[0] (the metric's workload); the others are configs[1..3], "
                     "for the record only (their JSON line says so in config.workload)")
     ap.add_argument("--gram-mode", type=str, default="tf32x3", choices=["fp32", "tf32x3", "bf16"])
+    ap.add_argument("--kernel-shares", action="store_true", help="profile two eager steps, write gpurun_out/kernel_shares_<workload>.txt, exit")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--sync-bn", action="store_true", help="N>1: SyncBatchNorm (global-batch BN statistics)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -95,6 +95,33 @@ def cpu_reference_run(steps, warmup, budget_s=150.0, batch=BATCH):
             "ms_per_step": dt / steps * 1e3}
 
 
+def gpu_eager_port_run(dev, steps=10, warmup=3, batch=BATCH):
+    """The same oracle restatement of the reference iteration, run in GPU EAGER mode (the ATen/cuDNN kernels the
+    reference itself launches on a GPU): the "same box, reference's own GPU path" bar beside the CPU baseline.
+    A reported baseline only -- nothing of the product goes through it."""
+    import torch
+    from oracle import models_oracle as MO
+
+    torch.manual_seed(0)
+    model = MO.resnet20_oracle(8, 8, "A", act_range=2.0, dim=batch).to(dev).train()
+    tr = MO.OracleTrainer(model, lr=0.04, momentum=0.9, weight_decay=1e-4, lam=1.0, lam2=4.0, bitW=8)
+    x = torch.randn(batch, 3, 32, 32, device=dev)
+    t = torch.randint(0, 10, (batch,), device=dev)
+    for _ in range(warmup):
+        tr.step(x, t)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        tr.step(x, t)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"value": batch / (ms * 1e-3), "unit": "img/s", "ms_per_step": ms,
+            "sample": f"{steps} iterations of batch {batch} after {warmup} warm-up, oracle/models_oracle.OracleTrainer "
+                      "with device=cuda (PyTorch eager, NCHW, cuDNN), CUDA events"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -209,6 +236,12 @@ def run_product(args):
         from alignq_b200.model.densenet import densenet_40_quant
         model = densenet_40_quant(8, 8, "second")
         CONFIG.update(workload="densenet_40_quant W8A8 (QA) CIFAR-10 synthetic, QAT step")
+    if args.strong:
+        if batch % world:
+            raise SystemExit(f"--strong: global batch {batch} is not divisible by {world} ranks")
+        batch //= world
+        aq.set_args(train_batch_size=batch)
+        CONFIG.update(per_gpu_batch=batch)
     model = model.to(dev).train()
     if world > 1 and args.sync_bn:
         model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
@@ -371,10 +404,15 @@ def run_product(args):
         if world == 1 and not args.no_cpu_baseline and args.workload == "resnet20":
             cb = cpu_reference_run(3, 1, budget_s=30.0)
             cpu = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            try:
+                cpu["gpu_eager_port"] = gpu_eager_port_run(dev)
+            except Exception as e:                          # pragma: no cover - a baseline, never fatal
+                cpu["gpu_eager_port"] = {"error": str(e)[:200]}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "strong" if args.strong else "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": dict(CONFIG, global_batch=batch * world, parallelism=f"dp{world}", cuda_graph=graphed,
                                activation_layout="nchw" if args.nchw else "channels_last", fused_bn_act=fuse,
@@ -407,6 +445,8 @@ def main():
                     "for the record only (their JSON line says so in config.workload)")
     ap.add_argument("--gram-mode", type=str, default="tf32x3", choices=["fp32", "tf32x3", "bf16"])
     ap.add_argument("--kernel-shares", action="store_true", help="profile two eager steps, write gpurun_out/kernel_shares_<workload>.txt, exit")
+    ap.add_argument("--strong", action="store_true", help="strong scaling: the GLOBAL batch stays 128 (per-GPU batch 128/N); "
+                    "default is weak scaling (per-GPU batch 128)")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--sync-bn", action="store_true", help="N>1: SyncBatchNorm (global-batch BN statistics)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

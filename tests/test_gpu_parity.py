@@ -476,6 +476,25 @@ def test_tc_corr_vs_oracle(mode, B, F, eps):
     assert err <= TC_TOL[mode]
 
 
+@pytest.mark.parametrize("mode,tol", [("fp32", 1e-5), ("tf32x3", 1e-5), ("bf16", 1e-2)])
+@pytest.mark.parametrize("B,F", [(28, 802816), (128, 16384), (128, 262144)])
+def test_gram_properties_at_full_size(mode, tol, B, F):
+    """Size-independent properties of corr() at the BASELINE sizes (config 5's largest layer, config 2's largest
+    layer, and a long-F case): with eps = 0 every standardised column has zero mean and unit unbiased variance, so
+    trace(G) = B - 1 and G 1 = 0; G is symmetric; and corr is invariant under x -> a x + b (a > 0)."""
+    torch.manual_seed(21)
+    aq.set_args(gram_mode=mode)
+    x = torch.randn(B, F, device=DEV) * 0.8 + 0.1
+    G = aq.corr(x, x, 0.0).double()
+    gmax = float(G.abs().max())
+    assert abs(float(G.trace()) - (B - 1)) <= tol * (B - 1)
+    assert float(G.sum(dim=1).abs().max()) <= tol * B * gmax
+    assert float((G - G.t()).abs().max()) <= tol * gmax
+    assert float(G.diagonal().min()) > 0.0
+    G2 = aq.corr(3.0 * x + 1.0, 3.0 * x + 1.0, 0.0).double()
+    assert float((G2 - G).abs().max()) <= 2 * tol * gmax
+
+
 @pytest.mark.parametrize("mode", ["tf32x3", "bf16"])
 @pytest.mark.parametrize("variant,B,shape", [("B", 128, (16, 32, 32)), ("B", 128, (64, 8, 8)), ("C", 28, (64, 14, 14)),
                                              ("B", 100, (3, 11, 13)), ("C", 28, (256, 14, 14)), ("B", 32, (5, 9, 4)),

@@ -395,7 +395,7 @@ def run_product(args):
             tf = 2.0 * Bg * Bg * Fg / (tg * 1e-3) / 1e12
             gram = {"bound": "tensor", "achieved": tf, "unit": "TFLOP/s", "peak": pk.get("bf16_tflops", 1590.0),
                     "frac": tf / pk.get("bf16_tflops", 1590.0), "frac_of_sustained": tf / pk.get("bf16_tflops_sustained", 1400.0),
-                    "ms": tg, "kernel": "gram_bf16_kernel (TMA + tcgen05.mma kind::f16, M=128 N=256, split-K) + reduce",
+                    "ms": tg, "kernel": "gram_bf16_ldgsts_kernel (cp.async producers with hand-applied 128B swizzle + tcgen05.mma kind::f16, M=128 N=256/128, split-K) + reduce",
                     "shape": [Bg, Fg], "flops": "2*B^2*F (full product)", "tolerance": "1e-2 rel vs fp32 inputs (bf16 operands)",
                     "input": "bf16 [256, 2^20] (537 MB >> L2)"}
             del xg, Gg, wsg

@@ -54,7 +54,9 @@ extern "C" int alignq_act_admm_fwd(const float* x, int B, int64_t F, int a_bit, 
     if (rc) return rc;
     rc = launch_gram_reduce(ws_partials(ws, B), nslabs, B, F, 1, nullptr, D, s);
   } else {
-    rc = gram_tc_fused_fwd(x, B, F, q, eps, y, D, ws, ws_bytes, gram_mode, s);
+    // tensor-core modes: the ADMM loss and dL/dD ride on the split-K reduction (one launch instead of two)
+    const AdmmFinish fin{Z, U, dim, mu, rho, loss, dLdD};
+    return gram_tc_fused_fwd(x, B, F, q, eps, y, D, ws, ws_bytes, gram_mode, &fin, s);
   }
   if (rc) return rc;
   return alignq_admm_loss(D, B, Z, U, dim, 1, mu, rho, nullptr, 0, loss, dLdD, nullptr, nullptr, stream);

@@ -40,11 +40,21 @@ __device__ __forceinline__ float act_quant_from_t(float t, const ActQ& q) {   //
 }
 #endif
 
+// ADMM loss fused behind the split-K reduction of the tensor-core forward (gram_tc.cu: gram_finish_tc_kernel)
+struct AdmmFinish {
+  const float* Z;      // alterD [dim, dim]
+  const float* U;      // gamma  [dim, dim]
+  int dim;
+  float mu, rho;
+  float* loss;         // scalar
+  float* dLdD;         // [B, B] or null
+};
+
 // gram_tc.cu (tcgen05 modes)
 int gram_tc_corr(const float* x, int B, int64_t F, float eps, float* G, void* ws, size_t ws_bytes, int gram_mode,
                  cudaStream_t s);
 int gram_tc_fused_fwd(const float* x, int B, int64_t F, ActQ q, float eps, float* y, float* D, void* ws,
-                      size_t ws_bytes, int gram_mode, cudaStream_t s);
+                      size_t ws_bytes, int gram_mode, const AdmmFinish* fin, cudaStream_t s);
 // gram_tc_bwd.cu
 int gram_tc_backward(const float* x, const float* gy, const float* Wsym, int Bp, const float* gloss, int B, int64_t F,
                      float ar, float eps, float* gx, int split, cudaStream_t s);

@@ -30,7 +30,7 @@
 
 namespace alignq {
 int gram_tc_small_partials(const float* x, int B, int64_t F, float eps, ActQ q, int fused, float* y, float* partials,
-                           int64_t cap, int gram_mode, int* nparts, cudaStream_t s);
+                           int64_t cap, int gram_mode, int* nparts, double* zero_acc, cudaStream_t s);
 
 namespace tc {
 
@@ -86,7 +86,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 template <int MODE, bool FUSED, bool STAGED>
 __global__ void __launch_bounds__(NT, 1)
 gram_tc_kernel(const float* __restrict__ x, int B, int64_t F, float eps, ActQ q, float* __restrict__ y,
-               float* __restrict__ partials, int64_t ntiles) {
+               float* __restrict__ partials, int64_t ntiles, double* __restrict__ zero_acc) {
   using C = Cfg<MODE, FUSED, STAGED>;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* stage_base = smem;
@@ -97,6 +97,7 @@ gram_tc_kernel(const float* __restrict__ x, int B, int64_t F, float eps, ActQ q,
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (zero_acc && blockIdx.x == 0 && threadIdx.x < 4) zero_acc[threadIdx.x] = 0.0;   // arms gram_finish_tc_kernel (next in stream)
 
   // ---- one-time setup ------------------------------------------------------------------------
   for (int i = threadIdx.x; i < 2 * C::STAGE_BYTES / 16; i += NT) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
@@ -359,9 +360,95 @@ static void launch_reduce_tc(const float* partials, int nparts, int B, int64_t F
   gram_reduce_tc_kernel<<<(bb + 31) / 32, dim3(32, 32), 0, s>>>(partials, nparts, B, 1.0f / (float)F, nacc, fused, G, D);
 }
 
+// Fused split-K reduction + ADMM.forward(D) (cdf_alignment_admm/resnet-56-cifar-10/utils/admm.py:24-33) + dL/dD for
+// the fused forward: same block shape as gram_reduce_tc_kernel, then every block adds its three partial sums
+// (sum|Z|, sum R^2, sum U|R|, fp64) to acc[0..2] and takes a ticket; the LAST block finishes loss and dL/dD.
+// acc[0..3] (3 sums + the ticket) sit at the start of the workspace and are zeroed by the Gram kernel that runs just
+// before.  One launch instead of reduce + an 8-CTA cluster launch; arithmetic identical to admm_loss_kernel.
+__global__ void __launch_bounds__(1024)
+gram_finish_tc_kernel(const float* __restrict__ partials, int nparts, int B, float invF, AdmmFinish f,
+                      float* __restrict__ D, double* __restrict__ acc) {
+  __shared__ float sm[2][32][33];
+  __shared__ unsigned last_flag;
+  const int bb = B * B;
+  const int e = blockIdx.x * 32 + threadIdx.x;
+  const int pl = threadIdx.y;
+  for (int a = 0; a < 2; ++a) {
+    float v = 0.f;
+    if (e < bb)
+      for (int p = pl; p < nparts; p += 32) v += partials[((size_t)p * 2 + a) * bb + e];
+    sm[a][pl][threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (pl == 0) {                                               // warp 0: one element per lane
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    if (e < bb) {
+      float gx = 0.f, gt = 0.f;
+#pragma unroll
+      for (int k = 0; k < 32; ++k) { gx += sm[0][k][threadIdx.x]; gt += sm[1][k][threadIdx.x]; }
+      gx = __fmul_rn(gx, invF);
+      const float d = __fsub_rn(__fmul_rn(gt, invF), gx);
+      D[e] = d;
+      const int i = e / B, j = e - i * B;
+      const float z = f.Z[(size_t)i * f.dim + j], u = f.U[(size_t)i * f.dim + j];
+      const float r = __fsub_rn(d, z);
+      s0 = (double)fabsf(z);
+      s1 = (double)__fmul_rn(r, r);
+      s2 = (double)__fmul_rn(u, fabsf(r));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (threadIdx.x == 0) { atomicAdd(acc + 0, s0); atomicAdd(acc + 1, s1); atomicAdd(acc + 2, s2); }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0 && pl == 0) {
+    const unsigned t = atomicAdd(reinterpret_cast<unsigned*>(acc + 3), 1u);
+    last_flag = (t == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!last_flag) return;
+  __threadfence();
+  const double S0 = __ldcg(acc + 0), S1 = __ldcg(acc + 1), S2 = __ldcg(acc + 2);
+  const float inv_bb = 1.0f / (float)bb;
+  const float rms = sqrtf((float)(S1 / bb));                  // mean(...) ** 0.5
+  const int tid = pl * 32 + threadIdx.x;
+  if (tid == 0 && f.loss) {
+    const float reg = f.mu * (float)(S0 / bb);
+    const float con = (f.rho / 2.0f) * rms;
+    *f.loss = (reg + con) + (float)(S2 / bb);
+  }
+  if (f.dLdD) {
+    const float k1 = (f.rho / 2.0f) / rms * inv_bb;           // rms == 0 -> inf, and 0 * inf = NaN as autograd gives
+    for (int q = tid; q < bb; q += 1024) {
+      const int i = q / B, j = q - i * B;
+      const float z = f.Z[(size_t)i * f.dim + j], u = f.U[(size_t)i * f.dim + j];
+      const float r = __fsub_rn(__ldcg(D + q), z);
+      const float sg = (r > 0.f) ? 1.f : ((r < 0.f) ? -1.f : 0.f);
+      f.dLdD[q] = k1 * r + u * sg * inv_bb;
+    }
+  }
+}
+
+// reduce, or reduce + ADMM loss when the caller asked for it (fused forward only)
+static void launch_finish_tc(const float* partials, int nparts, int B, int64_t F, int nacc, int fused, float* G, float* D,
+                             const AdmmFinish* fin, void* ws, cudaStream_t s) {
+  if (fin && fused) {
+    const int bb = B * B;
+    gram_finish_tc_kernel<<<(bb + 31) / 32, dim3(32, 32), 0, s>>>(partials, nparts, B, 1.0f / (float)F, *fin, D,
+                                                                   reinterpret_cast<double*>(ws));
+  } else {
+    launch_reduce_tc(partials, nparts, B, F, nacc, fused, G, D, s);
+  }
+}
+
 template <int MODE, bool FUSED, bool STAGED>
 static int launch_impl(const float* x, int B, int64_t F, float eps, ActQ q, float* y, float* G, float* D, void* ws,
-                       size_t ws_bytes, cudaStream_t s) {
+                       size_t ws_bytes, const AdmmFinish* fin, cudaStream_t s) {
   using C = Cfg<MODE, FUSED, STAGED>;
   const int64_t ntiles = (F + KB - 1) / KB;
   float* partials = reinterpret_cast<float*>(ws) + gram_wsym_floats(B);
@@ -369,24 +456,27 @@ static int launch_impl(const float* x, int B, int64_t F, float eps, ActQ q, floa
   if (ws_bytes <= head) return ALIGNQ_ENOSPACE;
   int64_t cap = (int64_t)((ws_bytes - head) / ((size_t)C::NACC * B * B * sizeof(float)));
   if (cap < 1) return ALIGNQ_ENOSPACE;
-  // >= 4 tiles per CTA: every CTA pays a fixed prologue (smem clear, TMEM alloc) and dumps NACC 64 KB
-  // partials that the reduce kernel re-reads, so small layers use fewer, longer-running CTAs
-  int64_t grid = (ntiles + 3) / 4;
+  // One wave of CTAs with an equal number of tiles each: tiles-per-CTA = ceil(ntiles / 148).  (Measured at B = 128:
+  // F = 4096 / 8192 / 16384 are all fastest with 128 CTAs of 1 / 2 / 4 tiles; fewer, longer CTAs lose more in the
+  // main loop than they save in partials.)
+  const int64_t tiles_per_cta = (ntiles + ALIGNQ_NUM_SMS - 1) / ALIGNQ_NUM_SMS;
+  int64_t grid = (ntiles + tiles_per_cta - 1) / tiles_per_cta;
   if (grid > ALIGNQ_NUM_SMS) grid = ALIGNQ_NUM_SMS;
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
   cudaError_t e = cudaFuncSetAttribute(gram_tc_kernel<MODE, FUSED, STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
   if (e != cudaSuccess) return (int)e;
-  gram_tc_kernel<MODE, FUSED, STAGED><<<(unsigned)grid, NT, C::SMEM_BYTES, s>>>(x, B, F, eps, q, y, partials, ntiles);
+  double* zero_acc = (fin && FUSED) ? reinterpret_cast<double*>(ws) : nullptr;
+  gram_tc_kernel<MODE, FUSED, STAGED><<<(unsigned)grid, NT, C::SMEM_BYTES, s>>>(x, B, F, eps, q, y, partials, ntiles, zero_acc);
   ALIGNQ_LAUNCH_CHECK();
-  launch_reduce_tc(partials, (int)grid, B, F, C::NACC, FUSED ? 1 : 0, G, D, s);
+  launch_finish_tc(partials, (int)grid, B, F, C::NACC, FUSED ? 1 : 0, G, D, fin, ws, s);
   ALIGNQ_LAUNCH_CHECK();
   return ALIGNQ_OK;
 }
 
 template <int MODE, bool FUSED>
 static int launch(const float* x, int B, int64_t F, float eps, ActQ q, float* y, float* G, float* D, void* ws,
-                  size_t ws_bytes, cudaStream_t s) {
+                  size_t ws_bytes, const AdmmFinish* fin, cudaStream_t s) {
   const bool staged = aligned16(x) && (F % 4 == 0);          // cp.async needs 16-byte aligned row segments
   if (B <= 32) {                                             // gram_tc_small.cu: thread-per-column variant
     constexpr int NACC = FUSED ? 2 : 1;
@@ -396,14 +486,15 @@ static int launch(const float* x, int B, int64_t F, float eps, ActQ q, float* y,
     const int64_t cap = (int64_t)((ws_bytes - head) / ((size_t)NACC * B * B * sizeof(float)));
     if (cap < 1) return ALIGNQ_ENOSPACE;
     int nparts = 0;
-    const int rc = gram_tc_small_partials(x, B, F, eps, q, FUSED ? 1 : 0, y, partials, cap, MODE, &nparts, s);
+    double* zero_acc = (fin && FUSED) ? reinterpret_cast<double*>(ws) : nullptr;
+    const int rc = gram_tc_small_partials(x, B, F, eps, q, FUSED ? 1 : 0, y, partials, cap, MODE, &nparts, zero_acc, s);
     if (rc != ALIGNQ_OK) return rc;
-    launch_reduce_tc(partials, nparts, B, F, NACC, FUSED ? 1 : 0, G, D, s);
+    launch_finish_tc(partials, nparts, B, F, NACC, FUSED ? 1 : 0, G, D, fin, ws, s);
     ALIGNQ_LAUNCH_CHECK();
     return ALIGNQ_OK;
   }
-  return staged ? launch_impl<MODE, FUSED, true>(x, B, F, eps, q, y, G, D, ws, ws_bytes, s)
-                : launch_impl<MODE, FUSED, false>(x, B, F, eps, q, y, G, D, ws, ws_bytes, s);
+  return staged ? launch_impl<MODE, FUSED, true>(x, B, F, eps, q, y, G, D, ws, ws_bytes, fin, s)
+                : launch_impl<MODE, FUSED, false>(x, B, F, eps, q, y, G, D, ws, ws_bytes, fin, s);
 }
 
 }  // namespace tc
@@ -412,16 +503,16 @@ int gram_tc_corr(const float* x, int B, int64_t F, float eps, float* G, void* ws
                  cudaStream_t s) {
   if (B > 128 || B < 2) return ALIGNQ_ERANGE;      // one 128-row UMMA tile; larger batches use the fp32 path
   ActQ q{0.f, 0.f, 0.f, 0};
-  if (gram_mode == ALIGNQ_GRAM_TF32X3) return tc::launch<ALIGNQ_GRAM_TF32X3, false>(x, B, F, eps, q, nullptr, G, nullptr, ws, ws_bytes, s);
-  if (gram_mode == ALIGNQ_GRAM_BF16) return tc::launch<ALIGNQ_GRAM_BF16, false>(x, B, F, eps, q, nullptr, G, nullptr, ws, ws_bytes, s);
+  if (gram_mode == ALIGNQ_GRAM_TF32X3) return tc::launch<ALIGNQ_GRAM_TF32X3, false>(x, B, F, eps, q, nullptr, G, nullptr, ws, ws_bytes, nullptr, s);
+  if (gram_mode == ALIGNQ_GRAM_BF16) return tc::launch<ALIGNQ_GRAM_BF16, false>(x, B, F, eps, q, nullptr, G, nullptr, ws, ws_bytes, nullptr, s);
   return ALIGNQ_EINVAL;
 }
 
 int gram_tc_fused_fwd(const float* x, int B, int64_t F, ActQ q, float eps, float* y, float* D, void* ws, size_t ws_bytes,
-                      int gram_mode, cudaStream_t s) {
+                      int gram_mode, const AdmmFinish* fin, cudaStream_t s) {
   if (B > 128 || B < 2) return ALIGNQ_ERANGE;
-  if (gram_mode == ALIGNQ_GRAM_TF32X3) return tc::launch<ALIGNQ_GRAM_TF32X3, true>(x, B, F, eps, q, y, nullptr, D, ws, ws_bytes, s);
-  if (gram_mode == ALIGNQ_GRAM_BF16) return tc::launch<ALIGNQ_GRAM_BF16, true>(x, B, F, eps, q, y, nullptr, D, ws, ws_bytes, s);
+  if (gram_mode == ALIGNQ_GRAM_TF32X3) return tc::launch<ALIGNQ_GRAM_TF32X3, true>(x, B, F, eps, q, y, nullptr, D, ws, ws_bytes, fin, s);
+  if (gram_mode == ALIGNQ_GRAM_BF16) return tc::launch<ALIGNQ_GRAM_BF16, true>(x, B, F, eps, q, y, nullptr, D, ws, ws_bytes, fin, s);
   return ALIGNQ_EINVAL;
 }
 

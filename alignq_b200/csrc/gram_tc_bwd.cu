@@ -277,7 +277,8 @@ int gram_tc_backward(const float* x, const float* gy, const float* Wsym, int Bp,
   if (B <= 32) return gram_tc_backward_small(x, gy, Wsym, Bp, gloss, B, F, ar, eps, gx, split, s);   // thread-per-column variant
   if (!aligned16(x) || (F % 4) != 0) return ALIGNQ_EALIGN;       // cp.async row segments
   const int64_t ntiles = (F + KB - 1) / KB;
-  int64_t grid = (ntiles + 1) / 2;                               // >= 2 tiles per CTA amortise the Wsym split
+  const int64_t tiles_per_cta = (ntiles + ALIGNQ_NUM_SMS - 1) / ALIGNQ_NUM_SMS;      // one wave, equal work per CTA
+  int64_t grid = (ntiles + tiles_per_cta - 1) / tiles_per_cta;
   if (grid > ALIGNQ_NUM_SMS) grid = ALIGNQ_NUM_SMS;
   if (grid < 1) grid = 1;
   cudaError_t e;

@@ -46,7 +46,7 @@ constexpr int KSTEPS = NT / 16;
 template <bool SPLIT, bool FUSED, int RBT>
 __global__ void __launch_bounds__(NT, CTAS_PER_SM)
 gram_tc_small_kernel(const float* __restrict__ x, int B, int64_t F, float eps, ActQ q, float* __restrict__ y,
-                     float* __restrict__ partials, int64_t ntiles) {
+                     float* __restrict__ partials, int64_t ntiles, double* __restrict__ zero_acc) {
   constexpr int NCOLS = FUSED ? 64 : 32;                          // accumulator columns per set = MMA N
   // both operands MN-major (bits 15, 16)
   constexpr uint32_t IDESC = make_idesc(1u /*bf16*/, 64u, (uint32_t)NCOLS) | (1u << 15) | (1u << 16);
@@ -54,6 +54,7 @@ gram_tc_small_kernel(const float* __restrict__ x, int B, int64_t F, float eps, A
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n = threadIdx.x;
+  if (zero_acc && blockIdx.x == 0 && threadIdx.x < 4) zero_acc[threadIdx.x] = 0.0;     // arms gram_finish_tc_kernel
 
   for (int i = threadIdx.x; i < OFF_BAR / 16; i += NT) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (threadIdx.x == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_barrier_init(); }
@@ -193,7 +194,7 @@ gram_tc_small_kernel(const float* __restrict__ x, int B, int64_t F, float eps, A
 
 template <bool SPLIT, bool FUSED, int RBT>
 static int launch_rbt(const float* x, int B, int64_t F, float eps, ActQ q, float* y, float* partials, int64_t cap,
-                  int* nparts, cudaStream_t s) {
+                  int* nparts, double* zero_acc, cudaStream_t s) {
   const int64_t ntiles = (F + NT - 1) / NT;
   int64_t grid = ntiles;
   if (grid > (int64_t)ALIGNQ_NUM_SMS * CTAS_PER_SM) grid = (int64_t)ALIGNQ_NUM_SMS * CTAS_PER_SM;
@@ -201,7 +202,7 @@ static int launch_rbt(const float* x, int B, int64_t F, float eps, ActQ q, float
   if (grid < 1) grid = 1;
   cudaError_t e = cudaFuncSetAttribute(gram_tc_small_kernel<SPLIT, FUSED, RBT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (e != cudaSuccess) return (int)e;
-  gram_tc_small_kernel<SPLIT, FUSED, RBT><<<(unsigned)grid, NT, SMEM_BYTES, s>>>(x, B, F, eps, q, y, partials, ntiles);
+  gram_tc_small_kernel<SPLIT, FUSED, RBT><<<(unsigned)grid, NT, SMEM_BYTES, s>>>(x, B, F, eps, q, y, partials, ntiles, zero_acc);
   ALIGNQ_LAUNCH_CHECK();
   *nparts = (int)grid;
   return ALIGNQ_OK;
@@ -209,26 +210,26 @@ static int launch_rbt(const float* x, int B, int64_t F, float eps, ActQ q, float
 
 template <bool SPLIT, bool FUSED>
 static int launch(const float* x, int B, int64_t F, float eps, ActQ q, float* y, float* partials, int64_t cap,
-                  int* nparts, cudaStream_t s) {
-  if (B <= 8) return launch_rbt<SPLIT, FUSED, 8>(x, B, F, eps, q, y, partials, cap, nparts, s);
-  if (B <= 16) return launch_rbt<SPLIT, FUSED, 16>(x, B, F, eps, q, y, partials, cap, nparts, s);
-  if (B <= 24) return launch_rbt<SPLIT, FUSED, 24>(x, B, F, eps, q, y, partials, cap, nparts, s);
-  if (B <= 28) return launch_rbt<SPLIT, FUSED, 28>(x, B, F, eps, q, y, partials, cap, nparts, s);
-  return launch_rbt<SPLIT, FUSED, 32>(x, B, F, eps, q, y, partials, cap, nparts, s);
+                  int* nparts, double* zero_acc, cudaStream_t s) {
+  if (B <= 8) return launch_rbt<SPLIT, FUSED, 8>(x, B, F, eps, q, y, partials, cap, nparts, zero_acc, s);
+  if (B <= 16) return launch_rbt<SPLIT, FUSED, 16>(x, B, F, eps, q, y, partials, cap, nparts, zero_acc, s);
+  if (B <= 24) return launch_rbt<SPLIT, FUSED, 24>(x, B, F, eps, q, y, partials, cap, nparts, zero_acc, s);
+  if (B <= 28) return launch_rbt<SPLIT, FUSED, 28>(x, B, F, eps, q, y, partials, cap, nparts, zero_acc, s);
+  return launch_rbt<SPLIT, FUSED, 32>(x, B, F, eps, q, y, partials, cap, nparts, zero_acc, s);
 }
 
 }  // namespace tcs
 
 // Partials [cta][nacc][B][B] like gram_tc.cu; the caller reduces them with the same kernel.
 int gram_tc_small_partials(const float* x, int B, int64_t F, float eps, ActQ q, int fused, float* y, float* partials,
-                           int64_t cap, int gram_mode, int* nparts, cudaStream_t s) {
+                           int64_t cap, int gram_mode, int* nparts, double* zero_acc, cudaStream_t s) {
   if (B > tcs::RB || B < 2) return ALIGNQ_ERANGE;
   if (gram_mode == ALIGNQ_GRAM_TF32X3)
-    return fused ? tcs::launch<true, true>(x, B, F, eps, q, y, partials, cap, nparts, s)
-                 : tcs::launch<true, false>(x, B, F, eps, q, y, partials, cap, nparts, s);
+    return fused ? tcs::launch<true, true>(x, B, F, eps, q, y, partials, cap, nparts, zero_acc, s)
+                 : tcs::launch<true, false>(x, B, F, eps, q, y, partials, cap, nparts, zero_acc, s);
   if (gram_mode == ALIGNQ_GRAM_BF16)
-    return fused ? tcs::launch<false, true>(x, B, F, eps, q, y, partials, cap, nparts, s)
-                 : tcs::launch<false, false>(x, B, F, eps, q, y, partials, cap, nparts, s);
+    return fused ? tcs::launch<false, true>(x, B, F, eps, q, y, partials, cap, nparts, zero_acc, s)
+                 : tcs::launch<false, false>(x, B, F, eps, q, y, partials, cap, nparts, zero_acc, s);
   return ALIGNQ_EINVAL;
 }
 

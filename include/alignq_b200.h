@@ -154,7 +154,7 @@ int alignq_sgd_step(const alignq_sgd_tensor_t* tensors, const int32_t* chunk_ten
                     const int32_t* tensor_chunk0, int ntensors, int64_t nchunks,
                     float lam, float lam2, int bitW, float grad_scale, alignq_stream_t stream);
 
-/* ---- bf16 Gram on the tensor cores (TMA + tcgen05, split-K) ---------------------------------------
+/* ---- bf16 Gram on the tensor cores (cp.async- or TMA-fed tcgen05 pipeline, split-K) ------------------
  * G = X X^T (divided by F if divide_by_F) for X [B <= 256, F] bf16 row-major, F % 8 == 0, 16-byte
  * aligned: the dense contraction of corr() (QB:137) for operands already standardised and stored
  * in bf16 (the tensor-bound micro-shape of SURVEY.md 8d).  G: [B, B] fp32.

@@ -11,8 +11,11 @@
 // registers and every global access is a coalesced 128-bit load.  Block totals are added to fp64
 // accumulators with one atomic per value; the LAST block to finish (threadfence + ticket, no
 // spinning) finalises the statistics and re-zeroes accumulators and ticket -- no extra launch, no memset.
+#include <cooperative_groups.h>
 #include "common.cuh"
 #include "../../include/alignq_b200.h"
+
+namespace cg = cooperative_groups;
 
 namespace alignq {
 
@@ -271,6 +274,118 @@ bnq_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ y, c
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Single-launch backward for small and mid-size tensors (up to ~24 MB: every layer of ResNet-20, most of DenseNet-40
+// and MobileNet-v2), where the reduce + apply pair above costs 9-35 us and much of it is latency: launch,
+// last-block ticket, finalize, launch, per-channel parameter loads.  One COOPERATIVE launch does reduce -> grid
+// barrier -> apply; every block re-derives the per-channel coefficients from the fp64 accumulators after the
+// barrier (C <= 256: a few KB from L2), so there is no ticket and no serial finalize.  Measured (graph replay):
+// [128,16,32,32] 15.4 -> 12.5 us, [128,168,16,16] 35.1 -> 24.9 us, [256,24,32,32] 34.7 -> 27.8 us; above ~24 MB
+// it is a wash, and for the FORWARD pair the same fusion was slower (the apply pass prefers twice the blocks), so
+// only the backward uses it.  The accumulators are double-buffered by a device-side epoch (counter[1]): a launch
+// uses set (epoch & 1), which the previous launch on the same workspace zeroed, and zeroes the other one; block 0
+// bumps the epoch after the barrier.  Its two sets live behind the set the two-kernel paths use.
+__device__ __forceinline__ void fused_zero_other(double* other, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) other[i] = 0.0;
+}
+
+__global__ void __launch_bounds__(BN_MAX_THREADS)
+bnq_bwd_fused_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ gy, int64_t R,
+                     int C, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     const float* __restrict__ mean, const float* __restrict__ invstd, int training, BnQ q,
+                     float* __restrict__ gx, float* __restrict__ g_residual, float* __restrict__ ggamma,
+                     float* __restrict__ gbeta, double* __restrict__ ws, unsigned* __restrict__ epoch) {
+  extern __shared__ float sh[];
+  cg::grid_group grid = cg::this_grid();
+  const int C4 = C >> 2, k = blockDim.x / C4;
+  const int c4 = threadIdx.x % C4, rsub = threadIdx.x / C4;
+  const unsigned ep = *reinterpret_cast<volatile unsigned*>(epoch);
+  const int setn = BN_SLOTS * C * 2;
+  double* acc = ws + (size_t)(1u + (ep & 1u)) * setn;             // sets 1 and 2; set 0 belongs to the two-kernel paths
+  fused_zero_other(ws + (size_t)(1u + ((ep & 1u) ^ 1u)) * setn, setn);
+  float m[4], is[4], g[4], b[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = 4 * c4 + j;
+    m[j] = mean[c]; is[j] = invstd[c]; g[j] = gamma ? gamma[c] : 1.f; b[j] = beta ? beta[c] : 0.f;
+  }
+  // ---- phase 1: sum g_z, sum g_z * xhat ----
+  float db[4] = {0, 0, 0, 0}, dg[4] = {0, 0, 0, 0};
+  const int64_t stride = (int64_t)gridDim.x * k;
+  const Lane4 ones = {{1.f, 1.f, 1.f, 1.f}};
+  for (int64_t r = (int64_t)blockIdx.x * k + rsub; r < R; r += 4 * stride) {
+    Lane4 xs_[4], gs_[4], ys_[4];
+    bool ok[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      ok[u] = r + u * stride < R;
+      const int64_t o = (r + u * stride) * C + 4 * c4;
+      xs_[u] = ok[u] ? ld4(x + o) : ones;
+      gs_[u] = ok[u] ? ld4(gy + o) : ones;
+      ys_[u] = (ok[u] && q.relu) ? ld4(y + o) : ones;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (!ok[u]) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float xh = (xs_[u].v[j] - m[j]) * is[j];
+        const float gz = bnq_gz(fmaf(xh, g[j], b[j]), gs_[u].v[j], ys_[u].v[j], q);
+        db[j] += gz;
+        dg[j] = fmaf(gz, xh, dg[j]);
+      }
+    }
+  }
+  block_accumulate(db, dg, C4, k, sh, acc);
+  __threadfence();
+  grid.sync();
+  float* sm_k1 = sh;
+  float* sm_k2 = sh + C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double S = 0.0, SS = 0.0;
+#pragma unroll
+    for (int sl = 0; sl < BN_SLOTS; ++sl) {
+      const double* a = acc + ((size_t)sl * C + c) * 2;
+      S += __ldcg(a); SS += __ldcg(a + 1);
+    }
+    sm_k1[c] = (float)(S / (double)R);
+    sm_k2[c] = (float)(SS / (double)R);
+    if (blockIdx.x == 0) {
+      if (gbeta) gbeta[c] = (float)S;
+      if (ggamma) ggamma[c] = (float)SS;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *epoch = ep + 1u;
+  __syncthreads();
+  float k1[4], k2[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    k1[j] = training ? sm_k1[4 * c4 + j] : 0.f;
+    k2[j] = training ? sm_k2[4 * c4 + j] : 0.f;
+  }
+  // ---- phase 2: gx (and the shortcut's gradient) ----
+  for (int64_t r = (int64_t)blockIdx.x * k + rsub; r < R; r += stride) {
+    const int64_t o = r * C + 4 * c4;
+    const Lane4 xv = ld4(x + o), gv = ld4(gy + o);
+    Lane4 yv = {{1.f, 1.f, 1.f, 1.f}};
+    if (q.relu) yv = ld4(y + o);
+    float out[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float xh = (xv.v[j] - m[j]) * is[j];
+      const float gz = bnq_gz(fmaf(xh, g[j], b[j]), gv.v[j], yv.v[j], q);
+      out[j] = g[j] * is[j] * (gz - k1[j] - xh * k2[j]);
+    }
+    *reinterpret_cast<float4*>(gx + o) = make_float4(out[0], out[1], out[2], out[3]);
+    if (g_residual) {
+      float gr[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) gr[j] = (q.relu && !(yv.v[j] > 0.f)) ? 0.f : gv.v[j];
+      *reinterpret_cast<float4*>(g_residual + o) = make_float4(gr[0], gr[1], gr[2], gr[3]);
+    }
+  }
+}
+
 struct BnLaunch { int threads, grid, k; size_t smem; };
 static BnLaunch bn_launch(int64_t R, int C, int max_grid = BN_MAX_GRID) {
   BnLaunch L;
@@ -283,6 +398,16 @@ static BnLaunch bn_launch(int64_t R, int C, int max_grid = BN_MAX_GRID) {
   L.grid = (int)g;
   L.smem = (size_t)L.threads * 8 * sizeof(float);
   return L;
+}
+
+// The single-launch path: small tensors, narrow layers, and a grid that is co-resident (cooperative launch).
+static bool bn_use_fused(int64_t R, int C, int64_t max_elems) { return C <= 256 && R * (int64_t)C <= max_elems; }
+template <typename K>
+static int bn_coop_grid(K kernel, const BnLaunch& L) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, L.threads, L.smem) != cudaSuccess || per_sm < 1) return 0;
+  const int cap = per_sm * ALIGNQ_NUM_SMS;
+  return L.grid < cap ? L.grid : cap;
 }
 
 static BnQ make_bnq(int a_bit, float act_range, int variant, int relu) {
@@ -306,7 +431,9 @@ using namespace alignq;
 
 extern "C" size_t alignq_bn_act_ws_doubles(int C) {
   if (C <= 0) return 0;
-  return (size_t)BN_SLOTS * C * 2 + (size_t)C;   // fp64 accumulators [slots][C][2] (ZERO before first use) + [C][2] float coefficients
+  // three fp64 accumulator sets [3][slots][C][2] (ZERO before first use: one for the two-kernel paths, two that the
+  // single-launch backward alternates between) + [C][2] float coefficients
+  return (size_t)3 * BN_SLOTS * C * 2 + (size_t)C;
 }
 
 extern "C" int alignq_bn_act_fwd(const float* x, int64_t rows, int C, const float* gamma, const float* beta,
@@ -345,8 +472,22 @@ extern "C" int alignq_bn_act_bwd(const float* x, const float* y, const float* gy
   if ((relu && !aligned16(y)) || (g_residual && !aligned16(g_residual))) return ALIGNQ_EALIGN;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const BnLaunch L = bn_launch(rows, C);
-  const BnQ q = make_bnq(a_bit, act_range, variant, relu);
-  float* coef = reinterpret_cast<float*>(ws + (size_t)BN_SLOTS * C * 2);       // [C][2] floats after the accumulators
+  BnQ q = make_bnq(a_bit, act_range, variant, relu);
+  if (bn_use_fused(rows, C, (int64_t)6 << 20)) {
+    const int grid = bn_coop_grid(bnq_bwd_fused_kernel, L);
+    if (grid > 0) {
+      uint32_t* epoch = counter + 1;
+      void* args[] = {(void*)&x, (void*)&y, (void*)&gy, (void*)&rows, (void*)&C, (void*)&gamma, (void*)&beta, (void*)&save_mean,
+                      (void*)&save_invstd, (void*)&training, (void*)&q, (void*)&gx, (void*)&g_residual, (void*)&ggamma,
+                      (void*)&gbeta, (void*)&ws, (void*)&epoch};
+      if (cudaLaunchCooperativeKernel((void*)bnq_bwd_fused_kernel, dim3(grid), dim3(L.threads), args, L.smem, s) == cudaSuccess) {
+        ALIGNQ_LAUNCH_CHECK();
+        return ALIGNQ_OK;
+      }
+      (void)cudaGetLastError();
+    }
+  }
+  float* coef = reinterpret_cast<float*>(ws + (size_t)3 * BN_SLOTS * C * 2);       // [C][2] floats after the accumulators
   bnq_bwd_reduce_kernel<<<L.grid, L.threads, L.smem, s>>>(x, y, gy, rows, C, gamma, beta, save_mean, save_invstd, q,
                                                           ggamma, gbeta, coef, ws, counter);
   ALIGNQ_LAUNCH_CHECK();

@@ -17,17 +17,15 @@ import torch.nn.functional as F
 from .. import _lib as L
 from ..utils.options import args
 
-_ws_cache = {}
-
-
-def _bn_ws(C: int, device):
-    """(fp64 scratch, zero-initialised ticket counter) per device; stream-ordered reuse across layers."""
-    need = int(L.load().alignq_bn_act_ws_doubles(max(C, 1024)))
-    ent = _ws_cache.get(device.index)
-    if ent is None or ent[0].numel() < need:
-        counter = ent[1] if ent is not None else torch.zeros(1, dtype=torch.int32, device=device)
-        ent = (torch.zeros(need, dtype=torch.float64, device=device), counter)   # kernels keep it zeroed
-        _ws_cache[device.index] = ent
+def _bn_ws(bn, C: int, device):
+    """(fp64 scratch, two zero-initialised uint32: ticket, epoch) of ONE BatchNorm layer.  The single-launch
+    backward alternates between two accumulator sets and leaves the one it used dirty for the next launch on the
+    same workspace to clear, so the scratch must not be shared between layers of different width."""
+    ent = getattr(bn, "_alignq_bn_ws", None)
+    need = int(L.load().alignq_bn_act_ws_doubles(C))
+    if ent is None or ent[0].device != device or ent[0].numel() < need:
+        ent = (torch.zeros(need, dtype=torch.float64, device=device), torch.zeros(2, dtype=torch.int32, device=device))
+        bn._alignq_bn_ws = ent
     return ent
 
 
@@ -40,7 +38,8 @@ class _BnActFn(torch.autograd.Function):
         y = torch.empty_like(x)
         mean = torch.empty(C, dtype=torch.float32, device=x.device)
         invstd = torch.empty(C, dtype=torch.float32, device=x.device)
-        ws, counter = _bn_ws(C, x.device)
+        ws, counter = _bn_ws(bn, C, x.device)
+        ctx.bn = bn
         with torch.cuda.device_of(x):
             L.check(L.load().alignq_bn_act_fwd(
                 x.data_ptr(), rows, C, L.ptr(weight), L.ptr(bias), L.ptr(bn.running_mean), L.ptr(bn.running_var),
@@ -62,7 +61,7 @@ class _BnActFn(torch.autograd.Function):
         gr = torch.empty_like(x) if (has_res and ctx.needs_input_grad[8]) else None
         gw = torch.empty(C, dtype=torch.float32, device=x.device) if weight is not None else None
         gb = torch.empty(C, dtype=torch.float32, device=x.device) if bias is not None else None
-        ws, counter = _bn_ws(C, x.device)
+        ws, counter = _bn_ws(ctx.bn, C, x.device)
         with torch.cuda.device_of(x):
             L.check(L.load().alignq_bn_act_bwd(
                 x.data_ptr(), L.ptr(y), gy.data_ptr(), rows, C, L.ptr(weight), L.ptr(bias), mean.data_ptr(),

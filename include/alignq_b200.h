@@ -172,7 +172,9 @@ int alignq_gram_bf16(const void* x_bf16, int B, int64_t F, int divide_by_F, floa
  * `momentum` (unbiased variance) unless NULL, *num_batches_tracked += 1 unless NULL; training == 0:
  * running statistics.  save_mean /
  * save_invstd: [C] out (forward) / in (backward).  ws: alignq_bn_act_ws_doubles(C) doubles and
- * counter: one uint32 -- both must be ZERO before the first call (the kernels re-arm them).
+ * counter: TWO uint32 -- both must be ZERO before the first call and belong to ONE layer (one value of
+ * C): the kernels keep state in them between calls (counter[0]: a ticket they re-arm; counter[1]: the
+ * epoch of the single-launch backward, which says which of its two accumulator sets is clean).
  * `residual` (nullable, same layout): y = relu(q(bn(x)) + residual), the block tail `out += shortcut;
  * F.relu(out)` (resnet.py:77-78); g_residual (nullable) receives its gradient.
  * Backward: g_z = gy [y > 0 if relu] * 2 ar phi(z) (z = BN output), then the BatchNorm backward;

@@ -13,8 +13,8 @@ g = torch.rand(C, device=dev) + 0.5; b = torch.randn(C, device=dev) * 0.1
 rm = torch.zeros(C, device=dev); rv = torch.ones(C, device=dev)
 mean = torch.empty(C, device=dev); invstd = torch.empty(C, device=dev)
 gg = torch.empty(C, device=dev); gb = torch.empty(C, device=dev)
-ws = torch.zeros(int(lib.alignq_bn_act_ws_doubles(max(C, 1024))), dtype=torch.float64, device=dev)
-counter = torch.zeros(1, dtype=torch.int32, device=dev)
+ws = torch.zeros(int(lib.alignq_bn_act_ws_doubles(C)), dtype=torch.float64, device=dev)
+counter = torch.zeros(2, dtype=torch.int32, device=dev)
 for _ in range(2):
     L.check(lib.alignq_bn_act_fwd(x.data_ptr(), rows, C, g.data_ptr(), b.data_ptr(), rm.data_ptr(), rv.data_ptr(), 0.1, 1e-5, 1,
             8, 2.0, 0, 1, 0, y.data_ptr(), mean.data_ptr(), invstd.data_ptr(), ws.data_ptr(), counter.data_ptr(), 0, L.stream_ptr()), "fwd")

@@ -24,7 +24,7 @@ extern "C" int alignq_corr_fwd(const float* x, const float* y, int B, int64_t F,
   if (B < 1 || F < 1 || !x || !y || !G || !ws) return ALIGNQ_EINVAL;
   if (B > 1024) return ALIGNQ_ERANGE;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (gram_mode == ALIGNQ_GRAM_FP32 || x != y) {
+  if (gram_mode == ALIGNQ_GRAM_FP32 || x != y || B > 128 || B < 2) {      // tcgen05 paths: one batch tile, 2 <= B <= 128
     ActQ q{0.f, 0.f, 0.f, 0};
     int nslabs = 0;
     int rc = gram_ffma_forward(x, y, B, F, eps, 0, q, nullptr, ws_partials(ws, B), &nslabs, ws_bytes, s);
@@ -48,7 +48,7 @@ extern "C" int alignq_act_admm_fwd(const float* x, int B, int64_t F, int a_bit, 
   q.n = (a_bit == 32) ? 1.0f : (float)((1ull << a_bit) - 1);
   q.inv_n = 1.0f / q.n;
   int rc;
-  if (gram_mode == ALIGNQ_GRAM_FP32) {
+  if (gram_mode == ALIGNQ_GRAM_FP32 || B > 128 || B < 2) {          // larger batches: the fp32 FFMA kernels
     int nslabs = 0;
     rc = gram_ffma_forward(x, x, B, F, eps, 1, q, y, ws_partials(ws, B), &nslabs, ws_bytes, s);
     if (rc) return rc;

@@ -536,6 +536,27 @@ def test_tc_fused_forward_vs_fp32_mode_and_oracle(mode, variant, B, shape):
         assert e <= 1e-2, f"gx bf16 backward rel-norm err {e:.2e}"
 
 
+def test_tensor_core_modes_fall_back_to_fp32_kernels_above_128_rows():
+    """The tcgen05 kernels cover one batch tile (2 <= B <= 128); above that every gram_mode runs the fp32 FFMA
+    kernels (forward and backward), so the results are bit-identical to gram_mode='fp32'."""
+    torch.manual_seed(31)
+    B, shape = 160, (4, 8, 8)
+    admm = aq.ADMM(B).to(DEV)
+    x0 = torch.randn(B, *shape, device=DEV)
+    gy = torch.randn_like(x0)
+    res = {}
+    for m in ("fp32", "tf32x3", "bf16"):
+        aq.set_args(variant="B", act_range=2, method="ours", gram_mode=m)
+        x = x0.clone().requires_grad_(True)
+        y, loss = aq.activation_quantize_fn(8, "second", admm)(x)
+        ((y * gy).sum() + loss).backward()
+        G = aq.corr(x0.view(B, -1), x0.view(B, -1), 0.0)
+        res[m] = (y.detach(), loss.detach(), admm.D.clone(), x.grad.clone(), G)
+    for m in ("tf32x3", "bf16"):
+        for a, b in zip(res[m], res["fp32"]):
+            assert torch.equal(a, b)
+
+
 def test_channels_last_activations_need_no_layout_copy():
     """NHWC (channels_last) activations go through the same kernels in place: element-wise results are
     identical element for element, and the ADMM Gram / trans_loss are invariant under the feature permutation."""

@@ -11,6 +11,7 @@
 // registers and every global access is a coalesced 128-bit load.  Block totals are added to fp64
 // accumulators with one atomic per value; the LAST block to finish (threadfence + ticket, no
 // spinning) finalises the statistics and re-zeroes accumulators and ticket -- no extra launch, no memset.
+// The backward of tensors up to ~24 MB runs as ONE cooperative launch instead (bnq_bwd_fused_kernel below).
 #include <cooperative_groups.h>
 #include "common.cuh"
 #include "../../include/alignq_b200.h"

@@ -13,13 +13,17 @@
 //      K-major no-swizzle layout (8-row x 16-byte core matrices),
 //   4. one elected thread issues tcgen05.mma (M = N = 128, A and B descriptors on the same tiles)
 //      accumulating in TMEM; tcgen05.commit -> mbarrier releases the smem stage.
-// Two smem stages overlap the MMAs of tile i with the ALU work of tile i+1.  Split-K over CTAs;
-// every CTA dumps its TMEM accumulators as fp32 partials, reduced by gram_reduce_tc_kernel.
+// Two smem stages overlap the MMAs of tile i with the ALU work of tile i+1.  Split-K over ONE wave of CTAs with
+// equal tile counts; every CTA dumps its TMEM accumulators as fp32 partials, which gram_reduce_tc_kernel sums --
+// or, for the fused forward, gram_finish_tc_kernel, which also evaluates ADMM.forward(D) and dL/dD in the same
+// launch.  Batches of 2..32 rows take the thread-per-column kernels of gram_tc_small.cu instead.
 //
 // Numerics modes
 //   ALIGNQ_GRAM_TF32X3: kind::tf32 with the operand split xs = H + L (H = top 19 bits):
-//       G = H H^T + H L^T + L H^T  (the L L^T term, <= 2^-22 relative, is dropped): three MMAs per
-//       k-step into ONE accumulator, fp32-level accuracy (tested to 1e-5 relative).
+//       G = H H^T + H L^T + L H^T  (the L L^T term, <= 2^-22 relative, is dropped): three MMAs per k-step.
+//       The tensor core TRUNCATES when it adds into the fp32 accumulator (~4.6e-8 relative per accumulate), so
+//       the small cross products have their own accumulator and both are flushed into the fp32 partials every
+//       FLUSH_TILES tiles: fp32-level accuracy independent of F (tested to 1e-5 relative).
 //   ALIGNQ_GRAM_BF16:   kind::f16 with bf16 operands, one MMA per k-step (tested to 1e-2 relative).
 #include <cuda_bf16.h>
 

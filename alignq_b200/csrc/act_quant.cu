@@ -38,7 +38,7 @@ __device__ __forceinline__ float act_fwd_one(float x, const ActParams& p, int& c
 }
 
 template <int VARIANT, int MODE, bool CODES, int UNROLL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 act_fwd_vec_kernel(const float4* __restrict__ x, float4* __restrict__ y, short4* __restrict__ codes,
                    int64_t n4, ActParams p) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;

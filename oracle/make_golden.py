@@ -231,8 +231,9 @@ def worker(variant: str) -> None:
                 _same(po[i], p.detach(), f"sgd {cfg_name} p step{s_} #{i}")
                 _same(og[i], p.grad.detach(), f"sgd {cfg_name} grad step{s_} #{i}")
 
-    os.makedirs(os.path.join(REPO, "tests", "golden"), exist_ok=True)
-    path = os.path.join(REPO, "tests", "golden", f"l1_{variant}.npz")
+    outdir = os.environ.get("ALIGNQ_GOLDEN_OUT") or os.path.join(REPO, "tests", "golden")   # tests regenerate into a temp dir
+    os.makedirs(outdir, exist_ok=True)
+    path = os.path.join(outdir, f"l1_{variant}.npz")
     np.savez_compressed(path, **out)
     print(f"variant {variant}: oracle == reference on {len(out)} arrays; wrote {path} "
           f"({os.path.getsize(path) / 1024:.0f} KiB)")

@@ -47,6 +47,7 @@ SIGNATURES = {
     "alignq_wq_backward": (_I, [_P, _P, _P, _P, _P, _P, _I, _L, _I, _P, _P, _I, _P, _P]),
     "alignq_gram_ws_bytes": (_Z, [_I, _L]),
     "alignq_corr_fwd": (_I, [_P, _P, _I, _L, _F, _P, _P, _Z, _I, _P]),
+    "alignq_corr_bwd": (_I, [_P, _P, _P, _I, _L, _F, _P, _P, _P, _Z, _P]),
     "alignq_act_admm_fwd": (_I, [_P, _I, _L, _I, _F, _F, _P, _P, _I, _F, _F, _P, _P, _P, _P, _P, _Z, _I, _P]),
     "alignq_act_admm_bwd": (_I, [_P, _P, _P, _P, _I, _L, _I, _F, _F, _P, _P, _Z, _I, _P]),
     "alignq_admm_loss": (_I, [_P, _I, _P, _P, _I, _I, _F, _F, _P, _I, _P, _P, _P, _P, _P]),

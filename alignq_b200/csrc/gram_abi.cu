@@ -34,6 +34,17 @@ extern "C" int alignq_corr_fwd(const float* x, const float* y, int B, int64_t F,
   return gram_tc_corr(x, B, F, eps, G, ws, ws_bytes, gram_mode, s);
 }
 
+extern "C" int alignq_corr_bwd(const float* x, const float* y, const float* dG, int B, int64_t F, float eps, float* gx,
+                               float* gy, void* ws, size_t ws_bytes, alignq_stream_t stream) {
+  if (B < 2 || F < 1 || !x || !y || !dG || !ws) return ALIGNQ_EINVAL;
+  if (B > 1024) return ALIGNQ_ERANGE;
+  if (x == y && gy && gy != gx) return ALIGNQ_EINVAL;            // one operand, one gradient
+  const size_t w = gram_wsym_floats(B);
+  if (ws_bytes < 2 * w * sizeof(float)) return ALIGNQ_ENOSPACE;
+  float* wt = reinterpret_cast<float*>(ws);
+  return corr_ffma_backward(x, y, dG, B, F, eps, gx, gy, wt, wt + w, reinterpret_cast<cudaStream_t>(stream));
+}
+
 extern "C" int alignq_act_admm_fwd(const float* x, int B, int64_t F, int a_bit, float act_range, float eps,
                                    const float* Z, const float* U, int dim, float mu, float rho, float* y, float* D,
                                    float* loss, float* dLdD, void* ws, size_t ws_bytes, int gram_mode,

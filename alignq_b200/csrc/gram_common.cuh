@@ -29,6 +29,9 @@ int gram_ffma_forward(const float* xa, const float* xb, int B, int64_t F, float 
 int gram_ffma_backward(const float* x, const float* gy, const float* Wsym, int Bp, const float* gloss, int B,
                        int64_t F, float ar, float eps, float* gx, cudaStream_t s);
 
+int corr_ffma_backward(const float* x, const float* y, const float* dG, int B, int64_t F, float eps, float* gx, float* gy,
+                       float* wt0, float* wt1, cudaStream_t s);
+
 #ifdef __CUDACC__
 __device__ __forceinline__ float act_map_t(float x, float ar) {           // QB:49-56
   return __fmul_rn(sym_map(normal_cdf_std(x)), ar);

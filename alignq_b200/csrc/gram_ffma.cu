@@ -307,6 +307,157 @@ gram_ffma_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gy, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Backward of the stand-alone corr(a, b) (quantization.py:134-137) with respect to ONE operand a, for an upstream
+// dG:  gAs = W Bs / F  with  Wt[j][i] = W[i][j]  (W = dG for a = x, dG^T for a = y, dG + dG^T when x is y),
+// then the standardise backward of a.  SAME: b aliases a (one tile, one set of statistics).
+__device__ __forceinline__ void col_stats_rows(const float* __restrict__ S, int B, float* __restrict__ mu, float* __restrict__ sd) {
+  const int k = threadIdx.x >> 3, l = threadIdx.x & 7;
+  float s = 0.f;
+  for (int i = l; i < B; i += 8) s += S[i * KTP + k];
+  s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 4);
+  const float m = s / (float)B;
+  float ss = 0.f;
+  for (int i = l; i < B; i += 8) { const float d = S[i * KTP + k] - m; ss = fmaf(d, d, ss); }
+  ss += __shfl_xor_sync(0xffffffffu, ss, 1); ss += __shfl_xor_sync(0xffffffffu, ss, 2); ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+  if (l == 0) { mu[k] = m; sd[k] = sqrtf(ss / (float)(B - 1)); }
+}
+
+template <bool SAME>
+__global__ void __launch_bounds__(GT)
+corr_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ Wt, int B, int Bp,
+                int64_t F, float eps, int tiles_per_slab, float* __restrict__ ga) {
+  extern __shared__ __align__(16) float smem[];
+  float* CA = smem;                                   // a tile: raw -> centred
+  float* CB = SAME ? CA : CA + B * KTP;               // b tile: raw -> centred
+  float* G = CB + B * KTP;
+  float* muA = G + B * KTP;
+  float* sdA = muA + KT;
+  float* muB = sdA + KT;
+  float* sdB = muB + KT;
+  float* red = sdB + KT;                              // [2 KT]
+  const float invF = 1.0f / (float)F;
+  const int64_t ntiles = (F + KT - 1) / KT;
+  const int64_t t0 = (int64_t)blockIdx.x * tiles_per_slab;
+  const int64_t t1 = (t0 + tiles_per_slab < ntiles) ? t0 + tiles_per_slab : ntiles;
+  for (int64_t t = t0; t < t1; ++t) {
+    const int64_t f0 = t * KT;
+    const int valid = (int)((F - f0 < KT) ? (F - f0) : KT);
+    __syncthreads();
+    for (int e = threadIdx.x; e < B * KT; e += GT) {
+      const int i = e / KT, k = e - i * KT;
+      CA[i * KTP + k] = (k < valid) ? a[(int64_t)i * F + f0 + k] : 0.f;
+      if (!SAME) CB[i * KTP + k] = (k < valid) ? b[(int64_t)i * F + f0 + k] : 0.f;
+    }
+    __syncthreads();
+    col_stats_rows(CA, B, muA, sdA);
+    if (!SAME) col_stats_rows(CB, B, muB, sdB);
+    __syncthreads();
+    for (int e = threadIdx.x; e < B * KT; e += GT) {
+      const int i = e / KT, k = e - i * KT;
+      CA[i * KTP + k] = (k < valid) ? (CA[i * KTP + k] - muA[k]) : 0.f;
+      if (!SAME) CB[i * KTP + k] = (k < valid) ? (CB[i * KTP + k] - muB[k]) : 0.f;
+    }
+    __syncthreads();
+    const float* sdb = SAME ? sdA : sdB;
+    {
+      const int kq = threadIdx.x & 7, ig = threadIdx.x >> 3;
+      float rs[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) rs[c] = invF / (sdb[4 * kq + c] + eps);
+      for (int ib = 0; ib < Bp; ib += 128) {
+        const int i = ib + 4 * ig;
+        if (i >= Bp) continue;
+        float acc[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+        for (int j = 0; j < B; ++j) {
+          const float4 w4 = __ldg(reinterpret_cast<const float4*>(Wt + (size_t)j * Bp + i));
+          const float w[4] = {w4.x, w4.y, w4.z, w4.w};
+          const float* sp = CB + j * KTP + 4 * kq;
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(w[r], sp[c], acc[r][c]);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+          if (i + r < B)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) G[(i + r) * KTP + 4 * kq + c] = acc[r][c] * rs[c];
+      }
+    }
+    __syncthreads();
+    {
+      const int k = threadIdx.x >> 3, l = threadIdx.x & 7;
+      float u = 0.f, v = 0.f;
+      for (int i = l; i < B; i += 8) { const float g = G[i * KTP + k]; u += g; v = fmaf(g, CA[i * KTP + k], v); }
+      u += __shfl_xor_sync(0xffffffffu, u, 1); u += __shfl_xor_sync(0xffffffffu, u, 2); u += __shfl_xor_sync(0xffffffffu, u, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 4);
+      if (l == 0) { red[k] = u / (float)B; red[KT + k] = v; }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < B * KT; e += GT) {
+      const int i = e / KT, k = e - i * KT;
+      if (k >= valid) continue;
+      const float se = sdA[k] + eps;
+      const float dsd = -red[KT + k] / (se * se);
+      const float through_sd = (sdA[k] > 0.f) ? dsd * CA[i * KTP + k] / ((float)(B - 1) * sdA[k]) : 0.f;   // torch masks std == 0
+      ga[(int64_t)i * F + f0 + k] = (G[i * KTP + k] - red[k]) / se + through_sd;
+    }
+  }
+}
+
+// Wt[j][i] (leading dimension Bp, zero padded) from dG [B][B]: mode 0: dG[i][j] (transpose), 1: dG[j][i], 2: both added
+__global__ void corr_wt_kernel(const float* __restrict__ dG, int B, int Bp, int mode, float* __restrict__ Wt) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= B * Bp) return;
+  const int j = e / Bp, i = e - j * Bp;
+  float v = 0.f;
+  if (i < B) v = (mode == 0) ? dG[(size_t)i * B + j] : (mode == 1) ? dG[(size_t)j * B + i] : dG[(size_t)i * B + j] + dG[(size_t)j * B + i];
+  Wt[e] = v;
+}
+
+int corr_ffma_backward(const float* x, const float* y, const float* dG, int B, int64_t F, float eps, float* gx, float* gy,
+                       float* wt0, float* wt1, cudaStream_t s) {
+  const int Bp = gram_bp(B);
+  const bool same = (x == y);
+  const int64_t ntiles = (F + KT - 1) / KT;
+  int64_t nslabs = ntiles < 4 * ALIGNQ_NUM_SMS ? ntiles : 4 * ALIGNQ_NUM_SMS;
+  const int tiles_per_slab = (int)((ntiles + nslabs - 1) / nslabs);
+  nslabs = (ntiles + tiles_per_slab - 1) / tiles_per_slab;
+  const size_t smem = ((size_t)(same ? 2 : 3) * B * KTP + 6 * KT) * sizeof(float);
+  if (smem > 227 * 1024) return ALIGNQ_ERANGE;
+  const int nb = (B * Bp + 255) / 256;
+  if (same) {
+    if (!gx) return ALIGNQ_OK;
+    corr_wt_kernel<<<nb, 256, 0, s>>>(dG, B, Bp, 2, wt0);
+    ALIGNQ_LAUNCH_CHECK();
+    cudaError_t e = cudaFuncSetAttribute(corr_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    corr_bwd_kernel<true><<<(unsigned)nslabs, GT, smem, s>>>(x, x, wt0, B, Bp, F, eps, tiles_per_slab, gx);
+    ALIGNQ_LAUNCH_CHECK();
+    return ALIGNQ_OK;
+  }
+  cudaError_t e = cudaFuncSetAttribute(corr_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  if (gx) {                                     // gXs = dG Ys / F: Wt[j][i] = dG[i][j]
+    corr_wt_kernel<<<nb, 256, 0, s>>>(dG, B, Bp, 0, wt0);
+    ALIGNQ_LAUNCH_CHECK();
+    corr_bwd_kernel<false><<<(unsigned)nslabs, GT, smem, s>>>(x, y, wt0, B, Bp, F, eps, tiles_per_slab, gx);
+    ALIGNQ_LAUNCH_CHECK();
+  }
+  if (gy) {                                     // gYs = dG^T Xs / F: Wt[j][i] = dG[j][i]
+    corr_wt_kernel<<<nb, 256, 0, s>>>(dG, B, Bp, 1, wt1);
+    ALIGNQ_LAUNCH_CHECK();
+    corr_bwd_kernel<false><<<(unsigned)nslabs, GT, smem, s>>>(y, x, wt1, B, Bp, F, eps, tiles_per_slab, gy);
+    ALIGNQ_LAUNCH_CHECK();
+  }
+  return ALIGNQ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 static int pick_tb(int B) { return B <= 32 ? 32 : (B <= 64 ? 64 : 128); }
 
 int gram_ffma_forward(const float* xa, const float* xb, int B, int64_t F, float eps, int fused, ActQ q, float* y,

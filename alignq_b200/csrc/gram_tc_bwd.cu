@@ -8,10 +8,17 @@
 //
 // The two [B,B] x [B,32] products per 32-column tile run on the tensor cores:
 //   D[i, n] = sum_j Wsym[i, j] * Xs[j, n]          M = 128 (i), N = 32 (columns), K = 128 (batch j)
-// A = Wsym (fixed for the layer: split once into bf16 H + L, kept in shared memory in the canonical
-// K-major core-matrix layout), B = the standardised tile transposed (N x K, K-major, bf16 H + L),
-// three kind::f16 MMAs per k-step (H H + H L + L H: 16 mantissa bits per operand, ~3e-5 relative),
-// fp32 accumulators in TMEM (32 columns per source).  Thread (warp w, lane n) owns rows 8w..8w+7 of
+// A = Wsym (fixed for the layer: split once, kept in shared memory in the canonical K-major core-matrix
+// layout), B = the standardised tile transposed (N x K, K-major).  Operand precision (NS = number of bf16
+// terms per fp32 value):
+//   NS = 3 (gram_mode tf32x3, the fp32-parity mode): v = H + M + L, three bf16 terms = 24 mantissa bits, and
+//          SIX kind::f16 MMAs per k-step: H H into the main accumulator, H M + M H + H L + L H + M M into a
+//          second one (the tensor core truncates when it adds into the fp32 accumulator, ~4.6e-8 per
+//          accumulate: the five small products must not ride on the large one); dropped terms <= 2^-24.
+//          Measured against fp64 autograd: at the level of the reference's own fp32 autograd (1e-6).
+//          (Round 1 used two terms, 16 bits: 3e-5 -- above north_star's 1e-5.)
+//   NS = 1 (gram_mode bf16): one bf16 term, one MMA per k-step (1e-2 mode).
+// fp32 accumulators in TMEM (32 columns per source and accumulator).  Thread (warp w, lane n) owns rows 8w..8w+7 of
 // column n, so one 16-byte store fills a whole core-matrix row of the B operand and all global
 // accesses are coalesced 128-byte rows.  The accumulators come back through tcgen05.ld + a smem
 // transpose; the per-column reductions reuse the forward's two-level warp reduction.
@@ -20,6 +27,7 @@
 #include "common.cuh"
 #include "gram_common.cuh"
 #include "tc_common.cuh"
+#include "tc_small_common.cuh"
 #include "../../include/alignq_b200.h"
 
 namespace alignq {
@@ -29,21 +37,33 @@ using namespace tc;
 
 constexpr int KB = 32;                        // columns per tile
 constexpr int NT = 512, NW = 16, RPT = 8;     // thread (w, n): rows 8w .. 8w+7 of column n
-constexpr int LBO = 144;                      // K-adjacent core matrices (padded)
+constexpr int LBO = 144;                      // B operand: K-adjacent core matrices (padded: conflict-free stores)
 constexpr int SBO = 16 * LBO;                 // 8-row groups: K = 128 bf16 = 16 core matrices
-constexpr int A_TILE = 16 * SBO;              // Wsym operand, 128 rows                  36 864 B
 constexpr int B_TILE = 4 * SBO;               // Xs^T operand, 32 rows (columns of x)     9 216 B
-constexpr int NRAW = 3;
+constexpr int LBO_A = 128;                    // A operand is written once per CTA: dense
+constexpr int SBO_A = 16 * LBO_A;
+constexpr int A_TILE = 16 * SBO_A;            // Wsym operand, 128 rows                  32 768 B
+constexpr int NRAW = 4;
 constexpr int RAW_TILE = 128 * KB * 4;        // 16 KB
 constexpr int GS_LD = 33;
-constexpr int OFF_A = 0;                                   // [H, L]
-constexpr int OFF_B = OFF_A + 2 * A_TILE;                  // [xH, xL, tH, tL]
-constexpr int OFF_RAW = OFF_B + 4 * B_TILE;
-constexpr int OFF_GS = OFF_RAW + NRAW * RAW_TILE;          // [2][128][33] floats
-constexpr int OFF_RED = OFF_GS + 2 * 128 * GS_LD * 4;      // [NW][32] float4
-constexpr int OFF_CS = OFF_RED + NW * KB * 16;             // column stats: 3 x [32] float4
-constexpr int OFF_BAR = OFF_CS + 3 * KB * 16;
-constexpr int SMEM_BYTES = OFF_BAR + 64;
+constexpr int GS_BYTES = 2 * 128 * GS_LD * 4; // [2][128][33] floats
+template <int NS>
+struct Lay {                                  // NS operand terms per value: A [NS], B [x: NS, t: NS]
+  static constexpr int OFF_A = 0;
+  static constexpr int OFF_B = OFF_A + NS * A_TILE;
+  // the gS staging tile is only alive between the MMAs of a tile and the end of that tile: when the B operands
+  // are large enough (NS = 3: 55 KB) it lives on top of them
+  static constexpr bool GS_ON_B = (2 * NS * B_TILE >= GS_BYTES);
+  static constexpr int OFF_RAW = OFF_B + 2 * NS * B_TILE;
+  static constexpr int OFF_GS = GS_ON_B ? OFF_B : OFF_RAW + NRAW * RAW_TILE;
+  static constexpr int OFF_RED = OFF_RAW + NRAW * RAW_TILE + (GS_ON_B ? 0 : GS_BYTES);   // [NW][32] float4
+  static constexpr int OFF_CS = OFF_RED + NW * KB * 16;      // column stats: 3 x [32] float4
+  static constexpr int OFF_BAR = OFF_CS + 3 * KB * 16;
+  static constexpr int SMEM_BYTES = OFF_BAR + 64;
+  static constexpr int ACC_PER_SRC = (NS > 1) ? 2 : 1;       // main + cross accumulator
+  static constexpr int TMEM_COLS = (NS > 1) ? 128 : 64;
+};
+static_assert(Lay<3>::SMEM_BYTES <= 232448, "gram_tc_bwd: shared memory");
 
 __device__ __forceinline__ void cp_async16_zfill(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
@@ -52,24 +72,18 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& h, __nv_bfloat16& l) {
-  h = __float2bfloat16_rn(v);
-  l = __float2bfloat16_rn(v - __bfloat162float(h));
-}
-__device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
-  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
-}
-
-template <bool SPLIT>
+template <int NS>
 __global__ void __launch_bounds__(NT, 1)
 gram_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gy, const float* __restrict__ Wsym, int Bp,
                    const float* __restrict__ gloss, int B, int64_t F, float ar, float eps, int64_t ntiles,
                    float* __restrict__ gx) {
+  using LY = Lay<NS>;
+  constexpr int OFF_A = LY::OFF_A, OFF_B = LY::OFF_B, OFF_RAW = LY::OFF_RAW;
   extern __shared__ __align__(128) uint8_t smem[];
-  float* GS = reinterpret_cast<float*>(smem + OFF_GS);
-  float4* red = reinterpret_cast<float4*>(smem + OFF_RED);
-  float4* cs = reinterpret_cast<float4*>(smem + OFF_CS);      // [0..31] x: (mean, rinv, sd, -)  [32..63] t  [64..95] second pass
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  float* GS = reinterpret_cast<float*>(smem + LY::OFF_GS);
+  float4* red = reinterpret_cast<float4*>(smem + LY::OFF_RED);
+  float4* cs = reinterpret_cast<float4*>(smem + LY::OFF_CS);      // [0..31] x: (mean, rinv, sd, -)  [32..63] t  [64..95] second pass
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + LY::OFF_BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -83,17 +97,11 @@ gram_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gy, co
       float v[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) v[k] = (8 * ch + k < B) ? __ldg(src + k) : 0.f;
-      __nv_bfloat16 h[8], l[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) split_bf16(v[k], h[k], l[k]);
-      uint8_t* dst = smem + OFF_A + (i >> 3) * SBO + (i & 7) * 16 + ch * LBO;
-      *reinterpret_cast<uint4*>(dst) = make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
-      if (SPLIT)
-        *reinterpret_cast<uint4*>(dst + A_TILE) = make_uint4(pack2(l[0], l[1]), pack2(l[2], l[3]), pack2(l[4], l[5]), pack2(l[6], l[7]));
+      tcsmall::store_chunk_n<NS>(smem + OFF_A + (i >> 3) * SBO_A + (i & 7) * 16 + ch * LBO_A, A_TILE, v);
     }
   }
   if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
-  if (warp == 0) tmem_alloc(tmem_slot, 64);
+  if (warp == 0) tmem_alloc(tmem_slot, LY::TMEM_COLS);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -172,16 +180,9 @@ gram_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gy, co
         cxs[k] = v ? (xv[k] - cx4.x) * cx4.y : 0.f;
         cts[k] = v ? (tv[k] - ct4.x) * ct4.y : 0.f;
       }
-      __nv_bfloat16 h[RPT], l[RPT];
       uint8_t* dst = smem + OFF_B + (lane >> 3) * SBO + (lane & 7) * 16 + warp * LBO;
-#pragma unroll
-      for (int k = 0; k < RPT; ++k) split_bf16(cxs[k], h[k], l[k]);
-      *reinterpret_cast<uint4*>(dst) = make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
-      if (SPLIT) *reinterpret_cast<uint4*>(dst + B_TILE) = make_uint4(pack2(l[0], l[1]), pack2(l[2], l[3]), pack2(l[4], l[5]), pack2(l[6], l[7]));
-#pragma unroll
-      for (int k = 0; k < RPT; ++k) split_bf16(cts[k], h[k], l[k]);
-      *reinterpret_cast<uint4*>(dst + 2 * B_TILE) = make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
-      if (SPLIT) *reinterpret_cast<uint4*>(dst + 3 * B_TILE) = make_uint4(pack2(l[0], l[1]), pack2(l[2], l[3]), pack2(l[4], l[5]), pack2(l[6], l[7]));
+      tcsmall::store_chunk_n<NS>(dst, B_TILE, cxs);                       // x terms: tiles 0 .. NS-1
+      tcsmall::store_chunk_n<NS>(dst + NS * B_TILE, B_TILE, cts);         // t terms: tiles NS .. 2 NS-1
     }
     fence_proxy_async();
     __syncthreads();
@@ -191,16 +192,23 @@ gram_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gy, co
       const uint32_t sa = smem_u32(smem + OFF_A), sb = smem_u32(smem + OFF_B);
 #pragma unroll
       for (int ks = 0; ks < 8; ++ks) {
-        const uint32_t koff = ks * 2 * LBO;
-        const uint64_t ah = make_desc(sa + koff, LBO, SBO), al = make_desc(sa + A_TILE + koff, LBO, SBO);
+        const uint32_t koa = ks * 2 * LBO_A, kob = ks * 2 * LBO;
+        const uint32_t acc = ks > 0 ? 1u : 0u;
+        const uint64_t ah = make_desc(sa + koa, LBO_A, SBO_A);
 #pragma unroll
         for (int src = 0; src < 2; ++src) {
-          const uint64_t bh = make_desc(sb + (2 * src) * B_TILE + koff, LBO, SBO);
-          const uint64_t bl = make_desc(sb + (2 * src + 1) * B_TILE + koff, LBO, SBO);
-          umma<false>(tmem_base + 32 * src, ah, bh, IDESC, ks > 0 ? 1u : 0u);
-          if (SPLIT) {
-            umma<false>(tmem_base + 32 * src, ah, bl, IDESC, 1u);
-            umma<false>(tmem_base + 32 * src, al, bh, IDESC, 1u);
+          const uint32_t d_main = tmem_base + 32 * LY::ACC_PER_SRC * src, d_cross = d_main + 32;
+          const uint64_t bh = make_desc(sb + (NS * src) * B_TILE + kob, LBO, SBO);
+          umma<false>(d_main, ah, bh, IDESC, acc);                          // H H
+          if (NS == 3) {
+            const uint64_t am = make_desc(sa + A_TILE + koa, LBO_A, SBO_A), al = make_desc(sa + 2 * A_TILE + koa, LBO_A, SBO_A);
+            const uint64_t bm = make_desc(sb + (NS * src + 1) * B_TILE + kob, LBO, SBO);
+            const uint64_t bl = make_desc(sb + (NS * src + 2) * B_TILE + kob, LBO, SBO);
+            umma<false>(d_cross, ah, bm, IDESC, acc);                       // the five products <= 2^-8 of H H
+            umma<false>(d_cross, am, bh, IDESC, 1u);
+            umma<false>(d_cross, ah, bl, IDESC, 1u);
+            umma<false>(d_cross, al, bh, IDESC, 1u);
+            umma<false>(d_cross, am, bm, IDESC, 1u);
           }
         }
       }
@@ -213,10 +221,17 @@ gram_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gy, co
 #pragma unroll 1
       for (int src = 0; src < 2; ++src) {
         uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + 32 * src, v);
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + 32 * LY::ACC_PER_SRC * src, v);
         float* g = GS + (src * 128 + warp * 32 + lane) * GS_LD;
+        if (NS > 1) {
+          uint32_t w[32];
+          tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + 32 * LY::ACC_PER_SRC * src + 32, w);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) g[j] = __uint_as_float(v[j]);
+          for (int j = 0; j < 32; ++j) g[j] = __uint_as_float(v[j]) + __uint_as_float(w[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) g[j] = __uint_as_float(v[j]);
+        }
       }
       tc_fence_before();
     }
@@ -262,7 +277,7 @@ gram_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gy, co
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 64);
+  if (warp == 0) tmem_dealloc(tmem_base, LY::TMEM_COLS);
 }
 
 }  // namespace tcb
@@ -283,13 +298,13 @@ int gram_tc_backward(const float* x, const float* gy, const float* Wsym, int Bp,
   if (grid < 1) grid = 1;
   cudaError_t e;
   if (split) {
-    e = cudaFuncSetAttribute(gram_tc_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    e = cudaFuncSetAttribute(gram_tc_bwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<3>::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
-    gram_tc_bwd_kernel<true><<<(unsigned)grid, NT, SMEM_BYTES, s>>>(x, gy, Wsym, Bp, gloss, B, F, ar, eps, ntiles, gx);
+    gram_tc_bwd_kernel<3><<<(unsigned)grid, NT, Lay<3>::SMEM_BYTES, s>>>(x, gy, Wsym, Bp, gloss, B, F, ar, eps, ntiles, gx);
   } else {
-    e = cudaFuncSetAttribute(gram_tc_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    e = cudaFuncSetAttribute(gram_tc_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<1>::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
-    gram_tc_bwd_kernel<false><<<(unsigned)grid, NT, SMEM_BYTES, s>>>(x, gy, Wsym, Bp, gloss, B, F, ar, eps, ntiles, gx);
+    gram_tc_bwd_kernel<1><<<(unsigned)grid, NT, Lay<1>::SMEM_BYTES, s>>>(x, gy, Wsym, Bp, gloss, B, F, ar, eps, ntiles, gx);
   }
   ALIGNQ_LAUNCH_CHECK();
   return ALIGNQ_OK;

@@ -8,11 +8,13 @@
 //     __syncthreads per tile.  Global loads/stores are coalesced across the warp (consecutive columns).
 //   * the per-tile product is flipped so the feature columns are the MMA's M dimension:
 //         D[n, i] = sum_j XsT[n, j] * Wsym[i, j]        M = 128 columns, N = 32 (i), K = 32 (batch j)
-//     A = the standardised tile transposed (thread n writes row n: 4 x 16-byte core-matrix rows, bf16 H + L),
+//     A = the standardised tile transposed (thread n writes row n: 4 x 16-byte core-matrix rows),
 //     B = Wsym (symmetric; split once per CTA).  The accumulator row n lands in TMEM lane n, so
 //     tcgen05.ld hands thread n exactly its own column of W Xs: no shared-memory transpose.
-//   * 128 threads per CTA, three CTAs per SM (37 KB smem, 64 TMEM columns each) overlap each other's
-//     load -> convert -> MMA -> combine phases.
+//     Operand precision as in gram_tc_bwd.cu: NS = 3 bf16 terms per value (24 mantissa bits, six MMAs per
+//     k-step, the five small products in their own accumulator) for gram_mode tf32x3, NS = 1 for bf16.
+//   * 128 threads per CTA, several CTAs per SM (NS = 3: 87 KB smem, 128 TMEM columns -> two per SM; NS = 1:
+//     three) overlap each other's load -> convert -> MMA -> combine phases.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -33,20 +35,27 @@ constexpr int LBO = 128;                // K-adjacent core matrices, dense
 constexpr int SBO = 4 * LBO;            // 8-row groups: K = 32 bf16 = 4 core matrices
 constexpr int A_TILE = 16 * SBO;        // XsT operand: 128 rows x 64 B            8 KB
 constexpr int W_TILE = 4 * SBO;         // Wsym operand: 32 rows x 64 B             2 KB
-constexpr int OFF_W = 0;                // [H, L]
-constexpr int OFF_A = OFF_W + 2 * W_TILE;          // [xH, xL, tH, tL]
-constexpr int OFF_XS = OFF_A + 4 * A_TILE;         // x of the NEXT tile, [32][128] floats (own column per thread)
-constexpr int OFF_GY = OFF_XS + RB * NT * 4;       // gy of THIS tile, same shape
-constexpr int OFF_BAR = OFF_GY + RB * NT * 4;
-constexpr int SMEM_BYTES = OFF_BAR + 64;
-constexpr int CTAS_PER_SM = 3;
+template <int NS>
+struct Lay {
+  static constexpr int OFF_W = 0;                          // [NS] terms
+  static constexpr int OFF_A = OFF_W + NS * W_TILE;        // [x: NS terms, t: NS terms]
+  static constexpr int OFF_XS = OFF_A + 2 * NS * A_TILE;   // x of the NEXT tile, [32][128] floats (own column per thread)
+  static constexpr int OFF_GY = OFF_XS + RB * NT * 4;      // gy of THIS tile, same shape
+  static constexpr int OFF_BAR = OFF_GY + RB * NT * 4;
+  static constexpr int SMEM_BYTES = OFF_BAR + 64;
+  static constexpr int CTAS_PER_SM = (NS > 1) ? 2 : 3;
+  static constexpr int ACC_PER_SRC = (NS > 1) ? 2 : 1;
+  static constexpr int TMEM_COLS = (NS > 1) ? 128 : 64;
+};
 
 // RBT = batch rows carried per thread (B rounded up to the next instantiated size; K entries RBT..31 stay zero)
-template <bool SPLIT, int RBT>
-__global__ void __launch_bounds__(NT, CTAS_PER_SM)
+template <int NS, int RBT>
+__global__ void __launch_bounds__(NT, Lay<NS>::CTAS_PER_SM)
 gram_tc_bwd_small_kernel(const float* __restrict__ x, const float* __restrict__ gy, const float* __restrict__ Wsym, int Bp,
                          const float* __restrict__ gloss, int B, int64_t F, float ar, float eps, int64_t ntiles,
                          float* __restrict__ gx) {
+  using LY = Lay<NS>;
+  constexpr int OFF_W = LY::OFF_W, OFF_A = LY::OFF_A, OFF_XS = LY::OFF_XS, OFF_GY = LY::OFF_GY, OFF_BAR = LY::OFF_BAR;
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
@@ -62,11 +71,11 @@ gram_tc_bwd_small_kernel(const float* __restrict__ x, const float* __restrict__ 
       float v[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) v[k] = (8 * ch + k < B) ? __ldg(src + k) : 0.f;
-      store_chunk<SPLIT>(smem + OFF_W + (i >> 3) * SBO + (i & 7) * 16 + ch * LBO, W_TILE, v);
+      store_chunk_n<NS>(smem + OFF_W + (i >> 3) * SBO + (i & 7) * 16 + ch * LBO, W_TILE, v);
     }
   }
   if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
-  if (warp == 0) tmem_alloc(tmem_slot, 64);
+  if (warp == 0) tmem_alloc(tmem_slot, LY::TMEM_COLS);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -136,8 +145,8 @@ gram_tc_bwd_small_kernel(const float* __restrict__ x, const float* __restrict__ 
         cx[k] = (8 * c + k < RBT) ? (xv[r] - mx) * rx : 0.f;
         ct[k] = (8 * c + k < RBT) ? (tv[r] - mt) * rt : 0.f;
       }
-      store_chunk<SPLIT>(arow + c * LBO, A_TILE, cx);
-      store_chunk<SPLIT>(arow + c * LBO + 2 * A_TILE, A_TILE, ct);
+      store_chunk_n<NS>(arow + c * LBO, A_TILE, cx);
+      store_chunk_n<NS>(arow + c * LBO + NS * A_TILE, A_TILE, ct);
     }
     fence_proxy_async();
     tc_fence_before();
@@ -149,15 +158,22 @@ gram_tc_bwd_small_kernel(const float* __restrict__ x, const float* __restrict__ 
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks) {
         const uint32_t koff = ks * 2 * LBO;
-        const uint64_t wh = make_desc(sw + koff, LBO, SBO), wl = make_desc(sw + W_TILE + koff, LBO, SBO);
+        const uint32_t acc = ks > 0 ? 1u : 0u;
+        const uint64_t wh = make_desc(sw + koff, LBO, SBO);
 #pragma unroll
         for (int src = 0; src < 2; ++src) {
-          const uint64_t ah = make_desc(sa + (2 * src) * A_TILE + koff, LBO, SBO);
-          const uint64_t al = make_desc(sa + (2 * src + 1) * A_TILE + koff, LBO, SBO);
-          umma<false>(tmem_base + 32 * src, ah, wh, IDESC, ks > 0 ? 1u : 0u);
-          if (SPLIT) {
-            umma<false>(tmem_base + 32 * src, ah, wl, IDESC, 1u);
-            umma<false>(tmem_base + 32 * src, al, wh, IDESC, 1u);
+          const uint32_t d_main = tmem_base + 32 * LY::ACC_PER_SRC * src, d_cross = d_main + 32;
+          const uint64_t ah = make_desc(sa + (NS * src) * A_TILE + koff, LBO, SBO);
+          umma<false>(d_main, ah, wh, IDESC, acc);                          // H H
+          if (NS == 3) {
+            const uint64_t wm = make_desc(sw + W_TILE + koff, LBO, SBO), wl = make_desc(sw + 2 * W_TILE + koff, LBO, SBO);
+            const uint64_t am = make_desc(sa + (NS * src + 1) * A_TILE + koff, LBO, SBO);
+            const uint64_t al = make_desc(sa + (NS * src + 2) * A_TILE + koff, LBO, SBO);
+            umma<false>(d_cross, ah, wm, IDESC, acc);                       // the five products <= 2^-8 of H H
+            umma<false>(d_cross, am, wh, IDESC, 1u);
+            umma<false>(d_cross, ah, wl, IDESC, 1u);
+            umma<false>(d_cross, al, wh, IDESC, 1u);
+            umma<false>(d_cross, am, wm, IDESC, 1u);
           }
         }
       }
@@ -170,6 +186,12 @@ gram_tc_bwd_small_kernel(const float* __restrict__ x, const float* __restrict__ 
     {
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16), v);
+      if (NS > 1) {
+        uint32_t w[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + 32, w);
+#pragma unroll
+        for (int r = 0; r < RBT; ++r) v[r] = __float_as_uint(__uint_as_float(v[r]) + __uint_as_float(w[r]));
+      }
       float a1 = 0.f, a2 = 0.f;
 #pragma unroll
       for (int r = 0; r < RBT; ++r) {
@@ -186,7 +208,13 @@ gram_tc_bwd_small_kernel(const float* __restrict__ x, const float* __restrict__ 
     // ---- 5. t source, straight-through factor, store ---------------------------------------------------------
     {
       uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + 32, v);
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + 32 * LY::ACC_PER_SRC, v);
+      if (NS > 1) {
+        uint32_t w[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + 32 * LY::ACC_PER_SRC + 32, w);
+#pragma unroll
+        for (int r = 0; r < RBT; ++r) v[r] = __float_as_uint(__uint_as_float(v[r]) + __uint_as_float(w[r]));
+      }
       tc_fence_before();
       float b1 = 0.f, b2 = 0.f;
 #pragma unroll
@@ -212,29 +240,29 @@ gram_tc_bwd_small_kernel(const float* __restrict__ x, const float* __restrict__ 
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 64);
+  if (warp == 0) tmem_dealloc(tmem_base, LY::TMEM_COLS);
 }
 
 }  // namespace tcsb
 
-template <bool SPLIT, int RBT>
+template <int NS, int RBT>
 static int launch_bwd_small(const float* x, const float* gy, const float* Wsym, int Bp, const float* gloss, int B, int64_t F,
                             float ar, float eps, float* gx, int64_t ntiles, int64_t grid, cudaStream_t s) {
   using namespace tcsb;
-  cudaError_t e = cudaFuncSetAttribute(gram_tc_bwd_small_kernel<SPLIT, RBT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  cudaError_t e = cudaFuncSetAttribute(gram_tc_bwd_small_kernel<NS, RBT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<NS>::SMEM_BYTES);
   if (e != cudaSuccess) return (int)e;
-  gram_tc_bwd_small_kernel<SPLIT, RBT><<<(unsigned)grid, NT, SMEM_BYTES, s>>>(x, gy, Wsym, Bp, gloss, B, F, ar, eps, ntiles, gx);
+  gram_tc_bwd_small_kernel<NS, RBT><<<(unsigned)grid, NT, Lay<NS>::SMEM_BYTES, s>>>(x, gy, Wsym, Bp, gloss, B, F, ar, eps, ntiles, gx);
   ALIGNQ_LAUNCH_CHECK();
   return ALIGNQ_OK;
 }
-template <bool SPLIT>
+template <int NS>
 static int launch_bwd_small_b(const float* x, const float* gy, const float* Wsym, int Bp, const float* gloss, int B, int64_t F,
                               float ar, float eps, float* gx, int64_t ntiles, int64_t grid, cudaStream_t s) {
-  if (B <= 8) return launch_bwd_small<SPLIT, 8>(x, gy, Wsym, Bp, gloss, B, F, ar, eps, gx, ntiles, grid, s);
-  if (B <= 16) return launch_bwd_small<SPLIT, 16>(x, gy, Wsym, Bp, gloss, B, F, ar, eps, gx, ntiles, grid, s);
-  if (B <= 24) return launch_bwd_small<SPLIT, 24>(x, gy, Wsym, Bp, gloss, B, F, ar, eps, gx, ntiles, grid, s);
-  if (B <= 28) return launch_bwd_small<SPLIT, 28>(x, gy, Wsym, Bp, gloss, B, F, ar, eps, gx, ntiles, grid, s);
-  return launch_bwd_small<SPLIT, 32>(x, gy, Wsym, Bp, gloss, B, F, ar, eps, gx, ntiles, grid, s);
+  if (B <= 8) return launch_bwd_small<NS, 8>(x, gy, Wsym, Bp, gloss, B, F, ar, eps, gx, ntiles, grid, s);
+  if (B <= 16) return launch_bwd_small<NS, 16>(x, gy, Wsym, Bp, gloss, B, F, ar, eps, gx, ntiles, grid, s);
+  if (B <= 24) return launch_bwd_small<NS, 24>(x, gy, Wsym, Bp, gloss, B, F, ar, eps, gx, ntiles, grid, s);
+  if (B <= 28) return launch_bwd_small<NS, 28>(x, gy, Wsym, Bp, gloss, B, F, ar, eps, gx, ntiles, grid, s);
+  return launch_bwd_small<NS, 32>(x, gy, Wsym, Bp, gloss, B, F, ar, eps, gx, ntiles, grid, s);
 }
 
 int gram_tc_backward_small(const float* x, const float* gy, const float* Wsym, int Bp, const float* gloss, int B,
@@ -242,11 +270,12 @@ int gram_tc_backward_small(const float* x, const float* gy, const float* Wsym, i
   using namespace tcsb;
   if (B > RB || B < 2) return ALIGNQ_ERANGE;
   const int64_t ntiles = (F + NT - 1) / NT;
+  const int per_sm = split ? Lay<3>::CTAS_PER_SM : Lay<1>::CTAS_PER_SM;
   int64_t grid = ntiles;
-  if (grid > (int64_t)ALIGNQ_NUM_SMS * CTAS_PER_SM) grid = (int64_t)ALIGNQ_NUM_SMS * CTAS_PER_SM;
+  if (grid > (int64_t)ALIGNQ_NUM_SMS * per_sm) grid = (int64_t)ALIGNQ_NUM_SMS * per_sm;
   if (grid < 1) grid = 1;
-  return split ? launch_bwd_small_b<true>(x, gy, Wsym, Bp, gloss, B, F, ar, eps, gx, ntiles, grid, s)
-               : launch_bwd_small_b<false>(x, gy, Wsym, Bp, gloss, B, F, ar, eps, gx, ntiles, grid, s);
+  return split ? launch_bwd_small_b<3>(x, gy, Wsym, Bp, gloss, B, F, ar, eps, gx, ntiles, grid, s)
+               : launch_bwd_small_b<1>(x, gy, Wsym, Bp, gloss, B, F, ar, eps, gx, ntiles, grid, s);
 }
 
 }  // namespace alignq

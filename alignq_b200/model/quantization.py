@@ -103,6 +103,12 @@ class cdf(nn.Module):
         self.variant = _variant(variant)
 
     def forward(self, tensor):
+        for name, v in (("m", self.m), ("s", self.s)):
+            if torch.is_tensor(v) and v.requires_grad and torch.is_grad_enabled():
+                # the reference's cdf differentiates through m and s (weight_quantize_fn passes mean/std of the
+                # weight, QA:70); that chain is implemented by the fused weight_quantize_fn kernels, not here
+                raise L.AlignQError(f"cdf(m, s, src): `{name}` requires grad; the stand-alone cdf treats m and s as "
+                                    "constants -- use weight_quantize_fn (gradient through mean/std) or detach them")
         m = torch.as_tensor(self.m, dtype=torch.float32, device=tensor.device).detach()
         s = torch.as_tensor(self.s, dtype=torch.float32, device=tensor.device).detach()
         return _CdfFn.apply(tensor, m, s, L.VARIANT_ID[self.variant], int(self.quant_src == "a"),
@@ -238,7 +244,8 @@ class _ActAdmmFn(torch.autograd.Function):
     """y, trans_loss, D = fused activation quantizer + corr(x) / corr(t) + ADMM loss."""
 
     @staticmethod
-    def forward(ctx, x, alterD, gamma, a_bit, act_range, eps, mu, rho, gram_mode, variant_id=1, d_out=None):
+    def forward(ctx, x, alterD, gamma, a_bit, act_range, eps, mu, rho, gram_mode, variant_id=1, d_out=None,
+                param_grads=True):
         xc = L.dev_f32_dense(x, "activation")      # per-sample feature order is irrelevant to the Gram
         Z = L.dev_f32(alterD, "alterD")
         U = L.dev_f32(gamma, "gamma")
@@ -259,7 +266,7 @@ class _ActAdmmFn(torch.autograd.Function):
                 y.data_ptr(), D.data_ptr(), loss.data_ptr(), dLdD.data_ptr(), ws.data_ptr(), ws.numel(),
                 gram_mode, L.stream_ptr()), "alignq_act_admm_fwd")
         ctx.save_for_backward(xc, dLdD, D, Z, U)
-        ctx.cfg = (a_bit, act_range, eps, mu, rho, gram_mode, variant_id)
+        ctx.cfg = (a_bit, act_range, eps, mu, rho, gram_mode, variant_id, bool(param_grads))
         ctx.mark_non_differentiable(D)
         ctx.set_materialize_grads(False)       # a backward pass that does not reach trans_loss skips the Gram backward
         return y, loss, D
@@ -267,7 +274,7 @@ class _ActAdmmFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy, gloss, _gD):
         xc, dLdD, D, Z, U = ctx.saved_tensors
-        a_bit, act_range, eps, mu, rho, gram_mode, variant_id = ctx.cfg
+        a_bit, act_range, eps, mu, rho, gram_mode, variant_id, param_grads = ctx.cfg
         B = xc.shape[0]
         Fdim = xc.numel() // B
         dim = Z.shape[0]
@@ -282,7 +289,7 @@ class _ActAdmmFn(torch.autograd.Function):
                     gx = torch.empty_like(xc)
                     L.check(lib.alignq_act_bwd(xc.data_ptr(), gyc.data_ptr(), gx.data_ptr(), xc.numel(), a_bit,
                                                act_range, variant_id, 0, L.stream_ptr()), "alignq_act_bwd")
-                return gx, None, None, None, None, None, None, None, None, None, None
+                return (gx,) + (None,) * 11
             gl = L.dev_f32(gloss.reshape(1), "grad of trans_loss")
             if ctx.needs_input_grad[0]:
                 gyc = None if gy is None else L.like_layout(gy, xc, "grad of quantized activation")
@@ -291,15 +298,15 @@ class _ActAdmmFn(torch.autograd.Function):
                 L.check(lib.alignq_act_admm_bwd(
                     xc.data_ptr(), L.ptr(gyc), dLdD.data_ptr(), gl.data_ptr(), B, Fdim, a_bit, act_range, eps,
                     gx.data_ptr(), ws.data_ptr(), ws.numel(), gram_mode, L.stream_ptr()), "alignq_act_admm_bwd")
-            want_z = ctx.needs_input_grad[1] and args.admm_param_grads
-            want_u = ctx.needs_input_grad[2] and args.admm_param_grads
+            want_z = ctx.needs_input_grad[1] and param_grads
+            want_u = ctx.needs_input_grad[2] and param_grads
             if want_z or want_u:
                 gZ = torch.empty_like(Z) if want_z else None
                 gU = torch.empty_like(U) if want_u else None
                 L.check(lib.alignq_admm_loss(D.data_ptr(), B, Z.data_ptr(), U.data_ptr(), dim, 1, mu, rho,
                                              gl.data_ptr(), 0, 0, 0, L.ptr(gZ), L.ptr(gU), L.stream_ptr()),
                         "alignq_admm_loss (parameter grads)")
-        return gx, gZ, gU, None, None, None, None, None, None, None, None
+        return (gx, gZ, gU) + (None,) * 9
 
 
 class activation_quantize_fn(nn.Module):
@@ -331,7 +338,8 @@ class activation_quantize_fn(nn.Module):
             y, loss, D = _ActAdmmFn.apply(x, self.opt.alterD, self.opt.gamma, self.a_bit, float(args.act_range),
                                           eps, float(self.opt.mu), float(self.opt.rho),
                                           L.GRAM_MODE_ID[args.gram_mode], L.VARIANT_ID[self.variant],
-                                          getattr(self.opt, "_D_slot", None))
+                                          self.opt.d_slot(x.shape[0]) if hasattr(self.opt, "d_slot") else None,
+                                          bool(getattr(self.opt, "param_grads", True)) and bool(args.admm_param_grads))
             self.opt.D = D
             return y, loss
         y = self._plain(x)
@@ -349,23 +357,54 @@ class activation_quantize_fn2(activation_quantize_fn):
 # ------------------------------------------------------------------------------------------------
 # corr(x, y)                                                          QB:134-137, QC:158-161
 # ------------------------------------------------------------------------------------------------
+class _CorrFn(torch.autograd.Function):
+    """corr(x, y) with the reference's autograd semantics: differentiable through mean and std of both
+    operands (QB:135-137).  Backward: ``alignq_corr_bwd`` (fp32 FFMA kernels)."""
+
+    @staticmethod
+    def forward(ctx, x, y, eps, gram_mode, same):
+        xc = L.dev_f32(x, "corr x")
+        yc = xc if same else L.dev_f32(y, "corr y")
+        B, Fdim = xc.shape
+        G = torch.empty(B, B, dtype=torch.float32, device=xc.device)
+        ws = _gram_ws(B, Fdim, xc.device)
+        with torch.cuda.device_of(xc):
+            L.check(L.load().alignq_corr_fwd(xc.data_ptr(), yc.data_ptr(), B, Fdim, float(eps), G.data_ptr(),
+                                             ws.data_ptr(), ws.numel(), gram_mode, L.stream_ptr()), "alignq_corr_fwd")
+        ctx.save_for_backward(xc, yc)
+        ctx.cfg = (float(eps), bool(same))
+        return G
+
+    @staticmethod
+    def backward(ctx, dG):
+        xc, yc = ctx.saved_tensors
+        eps, same = ctx.cfg
+        B, Fdim = xc.shape
+        dG = L.dev_f32(dG, "grad of corr")
+        want_x = ctx.needs_input_grad[0] or (same and ctx.needs_input_grad[1])
+        want_y = (not same) and ctx.needs_input_grad[1]
+        gx = torch.empty_like(xc) if want_x else None
+        gy = torch.empty_like(yc) if want_y else None
+        if B < 2:
+            raise L.AlignQError("corr backward needs a batch of at least 2 rows (unbiased std)")
+        ws = _gram_ws(B, Fdim, xc.device)
+        with torch.cuda.device_of(xc):
+            L.check(L.load().alignq_corr_bwd(xc.data_ptr(), yc.data_ptr(), dG.data_ptr(), B, Fdim, eps, L.ptr(gx),
+                                             L.ptr(gy), ws.data_ptr(), ws.numel(), L.stream_ptr()), "alignq_corr_bwd")
+        if same:          # one operand passed twice: autograd adds both slots, so hand the whole gradient to slot 0
+            return gx, None, None, None, None
+        return gx, gy, None, None, None
+
+
 def corr(x, y, eps=None):
-    """[B,F],[B,F] -> [B,B].  eps defaults to the variant's (0 for 'A'/'B', 1e-5 for 'C').
-    Forward only (the trainable path is the fused activation_quantize_fn)."""
+    """[B,F],[B,F] -> [B,B].  eps defaults to the variant's (0 for 'A'/'B', 1e-5 for 'C').  Differentiable with
+    respect to both operands like the reference's (QB:134-137); the training path uses the fused
+    activation_quantize_fn instead, which never materialises the standardised operands."""
     if eps is None:
         eps = 1e-5 if args.variant == "C" else 0.0
-    xc = L.dev_f32(x.detach(), "corr x")
-    yc = xc if y is x else L.dev_f32(y.detach(), "corr y")
-    if xc.dim() != 2 or xc.shape != yc.shape:
+    if x.dim() != 2 or x.shape != y.shape:
         raise L.AlignQError(f"corr expects two [B, F] matrices of equal shape, got {tuple(x.shape)}, {tuple(y.shape)}")
-    B, Fdim = xc.shape
-    G = torch.empty(B, B, dtype=torch.float32, device=xc.device)
-    ws = _gram_ws(B, Fdim, xc.device)
-    with torch.cuda.device_of(xc):
-        L.check(L.load().alignq_corr_fwd(xc.data_ptr(), yc.data_ptr(), B, Fdim, float(eps), G.data_ptr(),
-                                         ws.data_ptr(), ws.numel(), L.GRAM_MODE_ID[args.gram_mode],
-                                         L.stream_ptr()), "alignq_corr_fwd")
-    return G
+    return _CorrFn.apply(x, y, float(eps), L.GRAM_MODE_ID[args.gram_mode], y is x)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -52,6 +52,15 @@ class ADMM(Module):
         self.rho = 0.3
         self.alterD = Parameter(torch.rand(dim, dim))
         self.gamma = Parameter(torch.rand(dim, dim))
+        # d trans_loss / d(alterD, gamma) is produced by autograd in the reference but never read by ADMM_OPT
+        # (closed-form Z/U updates, optimizer.py:97-124).  An AdmmBank that owns this module's update switches
+        # it off PER MODULE (never through the process-global args) and serves D slots for any batch size.
+        self.param_grads = True
+        self._bank = None
+
+    def d_slot(self, B: int):
+        """Where the fused forward should write D for a batch of B rows (None: allocate)."""
+        return None if self._bank is None else self._bank[0].slot(self._bank[1], int(B))
 
     def forward(self, D):
         self.D = D

@@ -140,7 +140,11 @@ class ADMM_OPT(Optimizer):
         for group in self.param_groups:
             updated = None                           # (gamma tensor) paired with the last alterD visited
             for i, p in enumerate(group["params"]):
-                if p.grad is None:
+                # the reference skips parameters without .grad (optimizer.py:77-78), i.e. modules that did not take
+                # part in the forward.  Z/U whose autograd gradient is deliberately not computed (ADMM.param_grads =
+                # False: the closed-form update never reads it) count as present when the caller lists them.
+                if p.grad is None and not (getattr(p, "_alignq_closed_form", False)
+                                           and (i in alterD_idx or i in gamma_idx)):
                     continue
                 if args.bitW < 32 and i in alterD_idx:
                     j = alterD_idx.index(i)

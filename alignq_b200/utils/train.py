@@ -24,6 +24,13 @@ from .. import _lib as L
 from .sharding import allreduce_sum_
 
 
+def WeightBank_applies(model) -> bool:
+    """The bank needs at least one quantized conv / linear and ONE bit-width and variant for all of them."""
+    qs = [m.quantize_fn for m in model.modules() if hasattr(m, "quantize_fn") and hasattr(m, "weight")
+          and getattr(m.quantize_fn, "w_bit", 32) < 32]
+    return bool(qs) and len({(q.w_bit, q.variant) for q in qs}) == 1
+
+
 def quantized_convs(model):
     """Conv2d_Q / Linear_Q modules in registration order."""
     return [m for m in model.modules() if hasattr(m, "quantize_fn") and hasattr(m, "weight")]
@@ -68,13 +75,10 @@ class QATStep:
                 if p.dim() == 4:
                     p.data = p.data.contiguous(memory_format=torch.channels_last)
         self.bank = None
-        if bank_weights:                       # one multi-tensor weight-quantizer launch per step
+        if bank_weights and WeightBank_applies(model):   # one multi-tensor weight-quantizer launch per step
             from .weight_bank import WeightBank
-            try:
-                self.bank = WeightBank(model)
-                self.bank.batched_backward = True
-            except Exception:
-                self.bank = None
+            self.bank = WeightBank(model)      # a failure here is an error, not a silent 2x slower step
+            self.bank.batched_backward = True
         named = list(model.named_parameters())
         self.params = [p for n, p in named if "alterD" not in n and "gamma" not in n]       # main.py:87
         self.admm_params = [p for n, p in named if "alterD" in n or "gamma" in n]
@@ -83,11 +87,8 @@ class QATStep:
         self.admm_bank = None
         if self.admm_params and fast_admm:     # batched Z/U update; d loss / d(Z, U) is never read by ADMM_OPT
             from .admm_bank import AdmmBank
-            try:
-                self.admm_bank = AdmmBank(model, args.train_batch_size)
-                args.admm_param_grads = False
-            except Exception:
-                self.admm_bank = None
+            # per-module switch (ADMM.param_grads), never the process-global args; serves any batch size <= dim
+            self.admm_bank = AdmmBank(model, args.train_batch_size)
         self.lam = args.lam if lam is None else lam
         self.lam2 = args.lam2 if lam2 is None else lam2
         self.offset = trans_loss_offset
@@ -110,6 +111,8 @@ class QATStep:
             p.grad = None                                          # over its gradient buffers without an add
         if self.bank is not None:
             self.bank.quantize_all()
+        if self.admm_bank is not None:
+            self.admm_bank.begin_iteration()
         if self.forward_loss is not None:
             ce, trans_loss = self.forward_loss(self.model, x, t)
         else:
@@ -138,9 +141,12 @@ class QATStep:
             scale = 1.0 / self.world                               # the mean is folded into the SGD kernel
         idx, w_cdf, w_pdf = collect_sgd_args(self.model, self.params)
         self.opt.step(idx, w_cdf, w_pdf, self.lam, self.lam2, grad_scale=scale)
-        if self.admm_bank is not None and self.admm_bank.ready():
-            self.admm_bank.update()                                # all modules, one launch
+        nb = self.admm_bank.ready() if self.admm_bank is not None else 0
+        if nb:
+            self.admm_bank.update(nb)                              # all modules, one launch (any batch size <= dim)
         elif self.opt_admm is not None:
+            # some module did not run, or ran with a different batch: per-module updates of exactly the modules
+            # that produced a D in THIS forward (ADMM_OPT treats bank-owned Z/U as present without .grad)
             self.opt_admm.step(*collect_admm_args(self.model, self.admm_params))
         if self.bank is not None:
             self.bank.fresh = False                                # weights changed: slices are stale

@@ -103,6 +103,13 @@ int alignq_wq_backward(const float* flat, const float* g_wq, const float* const*
 size_t alignq_gram_ws_bytes(int B, int64_t F);
 int alignq_corr_fwd(const float* x, const float* y, int B, int64_t F, float eps, float* G, void* ws,
                     size_t ws_bytes, int gram_mode, alignq_stream_t stream);
+/* Autograd backward of corr(x, y) for an upstream dG [B, B] (the reference's corr is differentiable through
+ * mean and std, QB:135-137): gXs = dG Ys / F, gYs = dG^T Xs / F, then the standardise backward of each operand
+ * (the std term is masked at std == 0 as torch's std_backward does).  gx / gy are nullable;
+ * when y aliases x there is one operand and its gradient (both terms) goes to gx.  fp32 FFMA kernels.
+ * ws: at least 2 * roundup(B,4)^2 floats (alignq_gram_ws_bytes(B, F) always suffices).              */
+int alignq_corr_bwd(const float* x, const float* y, const float* dG, int B, int64_t F, float eps, float* gx,
+                    float* gy, void* ws, size_t ws_bytes, alignq_stream_t stream);
 
 /* ---- fused activation quantizer + ADMM correlation term --------------------------------------
  * activation_quantize_fn.forward with method=='ours' (QB:102-132) / activation_quantize_fn2

@@ -46,3 +46,18 @@ def test_admm_bank_stacks_dual_variables():
     assert m.admm0.alterD.data_ptr() == bank.Z[0].data_ptr()
     assert m.layers[0].act_q0.opt.alterD.data_ptr() == m.layers[0].admm0.alterD.data_ptr()   # shared module, shared view
     assert not bank.ready()                                     # no forward has written a D yet
+    # the closed-form update is switched on PER MODULE: the process-global flag is untouched
+    assert aq.args.admm_param_grads is True and all(mod.param_grads is False for mod in bank.mods)
+    assert m.admm0.alterD._alignq_closed_form and m.admm0.gamma._alignq_closed_form
+    # ragged last batch: D slots exist for any B <= dim, one [L, B, B] buffer per batch size
+    assert m.admm0.d_slot(6).data_ptr() == bank.D[0].data_ptr()
+    s4 = m.admm0.d_slot(4)
+    assert s4.shape == (4, 4) and m.layers[0].admm0.d_slot(4).data_ptr() != s4.data_ptr()
+    try:
+        m.admm0.d_slot(7)
+        raise AssertionError("batch above dim must raise")
+    except aq.AlignQError:
+        pass
+    bank.release()
+    assert all(mod.param_grads is True and mod._bank is None for mod in bank.mods)
+    assert not hasattr(m.admm0.alterD, "_alignq_closed_form")

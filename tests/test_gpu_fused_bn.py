@@ -1,7 +1,9 @@
 """GPU: fused BatchNorm2d -> activation quantizer -> (ReLU) against the un-fused
 reference pipeline: torch BatchNorm2d -> oracle activation quantizer -> F.relu, forward, backward,
-running statistics, eval mode.  The BN output differs from cuDNN's by a few ulp (different summation
-order), so a code that sits on a rounding tie may flip: bar = +-1 code on <= 1e-4 of the elements."""
+running statistics, eval mode.  The BN output differs from cuDNN's by an ulp (different summation order), so a
+code that sits on a rounding tie may flip: bar = north_star's +-1 code on <= 1e-5 of the elements (at least 2
+elements: one tie in a 100k-element tensor is already 1e-5), measured and printed per shape, beside the same count
+for cuDNN's own fp32 BN against an fp64 BN (the reference's own tie floor).  Gradients: 1e-5 relative."""
 import copy
 
 import pytest
@@ -19,6 +21,18 @@ DEV = "cuda"
 
 def rel(a, b):
     return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+
+def tie_budget(n):
+    return max(2, int(1e-5 * n))
+
+
+def close5(a, b, what):
+    """1e-5 relative: |a - b| <= 1e-5 |b| + 1e-6 max|b|"""
+    a, b = a.double(), b.double()
+    d = (a - b).abs()
+    tol = 1e-5 * b.abs() + 1e-6 * float(b.abs().max())
+    assert bool((d <= tol).all()), f"{what}: worst |d|/tol {float((d / tol).max()):.2f}"
 
 
 @pytest.mark.parametrize("variant", ["A", "B"])
@@ -45,14 +59,30 @@ def test_fused_bn_act_matches_unfused_pipeline(variant, shape, relu):
     yr = O.activation_quantize(z, 8, "second", variant, 2.0)
     yr = F.relu(yr) if relu else yr
     (yr * gy).sum().backward()
+    bn64 = copy.deepcopy(bn_ref).double()
+    with torch.no_grad():                                          # bn_ref has stepped its running stats: irrelevant in train mode
+        y64 = O.activation_quantize(bn64(x0.double()), 8, "second", variant, 2.0)
+        y64 = F.relu(y64) if relu else y64
     n = 255
     step = (4.0 / n) if variant == "A" else (1.0 / n)
     d = (y - yr).abs()
+    bad = int((d > 1e-6).sum())
+    bad64 = int(((y.double() - y64).abs() > 1e-6).sum())
+    floor64 = int(((yr.double() - y64).abs() > 1e-6).sum())
+    print(f"bn_act {variant} {shape}: {bad}/{y.numel()} codes differ from cuDNN-BN + oracle ({bad / y.numel():.1e}); vs fp64 BN: "
+          f"fused {bad64}, cuDNN fp32 {floor64}")
     assert float(d.max()) <= step * 1.001
-    assert int((d > 1e-6).sum()) <= max(1, int(1e-4 * y.numel())), f"{int((d > 1e-6).sum())} codes differ"
+    assert bad <= tie_budget(y.numel()), f"{bad} codes differ"
+    assert bad64 <= max(tie_budget(y.numel()), 2 * floor64)
     assert y.is_contiguous(memory_format=torch.channels_last)
-    assert rel(x.grad, xr.grad) <= 2e-3, "gx"                      # a flipped code moves the ReLU mask of that element
-    assert rel(bn.weight.grad, bn_ref.weight.grad) <= 2e-3 and rel(bn.bias.grad, bn_ref.bias.grad) <= 2e-3
+    same = d <= 1e-6                                               # a flipped code at 0 moves the ReLU mask of that element
+    close5(x.grad * same, xr.grad * same, "gx")
+    assert rel(x.grad, xr.grad) <= 1e-5 + 4.0 * bad / max(1.0, float(same.numel())) ** 0.5, "gx (all elements)"
+    if bad == 0:
+        close5(bn.weight.grad, bn_ref.weight.grad, "ggamma")
+        close5(bn.bias.grad, bn_ref.bias.grad, "gbeta")
+    else:                                                          # a flipped ReLU mask moves one addend of the sums
+        assert rel(bn.weight.grad, bn_ref.weight.grad) <= 1e-4 and rel(bn.bias.grad, bn_ref.bias.grad) <= 1e-4
     assert torch.allclose(bn.running_mean, bn_ref.running_mean, rtol=1e-5, atol=1e-6)
     assert torch.allclose(bn.running_var, bn_ref.running_var, rtol=1e-5, atol=1e-6)
     assert int(bn.num_batches_tracked) == 1
@@ -65,8 +95,10 @@ def test_fused_bn_act_matches_unfused_pipeline(variant, shape, relu):
     yr2 = O.activation_quantize(bn_ref(xr2), 8, "second", variant, 2.0)
     yr2 = F.relu(yr2) if relu else yr2
     (yr2 * gy).sum().backward()
-    assert int(((y2 - yr2).abs() > 1e-6).sum()) <= max(1, int(1e-4 * y.numel()))
-    assert rel(x2.grad, xr2.grad) <= 2e-3
+    bad2 = int(((y2 - yr2).abs() > 1e-6).sum())
+    assert bad2 <= tie_budget(y.numel())
+    same2 = (y2 - yr2).abs() <= 1e-6
+    close5(x2.grad * same2, xr2.grad * same2, "gx (eval mode)")
 
 
 def test_fused_path_is_skipped_when_it_does_not_apply():
@@ -125,6 +157,8 @@ def test_fused_bn_act_with_residual(relu):
     yr = F.relu(yr) if relu else yr
     (yr * gy).sum().backward()
     d = (y - yr).abs()
-    assert float(d.max()) <= 4.0 / 255 * 1.001 and int((d > 1e-6).sum()) <= max(1, int(1e-4 * y.numel()))
-    assert rel(x.grad, xr.grad) <= 2e-3 and rel(r.grad, rr.grad) <= 2e-3
-    assert rel(bn.weight.grad, bn_ref.weight.grad) <= 2e-3
+    assert float(d.max()) <= 4.0 / 255 * 1.001 and int((d > 1e-6).sum()) <= tie_budget(y.numel())
+    same = d <= 1e-6
+    close5(x.grad * same, xr.grad * same, "gx")
+    close5(r.grad * same, rr.grad * same, "g residual")
+    assert rel(bn.weight.grad, bn_ref.weight.grad) <= 1e-4

@@ -42,6 +42,23 @@ def rel_close(a, b, rtol=1e-5, atol_frac=1e-6, what=""):
     assert bool((err[mask] <= tol[mask]).all()), f"{what}: max rel err {float((err[mask] / (b[mask].abs() + 1e-30)).max()):.3e}, max abs {float(err[mask].max()):.3e}"
 
 
+def grad_close(mine, ref64, orc32, what="", rtol=1e-5, atol_frac=1e-6):
+    """Gradient bar: north_star's 1e-5 relative against the oracle's fp64 autograd,
+        |mine - ref64| <= 1e-5 |ref64| + max(1e-6 max|ref64|, 2 * floor),
+    where floor = max|oracle_fp32 - ref64| is the reference's OWN fp32 autograd noise on the same inputs (only
+    where the reference itself is noisier than 1e-6 of the gradient's magnitude does the floor widen the bar).
+    Prints both so the log carries the measured numbers."""
+    ref64 = ref64.double()
+    mx = float(ref64.abs().max())
+    floor = float((orc32.double() - ref64).abs().max())
+    d = (mine.double() - ref64).abs()
+    tol = rtol * ref64.abs() + max(atol_frac * mx, 2.0 * floor)
+    print(f"{what}: max|d|/max|ref| = {float(d.max()) / mx:.2e} (reference fp32 floor {floor / mx:.2e}), "
+          f"rel-norm {float(d.norm() / ref64.norm()):.2e}")
+    assert bool(torch.isfinite(mine).all()), f"{what}: non-finite gradient"
+    assert bool((d <= tol).all()), f"{what}: worst |d|/tol = {float((d / tol).max()):.2f}"
+
+
 def act_codes_via_abi(x, k, variant, ar=2.0, return_cdf=0):
     lib = L.load()
     y = torch.empty_like(x)
@@ -183,6 +200,8 @@ def test_weight_quantizer_vs_oracle(variant, k):
         wo = w.clone().requires_grad_(True)
         oq, oc, op = O.weight_quantize(wo, k, variant)
         (oq * gup).sum().backward()
+        w64 = w.double().clone().requires_grad_(True)
+        (O.weight_quantize(w64, k, variant)[0] * gup.double()).sum().backward()
         n = 2 ** k - 1
         mine_codes = torch.round(((wq + 1) / 2 if variant == "A" else wq) * n)
         ref_codes = torch.round(((oq.detach() + 1) / 2 if variant == "A" else oq.detach()) * n)
@@ -192,7 +211,7 @@ def test_weight_quantizer_vs_oracle(variant, k):
         total += w.numel()
         rel_close(mod.weight_cdf, oc.detach(), rtol=1e-5, atol_frac=2e-6, what=f"weight_cdf {shape}")
         rel_close(mod.weight_pdf, op.detach(), rtol=2e-5, atol_frac=2e-6, what=f"weight_pdf {shape}")
-        rel_close(wr.grad, wo.grad, rtol=1e-4, atol_frac=2e-5, what=f"gw {shape}")
+        grad_close(wr.grad, w64.grad, wo.grad, what=f"gw {variant} k={k} {shape}")
         assert abs(float(wr.grad.double().sum())) <= 1e-3 * float(wr.grad.double().abs().sum()) + 1e-6   # sum gw = 0
     # stats differ from torch's fp32 mean/std by <= 1 ulp, which can flip a code that sits on a tie
     assert bad <= max(2, int(2e-5 * total)), f"{bad}/{total} weight codes differ"
@@ -287,7 +306,8 @@ def test_weight_golden_fixtures(golden, variant):
         assert float(d.max()) <= step * 1.0001 and int((d > 1e-6).sum()) <= 1
         rel_close(mod.weight_cdf.cpu(), t(g[f"w_cdf_k{k}"]), rtol=1e-5, atol_frac=2e-6)
         rel_close(mod.weight_pdf.cpu(), t(g[f"w_pdf_k{k}"]), rtol=2e-5, atol_frac=2e-6)
-        rel_close(wr.grad.cpu(), t(g[f"w_g_k{k}"]), rtol=1e-4, atol_frac=2e-5, what=f"gw k={k}")
+        # the golden is the reference's fp32 CPU autograd (own noise 2e-7 of max|gw|): 1e-5 relative
+        rel_close(wr.grad.cpu(), t(g[f"w_g_k{k}"]), rtol=1e-5, atol_frac=1e-6, what=f"gw k={k}")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -330,7 +350,7 @@ def test_fused_act_admm_golden_fixtures(golden, variant):
             rel_close(y.detach().cpu(), t(g[f"fused_y_{tag}"]), rtol=2e-7, atol_frac=2e-7, what="fused y")
             rel_close(admm.D.cpu(), t(g[f"fused_D_{tag}"]), rtol=1e-5, atol_frac=1e-5, what="D")
             rel_close(loss.detach().cpu(), t(g[f"fused_loss_{tag}"]), rtol=1e-5, what="trans_loss")
-            rel_close(x.grad.cpu(), t(g[f"fused_gx_{tag}"]), rtol=1e-4, atol_frac=1e-5, what="fused gx")
+            rel_close(x.grad.cpu(), t(g[f"fused_gx_{tag}"]), rtol=1e-5, atol_frac=1e-6, what="fused gx")
 
 
 @pytest.mark.parametrize("variant,B,shape", [("B", 128, (16, 16, 16)), ("B", 128, (64, 8, 8)), ("C", 28, (64, 14, 14)),
@@ -359,9 +379,14 @@ def test_fused_act_admm_vs_gpu_eager_oracle(variant, B, shape):
     gmax = float(O.corr(xf, xf, eps).abs().max())
     assert float((admm.D - Do.detach()).abs().max()) <= 1e-5 * gmax, "D"
     rel_close(loss.detach(), lo.detach(), rtol=1e-5, what="trans_loss")
-    rel_close(x.grad, xo.grad, rtol=1e-4, atol_frac=1e-5, what="gx")
-    rel_close(admm.alterD.grad, Zo.grad, rtol=1e-4, atol_frac=1e-5, what="d loss / d alterD")
-    rel_close(admm.gamma.grad, Uo.grad, rtol=1e-4, atol_frac=1e-5, what="d loss / d gamma")
+    x64 = x0.double().clone().requires_grad_(True)
+    Z64 = admm.alterD.detach().double().clone().requires_grad_(True)
+    U64 = admm.gamma.detach().double().clone().requires_grad_(True)
+    y64, l64, _ = O.activation_quantize_admm(x64, 8, Z64, U64, "second", variant, 2.0)
+    ((y64 * gy.double()).sum() + l64).backward()
+    grad_close(x.grad, x64.grad, xo.grad, what="gx")
+    grad_close(admm.alterD.grad, Z64.grad, Zo.grad, what="d loss / d alterD")
+    grad_close(admm.gamma.grad, U64.grad, Uo.grad, what="d loss / d gamma")
 
 
 def test_fused_backward_with_constant_columns_matches_autograd():
@@ -382,7 +407,10 @@ def test_fused_backward_with_constant_columns_matches_autograd():
     yo, lo, _ = O.activation_quantize_admm(xo, 8, admm.alterD.detach(), admm.gamma.detach(), "second", "C", 2.0)
     ((yo * gy).sum() + lo).backward()
     assert bool(torch.isfinite(xo.grad).all()) and bool(torch.isfinite(x.grad).all())
-    rel_close(x.grad, xo.grad, rtol=1e-4, atol_frac=1e-5, what="gx with constant columns")
+    x64 = x0.double().clone().requires_grad_(True)
+    y64, l64, _ = O.activation_quantize_admm(x64, 8, admm.alterD.detach().double(), admm.gamma.detach().double(), "second", "C", 2.0)
+    ((y64 * gy.double()).sum() + l64).backward()
+    grad_close(x.grad, x64.grad, xo.grad, what="gx with constant columns")
 
 
 @pytest.mark.parametrize("variant", ["B", "C"])
@@ -523,14 +551,18 @@ def test_tc_fused_forward_vs_fp32_mode_and_oracle(mode, variant, B, shape):
     assert dl <= (1e-5 if mode == "tf32x3" else 2e-2)
     _, lo, Do = O.activation_quantize_admm(x0, 8, admm.alterD.detach(), admm.gamma.detach(), "second", variant, 2.0)
     assert float((res[mode][2] - Do).abs().max()) / gmax <= 2 * TC_TOL[mode]
-    # backward: tcgen05 products with bf16 H+L operands (16 mantissa bits) in tf32x3 mode, bf16 in bf16 mode,
-    # against the fp32 FFMA backward; also against the oracle's autograd (tf32x3: the 1e-4 bar of the fp32 path)
+    # backward: tcgen05 products with three bf16 terms per operand (24 mantissa bits, six MMAs) in tf32x3 mode, one
+    # bf16 term in bf16 mode.  tf32x3 is held to the same 1e-5 bar as the fp32 FFMA path, against fp64 autograd.
     if mode == "tf32x3":
-        rel_close(res[mode][3], res["fp32"][3], rtol=1e-4, atol_frac=2e-5, what="gx tcgen05 backward vs fp32 backward")
         xo = x0.clone().requires_grad_(True)
         yo, lo2, _ = O.activation_quantize_admm(xo, 8, admm.alterD.detach(), admm.gamma.detach(), "second", variant, 2.0)
         ((yo * gy).sum() + lo2).backward()
-        rel_close(res[mode][3], xo.grad, rtol=1e-4, atol_frac=2e-5, what="gx tcgen05 backward vs oracle autograd")
+        x64 = x0.double().clone().requires_grad_(True)
+        y64, l64, _ = O.activation_quantize_admm(x64, 8, admm.alterD.detach().double(), admm.gamma.detach().double(),
+                                                 "second", variant, 2.0)
+        ((y64 * gy.double()).sum() + l64).backward()
+        grad_close(res[mode][3], x64.grad, xo.grad, what="gx tcgen05 backward vs fp64 autograd")
+        grad_close(res["fp32"][3], x64.grad, xo.grad, what="gx fp32 FFMA backward vs fp64 autograd")
     else:
         e = float((res[mode][3] - res["fp32"][3]).norm() / res["fp32"][3].norm())
         assert e <= 1e-2, f"gx bf16 backward rel-norm err {e:.2e}"
@@ -584,7 +616,7 @@ def test_channels_last_activations_need_no_layout_copy():
     assert float((D1 - D2).abs().max()) <= 1e-5
     ((y1 * gy).sum() + l1).backward()
     ((y2 * gy).sum() + l2).backward()
-    rel_close(xc2.grad, xn2.grad, rtol=1e-4, atol_frac=1e-5, what="gx under feature permutation")
+    rel_close(xc2.grad, xn2.grad, rtol=1e-5, atol_frac=1e-6, what="gx under feature permutation")
 
 
 @pytest.mark.parametrize("B,F", [(256, 4096), (256, 65536), (128, 8192), (100, 8200), (17, 64), (256, 72)])
@@ -609,11 +641,16 @@ def test_gram_bf16_tma_tcgen05_vs_fp64(B, F):
     assert lib.alignq_gram_bf16(x.data_ptr(), B, F - 1, 0, G.data_ptr(), ws.data_ptr(), ws.numel(), L.stream_ptr()) == -2   # F % 8
 
 
-@pytest.mark.parametrize("mode,tol", [("fp32", 2e-4), ("tf32x3", 5e-4), ("bf16", 3e-2)])
-@pytest.mark.parametrize("variant,B,shape", [("B", 128, (16, 16, 16)), ("C", 28, (32, 14, 14)), ("B", 100, (3, 11, 12))])
+@pytest.mark.parametrize("mode,tol", [("fp32", 1e-5), ("tf32x3", 1e-5), ("bf16", 6e-2)])
+@pytest.mark.parametrize("variant,B,shape", [("B", 128, (16, 16, 16)), ("C", 28, (32, 14, 14)), ("B", 100, (3, 11, 12)),
+                                             ("B", 128, (16, 32, 32)), ("C", 28, (256, 14, 14)), ("C", 5, (3, 7, 5))])
 def test_pure_admm_gradient_vs_oracle_autograd(mode, tol, variant, B, shape):
     """d trans_loss / d x alone (no gradient through y): isolates the Gram backward -- the two [B,B]x[B,F]
-    products, the standardise backward and the chain through the CDF map -- from the much larger STE term."""
+    products, the standardise backward and the chain through the CDF map -- from the much larger STE term.
+    Bar for the fp32-parity modes (fp32 FFMA and the tcgen05 'tf32x3' mode): north_star's 1e-5 relative, both as
+    rel-norm and as max|d| / max|ref|, against fp64 autograd; the reference's own fp32 autograd sits at ~1e-6 on
+    the same inputs (printed).  bf16 mode: the Gram meets its 1e-2 bar (test_tc_corr_vs_oracle); this small
+    cancellation-heavy gradient is only bounded loosely (measured 0.8-5e-2)."""
     torch.manual_seed(15)
     aq.set_args(variant=variant, act_range=2, method="ours", gram_mode=mode)
     admm = aq.ADMM(128).to(DEV)
@@ -626,6 +663,101 @@ def test_pure_admm_gradient_vs_oracle_autograd(mode, tol, variant, B, shape):
     _, lo, _ = O.activation_quantize_admm(xo, 8, admm.alterD.detach().double(), admm.gamma.detach().double(),
                                           "second", variant, 2.0)
     lo.backward()
+    x32 = x0.clone().requires_grad_(True)
+    _, l32, _ = O.activation_quantize_admm(x32, 8, admm.alterD.detach(), admm.gamma.detach(), "second", variant, 2.0)
+    l32.backward()
     e = float((x.grad.double() - xo.grad).norm() / xo.grad.norm())
-    print(f"pure ADMM gradient {mode} {variant} B={B}: rel-norm err vs fp64 autograd {e:.2e}")
-    assert e <= tol
+    emax = float((x.grad.double() - xo.grad).abs().max() / xo.grad.abs().max())
+    fl = float((x32.grad.double() - xo.grad).norm() / xo.grad.norm())
+    print(f"pure ADMM gradient {mode} {variant} B={B}: rel-norm err vs fp64 autograd {e:.2e}, max|d|/max|ref| {emax:.2e} "
+          f"(reference fp32 autograd: {fl:.2e})")
+    assert e <= tol and emax <= (tol if mode != "bf16" else 1.0)
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,F,eps", [(8, 96, 0.0), (28, 3000, 1e-5), (128, 4096, 0.0), (100, 1027, 0.0), (160, 640, 1e-5)])
+def test_corr_autograd_vs_oracle(B, F, eps):
+    """corr(x, y) is differentiable through mean and std of both operands like the reference's (QB:134-137)."""
+    torch.manual_seed(16)
+    aq.set_args(gram_mode="fp32")
+    x0 = torch.randn(B, F, device=DEV) * 1.3 + 0.2
+    y0 = torch.randn(B, F, device=DEV) * 0.7 - 0.4
+    dG = torch.randn(B, B, device=DEV)
+    for same in (False, True):
+        x, y = x0.clone().requires_grad_(True), y0.clone().requires_grad_(True)
+        (aq.corr(x, x if same else y, eps) * dG).sum().backward()
+        ref = {}
+        for dt in (torch.float32, torch.float64):
+            xo, yo = x0.to(dt).clone().requires_grad_(True), y0.to(dt).clone().requires_grad_(True)
+            (O.corr(xo, xo if same else yo, eps) * dG.to(dt)).sum().backward()
+            ref[dt] = (xo.grad, None if same else yo.grad)
+        grad_close(x.grad, ref[torch.float64][0], ref[torch.float32][0], what=f"corr gx same={same}")
+        if same:
+            assert y.grad is None
+        else:
+            grad_close(y.grad, ref[torch.float64][1], ref[torch.float32][1], what="corr gy")
+    # only one operand needs a gradient
+    x = x0.clone().requires_grad_(True)
+    (aq.corr(x, y0, eps) * dG).sum().backward()
+    xo = x0.double().clone().requires_grad_(True)
+    (O.corr(xo, y0.double(), eps) * dG.double()).sum().backward()
+    assert float((x.grad.double() - xo.grad).abs().max()) <= 1e-5 * float(xo.grad.abs().max())
+
+
+def test_corr_autograd_in_tensor_core_modes_uses_the_same_backward():
+    torch.manual_seed(17)
+    x0 = torch.randn(64, 2048, device=DEV)
+    dG = torch.randn(64, 64, device=DEV)
+    grads = []
+    for mode in ("fp32", "tf32x3"):
+        aq.set_args(gram_mode=mode)
+        x = x0.clone().requires_grad_(True)
+        (aq.corr(x, x, 0.0) * dG).sum().backward()
+        grads.append(x.grad)
+    assert torch.equal(grads[0], grads[1])
+
+
+def test_cdf_standalone_refuses_to_drop_gradients_of_m_and_s():
+    aq.set_args(variant="A", act_range=2)
+    x = torch.randn(100, device=DEV)
+    m = torch.tensor(0.1, device=DEV, requires_grad=True)
+    with pytest.raises(aq.AlignQError):
+        aq.cdf(m, torch.tensor(0.7, device=DEV), "w")(x)
+    c, _ = aq.cdf(m.detach(), torch.tensor(0.7, device=DEV), "w")(x)        # constants are fine
+    assert c.shape == x.shape
+
+
+@pytest.mark.parametrize("variant", ["A", "B"])
+def test_linear_q_forward_backward_vs_oracle(variant):
+    """Linear_Q (cdf_alignment/dann_office/model/resnet.py:148-160): F.linear on the quantized weight."""
+    torch.manual_seed(18)
+    aq.set_args(variant=variant, bitW=8)
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        lin = aq.linear_Q_fn(8, "second")(96, 40).to(DEV)
+        x0 = torch.randn(32, 96, device=DEV)
+        gup = torch.randn(32, 40, device=DEV)
+        x = x0.clone().requires_grad_(True)
+        out = lin(x)
+        (out * gup).sum().backward()
+        res = {}
+        for dt in (torch.float32, torch.float64):
+            w = lin.weight.detach().to(dt).clone().requires_grad_(True)
+            b = lin.bias.detach().to(dt).clone().requires_grad_(True)
+            xo = x0.to(dt).clone().requires_grad_(True)
+            wq, _, _ = O.weight_quantize(w, 8, variant)
+            oo = torch.nn.functional.linear(xo, wq, b)
+            (oo * gup.to(dt)).sum().backward()
+            res[dt] = (oo.detach(), w.grad, xo.grad, b.grad, wq.detach())
+        n = 255
+        codes = lambda q: torch.round(((q + 1) / 2 if variant == "A" else q) * n)
+        assert int((codes(lin.quantize_fn.weight_q) != codes(res[torch.float32][4])).sum()) <= 1
+        if torch.equal(codes(lin.quantize_fn.weight_q).double(), codes(res[torch.float64][4])):
+            rel_close(out.detach(), res[torch.float64][0], rtol=1e-5, atol_frac=2e-6, what="Linear_Q out")
+            rel_close(x.grad, res[torch.float64][2], rtol=1e-5, atol_frac=2e-6, what="Linear_Q gx")
+        grad_close(lin.weight.grad, res[torch.float64][1], res[torch.float32][1], what="Linear_Q gw")
+        grad_close(lin.bias.grad, res[torch.float64][3], res[torch.float32][3], what="Linear_Q gb")
+        assert lin.w_bit == 8 and lin.quantize_fn.weight_pdf.shape == lin.weight.shape
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old

@@ -183,3 +183,52 @@ class QATStep:
             self._iteration(self.static_x, self.static_t)
         self.graph = g
         return self
+
+
+class HostFeeder:
+    """Double-buffered host -> device input staging for ``QATStep``: the H2D copy of batch i+1 runs on its own
+    stream while step i computes, so a training loop that reads its batches from (pinned) host memory does not
+    serialise a copy in front of every step.  Usage::
+
+        feeder = HostFeeder(step, x_example, t_example)
+        feeder.prefetch(x0, t0)
+        for (x_next, t_next) in batches:           # host tensors, ideally pinned
+            loss = feeder.step(x_next, t_next)      # runs the staged batch, stages the next one meanwhile
+
+    Every batch still crosses PCIe/NVLink-C2C exactly once; only the ordering changes."""
+
+    def __init__(self, step: QATStep, x_like, t_like):
+        dev = step.params[0].device
+        fmt = torch.channels_last if (x_like.dim() == 4 and x_like.is_contiguous(memory_format=torch.channels_last)
+                                      and not x_like.is_contiguous()) else torch.contiguous_format
+        self.qat = step
+        self.xs = [torch.empty(x_like.shape, dtype=x_like.dtype, device=dev).contiguous(memory_format=fmt) for _ in range(2)]
+        self.ts = [torch.empty(t_like.shape, dtype=t_like.dtype, device=dev) for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        self.slot = 0                      # slot holding the batch the next step() consumes
+        self.staged = False
+
+    def prefetch(self, host_x, host_t, slot=None):
+        slot = self.slot if slot is None else slot
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.consumed[slot])       # the step that last read this slot is done with it
+            self.xs[slot].copy_(host_x, non_blocking=True)
+            self.ts[slot].copy_(host_t, non_blocking=True)
+            self.ready[slot].record(self.copy_stream)
+        self.staged = True
+
+    def step(self, next_host_x=None, next_host_t=None):
+        if not self.staged:
+            raise L.AlignQError("HostFeeder.step(): nothing staged -- call prefetch(x, t) first")
+        cur = self.slot
+        main = torch.cuda.current_stream()
+        main.wait_event(self.ready[cur])
+        self.staged = False
+        if next_host_x is not None:                                # overlaps with the step launched just below
+            self.prefetch(next_host_x, next_host_t, slot=cur ^ 1)
+        loss = self.qat.step(self.xs[cur], self.ts[cur])
+        self.consumed[cur].record(main)
+        self.slot = cur ^ 1
+        return loss

@@ -64,35 +64,39 @@ def ncu_traffic_bytes():
 # ------------------------------------------------------------------------------------------------
 # CPU baseline: the oracle's port of the reference training iteration (kind = "port")
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_run(steps, warmup, budget_s=150.0, batch=BATCH):
+def cpu_reference_run(steps, warmup, budget_s=150.0, batch=BATCH, workload="resnet20"):
+    """The workload's batch is NEVER changed: when the box is slow the number of timed iterations
+    is cut instead (never below 10, warm-up never below 2), and the sample string says how many ran."""
     import torch
     from oracle import models_oracle as MO
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     torch.manual_seed(0)
-    model = MO.resnet20_oracle(8, 8, "A", act_range=2.0, dim=batch).train()
+    if workload == "resnet56_admm":                        # configs[1]: QB + ADMM (oracle pinned by make_model_golden.py)
+        model = MO.OracleResNet([9, 9, 9], 8, 8, "B", 2.0, dim=batch).train()
+    else:
+        model = MO.resnet20_oracle(8, 8, "A", act_range=2.0, dim=batch).train()
     tr = MO.OracleTrainer(model, lr=0.04, momentum=0.9, weight_decay=1e-4, lam=1.0, lam2=4.0, bitW=8)
     x = torch.randn(batch, 3, 32, 32)
     t = torch.randint(0, 10, (batch,))
     t0 = time.perf_counter()
     tr.step(x, t)                                          # first (untimed) iteration sizes the sample
     first = time.perf_counter() - t0
-    sample_batch = batch
-    total = steps + max(warmup - 1, 0)
-    if first * total > budget_s:                           # bound the run: shrink the per-step sample
-        sample_batch = max(8, int(batch * budget_s / (first * total)) // 8 * 8)
-        x, t = x[:sample_batch], t[:sample_batch]
-    for _ in range(max(warmup - 1, 0)):
+    warm = max(warmup - 1, 1)
+    if first * (steps + warm) > budget_s:                  # bound the run: fewer iterations, same batch
+        warm = min(warm, 2)
+        steps = max(10, min(steps, int(budget_s / first) - warm))
+    for _ in range(warm):
         tr.step(x, t)
     t0 = time.perf_counter()
     for _ in range(steps):
         tr.step(x, t)
     dt = time.perf_counter() - t0
-    return {"value": sample_batch * steps / dt, "unit": "img/s", "cores": cores, "kind": "port",
-            "sample": f"{steps} iterations of batch {sample_batch} (workload batch {batch}) after {warmup} warm-up, "
-                      f"oracle/models_oracle.OracleTrainer on CPU, torch threads={cores}",
-            "ms_per_step": dt / steps * 1e3}
+    return {"value": batch * steps / dt, "unit": "img/s", "cores": cores, "kind": "port",
+            "sample": f"{steps} timed iterations of the workload's batch {batch} after {warm + 1} warm-up, "
+                      f"oracle/models_oracle.OracleTrainer ({workload}) on CPU, torch threads={cores}",
+            "ms_per_step": dt / steps * 1e3, "steps_timed": steps}
 
 
 def gpu_eager_port_run(dev, steps=10, warmup=3, batch=BATCH):
@@ -127,13 +131,47 @@ def run_reference(args):
     if rank != 0:
         return
     cb = cpu_reference_run(args.steps, args.warmup)
+    # same config keys as the product arm's line (the CPU arm has one process whatever N is: it does not scale)
+    cfg = dict(CONFIG, global_batch=BATCH, parallelism="cpu", cpu_steps_timed=cb["steps_timed"])
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "img/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": CONFIG,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def fused_code_mismatch(dev):
+    """Fraction of activation codes of the fused BatchNorm -> act-quant -> ReLU kernels that differ (by one level: a BN
+    output on a rounding tie) from cuDNN BatchNorm + the stand-alone quantizer kernel, on the three layer shapes of the
+    headline workload; beside it the same count for cuDNN's fp32 BN against an fp64 BN (the reference's own tie floor)."""
+    import copy
+    import torch
+    import alignq_b200 as aq
+    from alignq_b200.model.fused import bn_act
+    out = {}
+    worst = 0.0
+    for shape in ((BATCH, 16, 32, 32), (BATCH, 32, 16, 16), (BATCH, 64, 8, 8)):
+        torch.manual_seed(0)
+        x = (torch.randn(shape, device=dev) * 1.5 + 0.3).contiguous(memory_format=torch.channels_last)
+        bn = torch.nn.BatchNorm2d(shape[1]).to(dev).train()
+        bn32, bn64 = copy.deepcopy(bn), copy.deepcopy(bn).double()
+        q = aq.activation_quantize_fn(8, "second")
+        with torch.no_grad():
+            y = bn_act(bn, q, x, True)
+            aq.set_args(fuse_bn_act=False)
+            y32 = torch.relu(q(bn32(x)))
+            z64 = bn64(x.double())
+            y64 = torch.relu(q(z64.float()))               # fp64 BN rounded once to fp32, then the same quantizer kernel
+            aq.set_args(fuse_bn_act=True)
+        n = y.numel()
+        f = float(((y - y32).abs() > 1e-6).sum()) / n
+        worst = max(worst, f)
+        out["x".join(map(str, shape))] = {"vs_cudnn_bn": f, "vs_fp64_bn": float(((y - y64).abs() > 1e-6).sum()) / n,
+                                          "cudnn_bn_vs_fp64_bn": float(((y32 - y64).abs() > 1e-6).sum()) / n}
+    return {"code_mismatch_frac_max": worst, "bar": 1e-5, "per_shape": out,
+            "what": "+-1 code at BatchNorm-output rounding ties, fused kernels vs cuDNN BN + quantizer kernel"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -186,7 +224,7 @@ def run_product(args):
     import alignq_b200 as aq
     from alignq_b200 import _lib as L
     from alignq_b200.model.resnet import resnet20_quant
-    from alignq_b200.utils.train import QATStep
+    from alignq_b200.utils.train import HostFeeder, QATStep
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -306,23 +344,31 @@ def run_product(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(k, w, host_inputs):
+    def timed(k, w, host_inputs, st=None):
         """k steps after w warm-ups; per-step CUDA events on the launching stream, L2 flushed between
-        steps (outside the events).  Returns summed device milliseconds."""
+        steps (outside the events).  Returns summed device milliseconds.
+        host_inputs: every step's batch starts in pinned HOST memory and is copied to the device inside the timed
+        region -- through HostFeeder, i.e. the copy of batch i+1 is issued (copy stream) right before step i is
+        launched and overlaps it; step i waits for ITS copy.  In steady state every timed step contains exactly one
+        H2D of a full batch and one D2H read of the loss."""
+        st = step if st is None else st
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k)]
         sink = 0.0
+        feeder = None
+        if host_inputs:
+            feeder = HostFeeder(st, dev_x[0], dev_t[0])
+            feeder.prefetch(host_x[0], host_t[0])
         for i in range(w + k):
             flush.zero_()
             j = i % n_host
             if i >= w:
                 ev[i - w][0].record()
             if host_inputs:
-                x = host_x[j].to(dev, non_blocking=True)
-                t = host_t[j].to(dev, non_blocking=True)
-                loss = step.step(x, t)
+                jn = (i + 1) % n_host
+                loss = feeder.step(host_x[jn], host_t[jn])
                 sink += float(loss.item())                  # D2H read of the step's loss (4 bytes), syncs
             else:
-                step.step(dev_x[j], dev_t[j])
+                st.step(dev_x[j], dev_t[j])
             if i >= w:
                 ev[i - w][1].record()
             if i == w - 1:
@@ -401,13 +447,30 @@ def run_product(args):
             del xg, Gg, wsg
         except Exception as e:                              # pragma: no cover
             gram = {"error": str(e)[:200]}
-        if world == 1 and not args.no_cpu_baseline and args.workload == "resnet20":
-            cb = cpu_reference_run(3, 1, budget_s=30.0)
+        if world == 1 and not args.no_cpu_baseline and args.workload in ("resnet20", "resnet56_admm"):
+            cb = cpu_reference_run(20, 3, budget_s=40.0, workload=args.workload)
             cpu = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
-            try:
-                cpu["gpu_eager_port"] = gpu_eager_port_run(dev)
-            except Exception as e:                          # pragma: no cover - a baseline, never fatal
-                cpu["gpu_eager_port"] = {"error": str(e)[:200]}
+            if args.workload == "resnet20":
+                try:
+                    cpu["gpu_eager_port"] = gpu_eager_port_run(dev)
+                except Exception as e:                      # pragma: no cover - a baseline, never fatal
+                    cpu["gpu_eager_port"] = {"error": str(e)[:200]}
+
+    fused_parity = no_fuse = None
+    if rank == 0 and world == 1 and fuse and args.workload == "resnet20":
+        fused_parity = fused_code_mismatch(dev)
+        # the same step with BatchNorm / quantizer / ReLU as separate kernels, beside the fused number
+        aq.set_args(fuse_bn_act=False)
+        torch.manual_seed(0)
+        m2 = resnet20_quant(8, 8, "second").to(dev).train()
+        st2 = QATStep(m2, lr=0.04, momentum=0.9, weight_decay=1e-4, channels_last=not args.nchw, single_backward=True)
+        if graphed:
+            st2.capture(dev_x[0], dev_t[0], warmup=3)
+        k2 = min(args.steps, 50)
+        ms2, _ = timed(k2, 5, host_inputs=False, st=st2)
+        no_fuse = {"value": batch * k2 / (ms2 * 1e-3), "unit": "img/s", "ms_per_step": ms2 / k2, "steps": k2,
+                   "what": "same workload with fuse_bn_act=False (cuDNN BatchNorm + act-quant kernel + ReLU)"}
+        aq.set_args(fuse_bn_act=True)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
@@ -422,7 +485,8 @@ def run_product(args):
                         "h2d_bytes_per_step": nimg * 3 * img_hw * img_hw * 4 + batch * 8, "d2h_bytes_per_step": 4},
                 "gpu_launches": int(launches_per_step) * args.steps,
                 "gpu_launches_per_step": int(launches_per_step),
-                "clocks": clocks, "roofline": roofline, "gram_tensor_roofline": gram, "cpu_baseline": cpu}
+                "clocks": clocks, "roofline": roofline, "gram_tensor_roofline": gram, "cpu_baseline": cpu,
+                "fused_bn_act_parity": fused_parity, "no_fuse": no_fuse}
         print(json.dumps(line), flush=True)
     if world > 1:
         # Tear down without NCCL's communicator destructor: with captured NCCL kernels still referenced

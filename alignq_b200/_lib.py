@@ -48,6 +48,9 @@ SIGNATURES = {
     "alignq_gram_ws_bytes": (_Z, [_I, _L]),
     "alignq_corr_fwd": (_I, [_P, _P, _I, _L, _F, _P, _P, _Z, _I, _P]),
     "alignq_corr_bwd": (_I, [_P, _P, _P, _I, _L, _F, _P, _P, _P, _Z, _P]),
+    "alignq_gram_sums_fwd": (_I, [_P, _I, _L, _F, _F, _P, _P, _Z, _I, _P]),
+    "alignq_gram_sums_to_d": (_I, [_P, _P, _I, _I, _P, _P]),
+    "alignq_act_bwd_add": (_I, [_P, _P, _P, _P, _L, _I, _F, _I, _I, _P]),
     "alignq_act_admm_fwd": (_I, [_P, _I, _L, _I, _F, _F, _P, _P, _I, _F, _F, _P, _P, _P, _P, _P, _Z, _I, _P]),
     "alignq_act_admm_bwd": (_I, [_P, _P, _P, _P, _I, _L, _I, _F, _F, _P, _P, _Z, _I, _P]),
     "alignq_admm_loss": (_I, [_P, _I, _P, _P, _I, _I, _F, _F, _P, _I, _P, _P, _P, _P, _P]),
@@ -57,6 +60,10 @@ SIGNATURES = {
     "alignq_bn_act_ws_doubles": (_Z, [_I]),
     "alignq_bn_act_fwd": (_I, [_P, _L, _I, _P, _P, _P, _P, _F, _F, _I, _I, _F, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "alignq_bn_act_bwd": (_I, [_P, _P, _P, _L, _I, _P, _P, _P, _P, _I, _I, _F, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "alignq_bn_act_sync_stats": (_I, [_P, _L, _I, _P, _P, _P, _P]),
+    "alignq_bn_act_sync_apply": (_I, [_P, _L, _L, _I, _P, _P, _P, _P, _P, _F, _F, _I, _F, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "alignq_bn_act_sync_bwd_reduce": (_I, [_P, _P, _P, _L, _I, _P, _P, _P, _P, _I, _F, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "alignq_bn_act_sync_bwd_apply": (_I, [_P, _P, _P, _L, _L, _I, _P, _P, _P, _P, _I, _F, _I, _I, _P, _P, _P, _P, _P]),
     "alignq_sgd_step": (_I, [_P, _P, _P, _I, _L, _F, _F, _I, _F, _P]),
 }
 

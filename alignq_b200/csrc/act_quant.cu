@@ -131,6 +131,27 @@ act_bwd_scalar_kernel(const float* __restrict__ x, const float* __restrict__ gy,
     gx[i] = act_bwd_one(x[i], gy[i], gscale);
 }
 
+// gx = gadd + gy * gscale * exp(-v^2): the straight-through term added to a gradient that arrived by another route
+// (data-parallel feature-sharded ADMM term: the all-to-all'ed Gram gradient, utils/dp_gram.py)
+__global__ void __launch_bounds__(256)
+act_bwd_add_kernel(const float* __restrict__ x, const float* __restrict__ gy, const float* __restrict__ gadd,
+                   float* __restrict__ gx, int64_t numel, int vec, float gscale) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n4 = vec ? numel / 4 : 0;
+  for (int64_t k = i; k < n4; k += stride) {
+    const float4 a = ld_stream(reinterpret_cast<const float4*>(x) + k), b = ld_stream(reinterpret_cast<const float4*>(gy) + k);
+    const float4 c = ld_stream(reinterpret_cast<const float4*>(gadd) + k);
+    float4 o;
+    o.x = c.x + act_bwd_one(a.x, b.x, gscale);
+    o.y = c.y + act_bwd_one(a.y, b.y, gscale);
+    o.z = c.z + act_bwd_one(a.z, b.z, gscale);
+    o.w = c.w + act_bwd_one(a.w, b.w, gscale);
+    reinterpret_cast<float4*>(gx)[k] = o;
+  }
+  for (int64_t k = n4 * 4 + i; k < numel; k += stride) gx[k] = gadd[k] + act_bwd_one(x[k], gy[k], gscale);
+}
+
 // grid sizing: whole multiples of the SM count, 8 resident 256-thread CTAs per SM at most
 static inline int stream_grid(int64_t work_items, int per_block) {
   int64_t blocks = (work_items + per_block - 1) / per_block;
@@ -225,6 +246,20 @@ extern "C" int alignq_act_bwd(const float* x, const float* gy, float* gx, int64_
     act_bwd_scalar_kernel<<<grid, 256, 0, s>>>(x, gy, gx, n4 * 4, numel, gscale);
     ALIGNQ_LAUNCH_CHECK();
   }
+  return ALIGNQ_OK;
+}
+
+extern "C" int alignq_act_bwd_add(const float* x, const float* gy, const float* gadd, float* gx, int64_t numel, int a_bit,
+                                  float act_range, int variant, int return_cdf, alignq_stream_t stream) {
+  if (numel < 0 || a_bit < 1 || a_bit > 32 || variant < 0 || variant > 2) return ALIGNQ_EINVAL;
+  if (a_bit == 32 && !return_cdf) return ALIGNQ_EINVAL;
+  if (numel == 0) return ALIGNQ_OK;
+  if (!x || !gy || !gadd || !gx) return ALIGNQ_EINVAL;
+  const float gscale = alignq_act_grad_scale(a_bit, act_range, variant, return_cdf);
+  const int vec = aligned16(x) && aligned16(gy) && aligned16(gx) && aligned16(gadd);
+  act_bwd_add_kernel<<<stream_grid((numel + 3) / 4, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, gy, gadd, gx, numel, vec, gscale);
+  ALIGNQ_LAUNCH_CHECK();
   return ALIGNQ_OK;
 }
 

@@ -70,8 +70,21 @@ gram_reduce_kernel(const float* __restrict__ partials, int nslabs, int B, float 
   if (fused) {
     const float* pt = partials + (size_t)nslabs * bb;
     for (int s = 0; s < nslabs; ++s) st += pt[(size_t)s * bb + e];
-    D[e] = __fsub_rn(__fmul_rn(st, invF), gx);
+    D[e] = (fused == 2) ? __fmul_rn(st, invF) : __fsub_rn(__fmul_rn(st, invF), gx);     // 2: the t sum itself
   }
+}
+
+// D = sum_t / F - sum_x / F (two separately rounded Grams, QB:118-122) from the un-normalised column sums of the
+// data-parallel feature-sharded path, after their all-reduce; module m: sums + m*2*B*B, invF[m], D + m*B*B.
+__global__ void __launch_bounds__(256)
+gram_sums_to_d_kernel(const float* __restrict__ sums, const float* __restrict__ invF, int B, float* __restrict__ D) {
+  const size_t bb = (size_t)B * B;
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= bb) return;
+  const int m = blockIdx.y;
+  const float f = invF[m];
+  const float* sm = sums + (size_t)m * 2 * bb;
+  D[(size_t)m * bb + e] = __fsub_rn(__fmul_rn(sm[bb + e], f), __fmul_rn(sm[e], f));
 }
 
 __global__ void __launch_bounds__(256)
@@ -180,6 +193,13 @@ int launch_gram_reduce(const float* partials, int nslabs, int B, int64_t F, int 
   return ALIGNQ_OK;
 }
 
+int launch_gram_reduce_raw(const float* partials, int nslabs, int B, float* Gx, float* Gt, cudaStream_t s) {
+  const int bb = B * B;
+  gram_reduce_kernel<<<(bb + 255) / 256, 256, 0, s>>>(partials, nslabs, B, 1.0f, 2, Gx, Gt);
+  ALIGNQ_LAUNCH_CHECK();
+  return ALIGNQ_OK;
+}
+
 int launch_wsym(const float* dLdD, int B, float* Wsym, cudaStream_t s) {
   const int Bp = gram_bp(B);
   wsym_kernel<<<(Bp * Bp + 255) / 256, 256, 0, s>>>(dLdD, B, Bp, Wsym);
@@ -199,6 +219,15 @@ extern "C" int alignq_admm_loss(const float* D, int B, const float* Z, const flo
   if (!D || !Z || !U) return ALIGNQ_EINVAL;
   admm_loss_kernel<<<nmod * ACL, AT, 0, reinterpret_cast<cudaStream_t>(stream)>>>(D, B, Z, U, dim, mu, rho, gloss,
                                                                            gloss_per_module, loss, dLdD, dLdZ, dLdU);
+  ALIGNQ_LAUNCH_CHECK();
+  return ALIGNQ_OK;
+}
+
+extern "C" int alignq_gram_sums_to_d(const float* sums, const float* inv_f, int B, int nmod, float* D, alignq_stream_t stream) {
+  if (B < 1 || nmod < 0) return ALIGNQ_EINVAL;
+  if (nmod == 0) return ALIGNQ_OK;
+  if (!sums || !inv_f || !D) return ALIGNQ_EINVAL;
+  gram_sums_to_d_kernel<<<dim3((B * B + 255) / 256, nmod), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(sums, inv_f, B, D);
   ALIGNQ_LAUNCH_CHECK();
   return ALIGNQ_OK;
 }

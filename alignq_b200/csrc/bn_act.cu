@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(BN_MAX_THREADS)
 bnq_stats_kernel(const float* __restrict__ x, int64_t R, int C, float* __restrict__ running_mean,
                  float* __restrict__ running_var, float momentum, float bn_eps, float* __restrict__ save_mean,
                  float* __restrict__ save_invstd, double* __restrict__ ws, unsigned* __restrict__ counter,
-                 long long* __restrict__ num_batches_tracked) {
+                 long long* __restrict__ num_batches_tracked, double* __restrict__ sums_out) {
   extern __shared__ float sh[];
   __shared__ unsigned flag;
 
@@ -116,6 +116,10 @@ bnq_stats_kernel(const float* __restrict__ x, int64_t R, int C, float* __restric
         S += __ldcg(a); SS += __ldcg(a + 1);
         a[0] = 0.0; a[1] = 0.0;                              // re-arm the accumulators
       }
+      if (sums_out) {                                        // data-parallel SyncBN: the caller all-reduces (sum, sum of
+        sums_out[c] = S; sums_out[C + c] = SS;               // squares) over the ranks, bnq_sync_finalize_kernel finishes
+        continue;
+      }
       const double mean = S / (double)R;
       double var = SS / (double)R - mean * mean;            // biased: what BN normalises with
       var = var < 0.0 ? 0.0 : var;
@@ -129,9 +133,36 @@ bnq_stats_kernel(const float* __restrict__ x, int64_t R, int C, float* __restric
     }
     if (threadIdx.x == 0) {
       *counter = 0u;                                        // re-arm for the next launch
-      if (num_batches_tracked) *num_batches_tracked += 1;   // BatchNorm2d.num_batches_tracked
+      if (num_batches_tracked && !sums_out) *num_batches_tracked += 1;   // BatchNorm2d.num_batches_tracked
     }
   }
+}
+
+// SyncBN: statistics of the GLOBAL batch from the all-reduced fp64 (sum, sum of squares) and the global row count
+__global__ void bnq_sync_finalize_kernel(const double* __restrict__ sums, double Rg, int C, float* __restrict__ running_mean,
+                                         float* __restrict__ running_var, float momentum, float bn_eps,
+                                         float* __restrict__ save_mean, float* __restrict__ save_invstd,
+                                         long long* __restrict__ num_batches_tracked) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    const double mean = sums[c] / Rg;
+    double var = sums[C + c] / Rg - mean * mean;
+    var = var < 0.0 ? 0.0 : var;
+    save_mean[c] = (float)mean;
+    save_invstd[c] = (float)(1.0 / sqrt(var + (double)bn_eps));
+    if (running_mean) {
+      const double unbiased = Rg > 1.0 ? var * Rg / (Rg - 1.0) : var;
+      running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * mean);
+      running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unbiased);
+    }
+  }
+  if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
+}
+
+// SyncBN backward: mean(g_z), mean(g_z xhat) over the GLOBAL batch from the all-reduced sums
+__global__ void bnq_sync_coef_kernel(const double* __restrict__ sums, double Rg, int C, float* __restrict__ coef) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) { coef[2 * c] = (float)(sums[c] / Rg); coef[2 * c + 1] = (float)(sums[C + c] / Rg); }
 }
 
 // eval mode: statistics are the running ones
@@ -178,7 +209,7 @@ bnq_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ y, 
                       int C, const float* __restrict__ gamma, const float* __restrict__ beta,
                       const float* __restrict__ mean, const float* __restrict__ invstd, BnQ q,
                       float* __restrict__ ggamma, float* __restrict__ gbeta, float* __restrict__ coef /* [C][2] */,
-                      double* __restrict__ ws, unsigned* __restrict__ counter) {
+                      double* __restrict__ ws, unsigned* __restrict__ counter, double* __restrict__ sums_out) {
   extern __shared__ float sh[];
   __shared__ unsigned flag;
 
@@ -228,8 +259,9 @@ bnq_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ y, 
         S += __ldcg(a); SS += __ldcg(a + 1);
         a[0] = 0.0; a[1] = 0.0;                              // re-arm the accumulators
       }
-      if (gbeta) gbeta[c] = (float)S;
-      if (ggamma) ggamma[c] = (float)SS;
+      if (gbeta) gbeta[c] = (float)S;                        // affine gradients: LOCAL sums in either mode (a data-parallel
+      if (ggamma) ggamma[c] = (float)SS;                     // step averages them with the other parameter gradients)
+      if (sums_out) { sums_out[c] = S; sums_out[C + c] = SS; continue; }
       coef[2 * c] = (float)(S / (double)R);
       coef[2 * c + 1] = (float)(SS / (double)R);
     }
@@ -451,7 +483,7 @@ extern "C" int alignq_bn_act_fwd(const float* x, int64_t rows, int C, const floa
   if (training) {
     bnq_stats_kernel<<<L.grid, L.threads, L.smem, s>>>(x, rows, C, running_mean, running_var, momentum, bn_eps,
                                                        save_mean, save_invstd, ws, counter,
-                                                       reinterpret_cast<long long*>(num_batches_tracked));
+                                                       reinterpret_cast<long long*>(num_batches_tracked), nullptr);
   } else {
     bnq_eval_stats_kernel<<<(C + 255) / 256, 256, 0, s>>>(running_mean, running_var, bn_eps, C, save_mean, save_invstd);
   }
@@ -490,10 +522,80 @@ extern "C" int alignq_bn_act_bwd(const float* x, const float* y, const float* gy
   }
   float* coef = reinterpret_cast<float*>(ws + (size_t)3 * BN_SLOTS * C * 2);       // [C][2] floats after the accumulators
   bnq_bwd_reduce_kernel<<<L.grid, L.threads, L.smem, s>>>(x, y, gy, rows, C, gamma, beta, save_mean, save_invstd, q,
-                                                          ggamma, gbeta, coef, ws, counter);
+                                                          ggamma, gbeta, coef, ws, counter, nullptr);
   ALIGNQ_LAUNCH_CHECK();
   bnq_bwd_apply_kernel<<<L.grid * 2, L.threads, 0, s>>>(x, y, gy, rows, C, gamma, beta, save_mean, save_invstd, coef,
                                                         training, q, gx, g_residual);
+  ALIGNQ_LAUNCH_CHECK();
+  return ALIGNQ_OK;
+}
+
+// ---- data-parallel SyncBN: the same kernels cut at the point where the ranks' fp64 sums are all-reduced ----------
+extern "C" int alignq_bn_act_sync_stats(const float* x, int64_t rows, int C, double* sums, double* ws, uint32_t* counter,
+                                        alignq_stream_t stream) {
+  if (rows < 1 || C < 4 || (C & 3) || C > 4 * BN_MAX_THREADS || !x || !sums || !ws || !counter) return ALIGNQ_EINVAL;
+  if (!aligned16(x)) return ALIGNQ_EALIGN;
+  const BnLaunch L = bn_launch(rows, C);
+  bnq_stats_kernel<<<L.grid, L.threads, L.smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, rows, C, nullptr, nullptr, 0.f, 0.f, nullptr, nullptr, ws, counter, nullptr, sums);
+  ALIGNQ_LAUNCH_CHECK();
+  return ALIGNQ_OK;
+}
+
+extern "C" int alignq_bn_act_sync_apply(const float* x, int64_t rows, int64_t rows_global, int C, const double* sums,
+                                        const float* gamma, const float* beta, float* running_mean, float* running_var,
+                                        float momentum, float bn_eps, int a_bit, float act_range, int variant, int relu,
+                                        const float* residual, float* y, float* save_mean, float* save_invstd,
+                                        int64_t* num_batches_tracked, alignq_stream_t stream) {
+  int rc = bn_check(rows, C, a_bit, variant, x, y, residual);
+  if (rc) return rc;
+  if (!x || !y || !sums || !save_mean || !save_invstd || rows_global < rows) return ALIGNQ_EINVAL;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  bnq_sync_finalize_kernel<<<(C + 255) / 256, 256, 0, s>>>(sums, (double)rows_global, C, running_mean, running_var, momentum,
+                                                            bn_eps, save_mean, save_invstd,
+                                                            reinterpret_cast<long long*>(num_batches_tracked));
+  ALIGNQ_LAUNCH_CHECK();
+  const BnLaunch L = bn_launch(rows, C);
+  bnq_apply_kernel<<<L.grid * 2, L.threads, 0, s>>>(x, rows, C, gamma, beta, save_mean, save_invstd,
+                                                    make_bnq(a_bit, act_range, variant, relu), residual, y);
+  ALIGNQ_LAUNCH_CHECK();
+  return ALIGNQ_OK;
+}
+
+extern "C" int alignq_bn_act_sync_bwd_reduce(const float* x, const float* y, const float* gy, int64_t rows, int C,
+                                             const float* gamma, const float* beta, const float* save_mean,
+                                             const float* save_invstd, int a_bit, float act_range, int variant, int relu,
+                                             double* sums, float* ggamma, float* gbeta, double* ws, uint32_t* counter,
+                                             alignq_stream_t stream) {
+  int rc = bn_check(rows, C, a_bit, variant, x, gy, nullptr);
+  if (rc) return rc;
+  if (!x || !gy || !sums || !save_mean || !save_invstd || !ws || !counter || (relu && !y)) return ALIGNQ_EINVAL;
+  if (relu && !aligned16(y)) return ALIGNQ_EALIGN;
+  const BnLaunch L = bn_launch(rows, C);
+  float* coef = reinterpret_cast<float*>(ws + (size_t)3 * BN_SLOTS * C * 2);
+  bnq_bwd_reduce_kernel<<<L.grid, L.threads, L.smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, y, gy, rows, C, gamma, beta, save_mean, save_invstd, make_bnq(a_bit, act_range, variant, relu), ggamma, gbeta, coef,
+      ws, counter, sums);
+  ALIGNQ_LAUNCH_CHECK();
+  return ALIGNQ_OK;
+}
+
+extern "C" int alignq_bn_act_sync_bwd_apply(const float* x, const float* y, const float* gy, int64_t rows, int64_t rows_global,
+                                            int C, const float* gamma, const float* beta, const float* save_mean,
+                                            const float* save_invstd, int a_bit, float act_range, int variant, int relu,
+                                            const double* sums, float* gx, float* g_residual, double* ws,
+                                            alignq_stream_t stream) {
+  int rc = bn_check(rows, C, a_bit, variant, x, gy, gx);
+  if (rc) return rc;
+  if (!x || !gy || !gx || !sums || !save_mean || !save_invstd || !ws || (relu && !y) || rows_global < rows) return ALIGNQ_EINVAL;
+  if ((relu && !aligned16(y)) || (g_residual && !aligned16(g_residual))) return ALIGNQ_EALIGN;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  float* coef = reinterpret_cast<float*>(ws + (size_t)3 * BN_SLOTS * C * 2);
+  bnq_sync_coef_kernel<<<(C + 255) / 256, 256, 0, s>>>(sums, (double)rows_global, C, coef);
+  ALIGNQ_LAUNCH_CHECK();
+  const BnLaunch L = bn_launch(rows, C);
+  bnq_bwd_apply_kernel<<<L.grid * 2, L.threads, 0, s>>>(x, y, gy, rows, C, gamma, beta, save_mean, save_invstd, coef, 1,
+                                                        make_bnq(a_bit, act_range, variant, relu), gx, g_residual);
   ALIGNQ_LAUNCH_CHECK();
   return ALIGNQ_OK;
 }

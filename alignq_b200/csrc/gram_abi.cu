@@ -73,6 +73,23 @@ extern "C" int alignq_act_admm_fwd(const float* x, int B, int64_t F, int a_bit, 
   return alignq_admm_loss(D, B, Z, U, dim, 1, mu, rho, nullptr, 0, loss, dLdD, nullptr, nullptr, stream);
 }
 
+extern "C" int alignq_gram_sums_fwd(const float* x, int B, int64_t F, float act_range, float eps, float* sums, void* ws,
+                                    size_t ws_bytes, int gram_mode, alignq_stream_t stream) {
+  if (B < 2 || F < 1 || !x || !sums || !ws) return ALIGNQ_EINVAL;
+  if (B > 1024) return ALIGNQ_ERANGE;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  ActQ q{act_range, 1.0f, 1.0f, 32};                           // only the map t = (2 Phi(x) - 1) ar is needed, no rounding
+  float* Gx = sums;
+  float* Gt = sums + (size_t)B * B;
+  if (gram_mode == ALIGNQ_GRAM_FP32 || B > 128) {
+    int nslabs = 0;
+    int rc = gram_ffma_forward(x, x, B, F, eps, 1, q, nullptr, ws_partials(ws, B), &nslabs, ws_bytes, s);
+    if (rc) return rc;
+    return launch_gram_reduce_raw(ws_partials(ws, B), nslabs, B, Gx, Gt, s);
+  }
+  return gram_tc_sums(x, B, F, q, eps, Gx, Gt, ws, ws_bytes, gram_mode, s);
+}
+
 extern "C" int alignq_act_admm_bwd(const float* x, const float* gy, const float* dLdD, const float* gloss, int B,
                                    int64_t F, int a_bit, float act_range, float eps, float* gx, void* ws,
                                    size_t ws_bytes, int gram_mode, alignq_stream_t stream) {

@@ -58,12 +58,16 @@ int gram_tc_corr(const float* x, int B, int64_t F, float eps, float* G, void* ws
                  cudaStream_t s);
 int gram_tc_fused_fwd(const float* x, int B, int64_t F, ActQ q, float eps, float* y, float* D, void* ws,
                       size_t ws_bytes, int gram_mode, const AdmmFinish* fin, cudaStream_t s);
+// un-normalised column sums  sum_f Xs Xs^T -> Gx,  sum_f Ts Ts^T -> Gt  (data-parallel feature-sharded partials)
+int gram_tc_sums(const float* x, int B, int64_t F, ActQ q, float eps, float* Gx, float* Gt, void* ws, size_t ws_bytes,
+                 int gram_mode, cudaStream_t s);
 // gram_tc_bwd.cu
 int gram_tc_backward(const float* x, const float* gy, const float* Wsym, int Bp, const float* gloss, int B, int64_t F,
                      float ar, float eps, float* gx, int split, cudaStream_t s);
 // admm.cu
 int launch_gram_reduce(const float* partials, int nslabs, int B, int64_t F, int fused, float* Gx_or_G, float* D,
                        cudaStream_t s);
+int launch_gram_reduce_raw(const float* partials, int nslabs, int B, float* Gx, float* Gt, cudaStream_t s);
 int launch_wsym(const float* dLdD, int B, float* Wsym, cudaStream_t s);
 
 }  // namespace alignq

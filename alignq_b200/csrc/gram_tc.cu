@@ -354,7 +354,7 @@ gram_reduce_tc_kernel(const float* __restrict__ partials, int nparts, int B, flo
   if (fused) {
 #pragma unroll
     for (int k = 0; k < 32; ++k) gt += sm[1][k][threadIdx.x];
-    D[e] = __fsub_rn(__fmul_rn(gt, invF), gx);
+    D[e] = (fused == 2) ? __fmul_rn(gt, invF) : __fsub_rn(__fmul_rn(gt, invF), gx);      // 2: the t sum itself
   }
 }
 
@@ -441,6 +441,11 @@ gram_finish_tc_kernel(const float* __restrict__ partials, int nparts, int B, flo
 // reduce, or reduce + ADMM loss when the caller asked for it (fused forward only)
 static void launch_finish_tc(const float* partials, int nparts, int B, int64_t F, int nacc, int fused, float* G, float* D,
                              const AdmmFinish* fin, void* ws, cudaStream_t s) {
+  if (fused && G && D && !fin) {              // raw sums (gram_tc_sums): G <- sum_x, D <- sum_t, not divided by F
+    const int bb = B * B;
+    gram_reduce_tc_kernel<<<(bb + 31) / 32, dim3(32, 32), 0, s>>>(partials, nparts, B, 1.0f, nacc, 2, G, D);
+    return;
+  }
   if (fin && fused) {
     const int bb = B * B;
     gram_finish_tc_kernel<<<(bb + 31) / 32, dim3(32, 32), 0, s>>>(partials, nparts, B, 1.0f / (float)F, *fin, D,
@@ -509,6 +514,14 @@ int gram_tc_corr(const float* x, int B, int64_t F, float eps, float* G, void* ws
   ActQ q{0.f, 0.f, 0.f, 0};
   if (gram_mode == ALIGNQ_GRAM_TF32X3) return tc::launch<ALIGNQ_GRAM_TF32X3, false>(x, B, F, eps, q, nullptr, G, nullptr, ws, ws_bytes, nullptr, s);
   if (gram_mode == ALIGNQ_GRAM_BF16) return tc::launch<ALIGNQ_GRAM_BF16, false>(x, B, F, eps, q, nullptr, G, nullptr, ws, ws_bytes, nullptr, s);
+  return ALIGNQ_EINVAL;
+}
+
+int gram_tc_sums(const float* x, int B, int64_t F, ActQ q, float eps, float* Gx, float* Gt, void* ws, size_t ws_bytes,
+                 int gram_mode, cudaStream_t s) {
+  if (B > 128 || B < 2 || !Gx || !Gt) return ALIGNQ_ERANGE;
+  if (gram_mode == ALIGNQ_GRAM_TF32X3) return tc::launch<ALIGNQ_GRAM_TF32X3, true>(x, B, F, eps, q, nullptr, Gx, Gt, ws, ws_bytes, nullptr, s);
+  if (gram_mode == ALIGNQ_GRAM_BF16) return tc::launch<ALIGNQ_GRAM_BF16, true>(x, B, F, eps, q, nullptr, Gx, Gt, ws, ws_bytes, nullptr, s);
   return ALIGNQ_EINVAL;
 }
 

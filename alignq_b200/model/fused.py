@@ -70,6 +70,72 @@ class _BnActFn(torch.autograd.Function):
         return gx, gw, gb, None, None, None, None, None, gr
 
 
+class _SyncBnActFn(torch.autograd.Function):
+    """Data-parallel form: BatchNorm statistics of the GLOBAL batch.  The kernels' own fp64 (sum, sum of squares)
+    accumulators are all-reduced between the statistics and the apply launch (forward), and (sum g_z, sum g_z xhat)
+    between the reduce and the apply launch (backward) -- one [2 C] fp64 NCCL all-reduce each, so ``sync_bn`` keeps the
+    fused path instead of falling back to torch.nn.SyncBatchNorm + separate quantizer kernels."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, bn, a_bit, act_range, variant, relu, residual, group, world):
+        import torch.distributed as dist
+        B, C, H, W = x.shape
+        rows = B * H * W
+        y = torch.empty_like(x)
+        mean = torch.empty(C, dtype=torch.float32, device=x.device)
+        invstd = torch.empty(C, dtype=torch.float32, device=x.device)
+        ws, counter = _bn_ws(bn, C, x.device)
+        sums = torch.empty(2 * C, dtype=torch.float64, device=x.device)
+        lib = L.load()
+        with torch.cuda.device_of(x):
+            L.check(lib.alignq_bn_act_sync_stats(x.data_ptr(), rows, C, sums.data_ptr(), ws.data_ptr(), counter.data_ptr(),
+                                                 L.stream_ptr()), "alignq_bn_act_sync_stats")
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+            rows_global = rows * world                             # equal shards (QATStep shards the batch evenly)
+            L.check(lib.alignq_bn_act_sync_apply(
+                x.data_ptr(), rows, rows_global, C, sums.data_ptr(), L.ptr(weight), L.ptr(bias), L.ptr(bn.running_mean),
+                L.ptr(bn.running_var), float(bn.momentum), float(bn.eps), a_bit, act_range, variant, int(relu),
+                L.ptr(residual), y.data_ptr(), mean.data_ptr(), invstd.data_ptr(), L.ptr(bn.num_batches_tracked),
+                L.stream_ptr()), "alignq_bn_act_sync_apply")
+        ctx.bn, ctx.group = bn, group
+        ctx.save_for_backward(x, y if relu else None, weight, bias, mean, invstd)
+        ctx.cfg = (rows, rows_global, C, a_bit, act_range, variant, relu, residual is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        import torch.distributed as dist
+        x, y, weight, bias, mean, invstd = ctx.saved_tensors
+        rows, rows_global, C, a_bit, act_range, variant, relu, has_res = ctx.cfg
+        gy = L.like_layout(gy, x, "grad of fused bn-act output")
+        gx = torch.empty_like(x)
+        gr = torch.empty_like(x) if (has_res and ctx.needs_input_grad[8]) else None
+        gw = torch.empty(C, dtype=torch.float32, device=x.device) if weight is not None else None
+        gb = torch.empty(C, dtype=torch.float32, device=x.device) if bias is not None else None
+        ws, counter = _bn_ws(ctx.bn, C, x.device)
+        sums = torch.empty(2 * C, dtype=torch.float64, device=x.device)
+        lib = L.load()
+        with torch.cuda.device_of(x):
+            L.check(lib.alignq_bn_act_sync_bwd_reduce(
+                x.data_ptr(), L.ptr(y), gy.data_ptr(), rows, C, L.ptr(weight), L.ptr(bias), mean.data_ptr(), invstd.data_ptr(),
+                a_bit, act_range, variant, int(relu), sums.data_ptr(), L.ptr(gw), L.ptr(gb), ws.data_ptr(), counter.data_ptr(),
+                L.stream_ptr()), "alignq_bn_act_sync_bwd_reduce")
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=ctx.group)
+            L.check(lib.alignq_bn_act_sync_bwd_apply(
+                x.data_ptr(), L.ptr(y), gy.data_ptr(), rows, rows_global, C, L.ptr(weight), L.ptr(bias), mean.data_ptr(),
+                invstd.data_ptr(), a_bit, act_range, variant, int(relu), sums.data_ptr(), gx.data_ptr(), L.ptr(gr),
+                ws.data_ptr(), L.stream_ptr()), "alignq_bn_act_sync_bwd_apply")
+        return gx, gw, gb, None, None, None, None, None, gr, None, None
+
+
+def _sync_world():
+    """(group, world) of the data-parallel SyncBN mode, or (None, 1)."""
+    if not args.sync_bn:
+        return None, 1
+    from ..utils import dp_gram
+    return dp_gram._state["group"], dp_gram.world()
+
+
 def can_fuse(bn, actq, x) -> bool:
     return (bool(args.fuse_bn_act) and type(bn) is nn.BatchNorm2d and bn.momentum is not None
             and (bn.training or bn.running_mean is not None)
@@ -85,6 +151,10 @@ def bn_act(bn, actq, x, relu: bool, residual=None):
     if can_fuse(bn, actq, x) and (residual is None or (residual.shape == x.shape and residual.stride() == x.stride()
                                                        and residual.dtype == torch.float32
                                                        and residual.data_ptr() % 16 == 0)):
+        group, world = _sync_world()
+        if world > 1 and bn.training:                      # global-batch statistics, still the fused kernels
+            return _SyncBnActFn.apply(x, bn.weight, bn.bias, bn, actq.a_bit, float(args.act_range),
+                                      L.VARIANT_ID[actq.variant], relu, residual, group, world)
         return _BnActFn.apply(x, bn.weight, bn.bias, bn, actq.a_bit, float(args.act_range),
                               L.VARIANT_ID[actq.variant], relu, residual)
     y = actq(bn(x))

@@ -335,6 +335,11 @@ class activation_quantize_fn(nn.Module):
             return (x, 0) if tuple_out else x
         if tuple_out and args.method == "ours" and self.a_bit < 32:   # QB:112-123
             eps = 0.0 if self.variant == "B" else 1e-5
+            if args.dp_gram == "feature":
+                from ..utils import dp_gram
+                if dp_gram.world() > 1:                # global-batch Gram over the ranks' feature slices
+                    return dp_gram.feature_sharded_act_admm(x, self.opt, self.a_bit, float(args.act_range), eps,
+                                                            L.GRAM_MODE_ID[args.gram_mode], L.VARIANT_ID[self.variant])
             y, loss, D = _ActAdmmFn.apply(x, self.opt.alterD, self.opt.gamma, self.a_bit, float(args.act_range),
                                           eps, float(self.opt.mu), float(self.opt.rho),
                                           L.GRAM_MODE_ID[args.gram_mode], L.VARIANT_ID[self.variant],

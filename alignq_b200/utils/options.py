@@ -12,7 +12,11 @@ variants the math follows ('A' = cdf_alignment/*, 'B' = cdf_alignment_admm/resne
 ('fp32' FFMA parity mode, 'tf32x3' / 'bf16' tcgen05 modes); ``fuse_bn_act`` lets the model files run
 BatchNorm -> activation quantizer -> ReLU as one fused kernel pair on channels_last inputs;
 ``admm_param_grads=False`` skips d trans_loss / d(alterD, gamma), which ``ADMM_OPT`` never reads
-(it applies closed-form Z/U updates, optimizer.py:97-124).
+(it applies closed-form Z/U updates, optimizer.py:97-124).  Data-parallel (one process per GPU): ``dp_gram``
+= 'replica' (every rank its own [b, b] Gram and ADMM(b): the reference at train_batch_size = b) or 'feature'
+(global-batch Gram: all-to-all to feature slices, partial sums, one all-reduce -- utils/dp_gram.py);
+``sync_bn`` makes the fused BatchNorm -> act-quant kernels all-reduce their fp64 (sum, sum of squares)
+accumulators so the batch statistics are those of the global batch (model/fused.py).
 """
 from __future__ import annotations
 
@@ -23,6 +27,7 @@ _DEFAULTS = dict(
     gpus=[0], bitW=2, abitW=2, act_range=2, lam=1.0, lam2=4.0, method="ours", stage="second",
     train_batch_size=128, eval_batch_size=100, lr=0.04, momentum=0.9, weight_decay=1e-4,
     variant="A", gram_mode="fp32", store_weight_attrs=True, fuse_bn_act=False, admm_param_grads=True,
+    dp_gram="replica", sync_bn=False,
 )
 
 args = SimpleNamespace(**_DEFAULTS)
@@ -37,6 +42,8 @@ def set_args(**kw):
             raise ValueError("variant must be 'A', 'B' or 'C'")
         if k == "gram_mode" and v not in ("fp32", "tf32x3", "bf16"):
             raise ValueError("gram_mode must be 'fp32', 'tf32x3' or 'bf16'")
+        if k == "dp_gram" and v not in ("replica", "feature"):
+            raise ValueError("dp_gram must be 'replica' (per-rank [b,b] Gram) or 'feature' (global-batch Gram)")
         setattr(args, k, v)
     return args
 

@@ -119,6 +119,10 @@ class QATStep:
             out = self.model(x)
             logits, trans_loss = out if isinstance(out, tuple) else (out, None)
             ce = F.cross_entropy(logits, t)
+        if torch.is_tensor(trans_loss) and self.world > 1 and args.dp_gram == "feature":
+            # global-batch trans_loss is the SAME scalar on every rank and each rank holds the gradient of its own
+            # rows only: the mean over ranks (grad_scale = 1/world below) must see it world times
+            trans_loss = trans_loss * float(self.world)
         if torch.is_tensor(trans_loss) and self.single_backward:
             self._backward(ce + trans_loss + self.offset)
         elif torch.is_tensor(trans_loss):

@@ -126,6 +126,21 @@ int alignq_act_admm_bwd(const float* x, const float* gy, const float* dLdD, cons
                         int B, int64_t F, int a_bit, float act_range, float eps, float* gx,
                         void* ws, size_t ws_bytes, int gram_mode, alignq_stream_t stream);
 
+/* ---- data-parallel (feature-sharded) pieces of the same term ------------------------------------
+ * With the batch sharded over P GPUs the Gram is [B_global, B_global] ACROSS samples: every rank receives
+ * (all-to-all) all B_global rows of its slice of the feature columns and computes the UN-NORMALISED column sums
+ *   sums[0] = sum_f Xs Xs^T,  sums[1] = sum_f Ts Ts^T      (Xs, Ts standardised over all B_global rows: exact)
+ * (alignq_gram_sums_fwd); the sums of all ranks are added with ONE all-reduce (NCCL), then
+ * alignq_gram_sums_to_d forms D = sums[1]/F - sums[0]/F with the single-device rounding (QB:118-122) for nmod
+ * modules at once (inv_f: DEVICE array of 1/F per module), and alignq_admm_loss evaluates ADMM.forward.
+ * Backward: alignq_act_admm_bwd on the slice with gy = NULL and *gloss / P, all-to-all back, and
+ * alignq_act_bwd_add adds the straight-through term: gx = gadd + gy * 2 ar phi(x).                  */
+int alignq_gram_sums_fwd(const float* x, int B, int64_t F, float act_range, float eps, float* sums, void* ws,
+                         size_t ws_bytes, int gram_mode, alignq_stream_t stream);
+int alignq_gram_sums_to_d(const float* sums, const float* inv_f, int B, int nmod, float* D, alignq_stream_t stream);
+int alignq_act_bwd_add(const float* x, const float* gy, const float* gadd, float* gx, int64_t numel, int a_bit,
+                       float act_range, int variant, int return_cdf, alignq_stream_t stream);
+
 /* ---- ADMM loss and Z/U update (batched over nmod modules) ------------------------------------
  * ADMM.forward (ADMM:24-33): loss = mu mean|Z| + rho/2 sqrt(mean (D-Z)^2) + mean(U |D-Z|), and
  * dLdD.  Module m uses D + m*B*B, Z + m*dim*dim, U + m*dim*dim, loss[m],
@@ -197,6 +212,28 @@ int alignq_bn_act_bwd(const float* x, const float* y, const float* gy, int64_t r
                       int training, int a_bit, float act_range, int variant, int relu, float* gx,
                       float* g_residual, float* ggamma, float* gbeta, double* ws, uint32_t* counter,
                       alignq_stream_t stream);
+
+/* Data-parallel SyncBN inside the fused kernels (BASELINE.json north_star (3): "(sum, sum-of-squares) ... combined with
+ * NCCL all-reduce ... so global statistics match the single-device reference"): the same kernels, cut where the ranks'
+ * fp64 sums are exchanged.  The caller all-reduces `sums` ([2 C] doubles: per-channel sum and sum of squares forward;
+ * sum g_z and sum g_z xhat backward) between the two calls of a pass; rows_global = rows summed over the ranks.
+ * ggamma / gbeta are the LOCAL sums (they are averaged with the other parameter gradients).  Training mode only. */
+int alignq_bn_act_sync_stats(const float* x, int64_t rows, int C, double* sums, double* ws, uint32_t* counter,
+                             alignq_stream_t stream);
+int alignq_bn_act_sync_apply(const float* x, int64_t rows, int64_t rows_global, int C, const double* sums,
+                             const float* gamma, const float* beta, float* running_mean, float* running_var,
+                             float momentum, float bn_eps, int a_bit, float act_range, int variant, int relu,
+                             const float* residual, float* y, float* save_mean, float* save_invstd,
+                             int64_t* num_batches_tracked, alignq_stream_t stream);
+int alignq_bn_act_sync_bwd_reduce(const float* x, const float* y, const float* gy, int64_t rows, int C,
+                                  const float* gamma, const float* beta, const float* save_mean,
+                                  const float* save_invstd, int a_bit, float act_range, int variant, int relu,
+                                  double* sums, float* ggamma, float* gbeta, double* ws, uint32_t* counter,
+                                  alignq_stream_t stream);
+int alignq_bn_act_sync_bwd_apply(const float* x, const float* y, const float* gy, int64_t rows, int64_t rows_global,
+                                 int C, const float* gamma, const float* beta, const float* save_mean,
+                                 const float* save_invstd, int a_bit, float act_range, int variant, int relu,
+                                 const double* sums, float* gx, float* g_residual, double* ws, alignq_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -162,3 +162,81 @@ def test_fused_bn_act_with_residual(relu):
     close5(x.grad * same, xr.grad * same, "gx")
     close5(r.grad * same, rr.grad * same, "g residual")
     assert rel(bn.weight.grad, bn_ref.weight.grad) <= 1e-4
+
+
+@pytest.mark.parametrize("P,shape,relu,res", [(2, (64, 16, 16, 16), True, False), (4, (32, 64, 8, 8), True, True),
+                                               (2, (16, 24, 5, 7), False, False)])
+def test_sync_bn_entries_compose_to_the_single_device_kernels(P, shape, relu, res):
+    """Data-parallel SyncBN inside the fused kernels (alignq_bn_act_sync_*): P ranks' row shards are run one after the
+    other on ONE device, the all-reduce of the fp64 sums is a plain addition, and the result must equal the
+    single-device fused kernels on the whole batch (same global statistics; +-1 code only at BN-output ties)."""
+    from alignq_b200 import _lib as L
+    from alignq_b200.model.fused import _bn_ws
+    torch.manual_seed(7)
+    aq.set_args(variant="A", act_range=2, abitW=8, fuse_bn_act=True, method="none")
+    lib = L.load()
+    cl = lambda t_: t_.contiguous(memory_format=torch.channels_last)
+    B, C, H, W = shape
+    x0, gy = cl(torch.randn(shape, device=DEV) * 1.4 + 0.2), cl(torch.randn(shape, device=DEV))
+    r0 = cl(torch.randn(shape, device=DEV)) if res else None
+    bn = nn.BatchNorm2d(C).to(DEV).train()
+    with torch.no_grad():
+        bn.weight.copy_(1 + 0.2 * torch.randn(C))
+        bn.bias.copy_(0.1 * torch.randn(C))
+    bn_s = copy.deepcopy(bn)
+    actq = aq.activation_quantize_fn(8, "second")
+    x = x0.clone().requires_grad_(True)
+    rr = r0.clone().requires_grad_(True) if res else None
+    y = bn_act(bn, actq, x, relu, residual=rr)
+    (y * gy).sum().backward()
+    # the same through the sync entries, shard by shard
+    b = B // P
+    rows, rows_g = b * H * W, B * H * W
+    sh = lambda t_, r: cl(t_[r * b:(r + 1) * b])
+    xs, gys = [sh(x0, r) for r in range(P)], [sh(gy, r) for r in range(P)]
+    rs = [sh(r0, r) for r in range(P)] if res else [None] * P
+    ws, counter = _bn_ws(bn_s, C, x0.device)
+    st = L.stream_ptr()
+    sums = []
+    for r in range(P):
+        s_ = torch.empty(2 * C, dtype=torch.float64, device=DEV)
+        L.check(lib.alignq_bn_act_sync_stats(xs[r].data_ptr(), rows, C, s_.data_ptr(), ws.data_ptr(), counter.data_ptr(), st), "stats")
+        sums.append(s_)
+    tot = torch.stack(sums).sum(0)                                                        # the all-reduce
+    ys, means, invs = [], [], []
+    for r in range(P):
+        yr = torch.empty_like(xs[r])
+        m, iv = torch.empty(C, device=DEV), torch.empty(C, device=DEV)
+        rm, rv = bn_s.running_mean.clone(), bn_s.running_var.clone()                      # every rank updates its own copy
+        L.check(lib.alignq_bn_act_sync_apply(xs[r].data_ptr(), rows, rows_g, C, tot.data_ptr(), bn_s.weight.data_ptr(),
+                                             bn_s.bias.data_ptr(), rm.data_ptr(), rv.data_ptr(), float(bn_s.momentum),
+                                             float(bn_s.eps), 8, 2.0, 0, int(relu), L.ptr(rs[r]), yr.data_ptr(), m.data_ptr(),
+                                             iv.data_ptr(), 0, st), "apply")
+        ys.append(yr); means.append(m); invs.append(iv)
+    ysync = torch.cat(ys)
+    assert int(((ysync - y.detach()).abs() > 1e-6).sum()) <= tie_budget(y.numel())
+    assert torch.allclose(rm, bn.running_mean, rtol=1e-6, atol=1e-7) and torch.allclose(rv, bn.running_var, rtol=1e-6, atol=1e-7)
+    bsums, gws, gbs = [], [], []
+    for r in range(P):
+        s_ = torch.empty(2 * C, dtype=torch.float64, device=DEV)
+        gw, gb = torch.empty(C, device=DEV), torch.empty(C, device=DEV)
+        L.check(lib.alignq_bn_act_sync_bwd_reduce(xs[r].data_ptr(), ys[r].data_ptr(), gys[r].data_ptr(), rows, C,
+                                                  bn_s.weight.data_ptr(), bn_s.bias.data_ptr(), means[r].data_ptr(),
+                                                  invs[r].data_ptr(), 8, 2.0, 0, int(relu), s_.data_ptr(), gw.data_ptr(),
+                                                  gb.data_ptr(), ws.data_ptr(), counter.data_ptr(), st), "bwd_reduce")
+        bsums.append(s_); gws.append(gw); gbs.append(gb)
+    btot = torch.stack(bsums).sum(0)
+    gxs, grs = [], []
+    for r in range(P):
+        gx = torch.empty_like(xs[r])
+        gr = torch.empty_like(xs[r]) if res else None
+        L.check(lib.alignq_bn_act_sync_bwd_apply(xs[r].data_ptr(), ys[r].data_ptr(), gys[r].data_ptr(), rows, rows_g, C,
+                                                 bn_s.weight.data_ptr(), bn_s.bias.data_ptr(), means[r].data_ptr(),
+                                                 invs[r].data_ptr(), 8, 2.0, 0, int(relu), btot.data_ptr(), gx.data_ptr(),
+                                                 L.ptr(gr), ws.data_ptr(), st), "bwd_apply")
+        gxs.append(gx); grs.append(gr)
+    same = (ysync - y.detach()).abs() <= 1e-6
+    close5(torch.cat(gxs) * same, x.grad * same, "sync gx")
+    assert rel(torch.stack(gws).sum(0), bn.weight.grad) <= 1e-5 and rel(torch.stack(gbs).sum(0), bn.bias.grad) <= 1e-5
+    if res:
+        close5(torch.cat(grs) * same, rr.grad * same, "sync g residual")

@@ -1,9 +1,6 @@
 """CPU, world_size = 2 over gloo: the host-side data-parallel logic (batch / feature sharding, the
 gradient all-reduce over the flat buffer, (sum, sumsq) statistics, feature-sharded Gram partials).
 The local compute in these tests is the oracle (CPU); on the box the same helpers wrap the kernels."""
-import os
-import socket
-
 import pytest
 import torch
 import torch.distributed as dist
@@ -12,28 +9,7 @@ import torch.multiprocessing as mp
 from alignq_b200.utils import sharding as S
 
 
-def _free_port():
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    p = s.getsockname()[1]
-    s.close()
-    return p
-
-
-def _worker(rank, world, port, fn, ret):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    try:
-        ret[rank] = fn(rank, world)
-    finally:
-        dist.destroy_process_group()
-
-
-def run2(fn, world=2):
-    mgr = mp.Manager()
-    ret = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), fn, ret), nprocs=world, join=True)
-    return [ret[r] for r in range(world)]
+from _dist_util import run2
 
 
 def _grad_exchange(rank, world):

@@ -64,6 +64,9 @@ SIGNATURES = {
     "alignq_bn_act_sync_apply": (_I, [_P, _L, _L, _I, _P, _P, _P, _P, _P, _F, _F, _I, _F, _I, _I, _P, _P, _P, _P, _P, _P]),
     "alignq_bn_act_sync_bwd_reduce": (_I, [_P, _P, _P, _L, _I, _P, _P, _P, _P, _I, _F, _I, _I, _P, _P, _P, _P, _P, _P]),
     "alignq_bn_act_sync_bwd_apply": (_I, [_P, _P, _P, _L, _L, _I, _P, _P, _P, _P, _I, _F, _I, _I, _P, _P, _P, _P, _P]),
+    "alignq_bn_act_peer_bytes": (_Z, []),
+    "alignq_bn_act_fwd_peer": (_I, [_P, _L, _L, _I, _P, _P, _P, _P, _F, _F, _I, _F, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
+    "alignq_bn_act_bwd_peer": (_I, [_P, _P, _P, _L, _L, _I, _P, _P, _P, _P, _I, _F, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "alignq_sgd_step": (_I, [_P, _P, _P, _I, _L, _F, _F, _I, _F, _P]),
 }
 

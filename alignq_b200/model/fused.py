@@ -128,6 +128,78 @@ class _SyncBnActFn(torch.autograd.Function):
         return gx, gw, gb, None, None, None, None, None, gr, None, None
 
 
+class PeerExchange:
+    """Peer-mapped buffers for the in-kernel SyncBN exchange (alignq_bn_act_*_peer): one symmetric-memory allocation
+    per process group, rendezvoused once; the kernels write straight into the other ranks' copies over NVLink."""
+
+    _inst = {}
+
+    def __init__(self, group, device):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = dist.group.WORLD if group is None else group
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        nbytes = int(L.load().alignq_bn_act_peer_bytes())
+        self.buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, self.group)
+        self.buf.zero_()
+        self.seq = torch.zeros(2, dtype=torch.int32, device=device)   # exchange counter (+ one spare word)
+        self.ptrs_dev = int(self.hdl.buffer_ptrs_dev)
+        torch.cuda.synchronize(device)
+        dist.barrier(group=self.group)                    # every rank's buffer is zero before anyone publishes
+
+    @classmethod
+    def get(cls, group, device):
+        key = (id(group), device.index)
+        if key not in cls._inst:
+            cls._inst[key] = cls(group, device)
+        return cls._inst[key]
+
+
+class _PeerBnActFn(torch.autograd.Function):
+    """Global-batch BatchNorm statistics with the exchange inside the kernels (NVLink peer stores + flags): still two
+    launches forward and two backward, no NCCL call on the path."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, bn, a_bit, act_range, variant, relu, residual, peer):
+        B, C, H, W = x.shape
+        rows = B * H * W
+        rows_global = rows * peer.world
+        y = torch.empty_like(x)
+        mean = torch.empty(C, dtype=torch.float32, device=x.device)
+        invstd = torch.empty(C, dtype=torch.float32, device=x.device)
+        ws, counter = _bn_ws(bn, C, x.device)
+        with torch.cuda.device_of(x):
+            L.check(L.load().alignq_bn_act_fwd_peer(
+                x.data_ptr(), rows, rows_global, C, L.ptr(weight), L.ptr(bias), L.ptr(bn.running_mean), L.ptr(bn.running_var),
+                float(bn.momentum), float(bn.eps), a_bit, act_range, variant, int(relu), L.ptr(residual), y.data_ptr(),
+                mean.data_ptr(), invstd.data_ptr(), ws.data_ptr(), counter.data_ptr(), L.ptr(bn.num_batches_tracked),
+                peer.ptrs_dev, peer.seq.data_ptr(), peer.rank, peer.world, L.stream_ptr()), "alignq_bn_act_fwd_peer")
+        ctx.bn, ctx.peer = bn, peer
+        ctx.save_for_backward(x, y if relu else None, weight, bias, mean, invstd)
+        ctx.cfg = (rows, rows_global, C, a_bit, act_range, variant, relu, residual is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, y, weight, bias, mean, invstd = ctx.saved_tensors
+        rows, rows_global, C, a_bit, act_range, variant, relu, has_res = ctx.cfg
+        peer = ctx.peer
+        gy = L.like_layout(gy, x, "grad of fused bn-act output")
+        gx = torch.empty_like(x)
+        gr = torch.empty_like(x) if (has_res and ctx.needs_input_grad[8]) else None
+        gw = torch.empty(C, dtype=torch.float32, device=x.device) if weight is not None else None
+        gb = torch.empty(C, dtype=torch.float32, device=x.device) if bias is not None else None
+        ws, counter = _bn_ws(ctx.bn, C, x.device)
+        with torch.cuda.device_of(x):
+            L.check(L.load().alignq_bn_act_bwd_peer(
+                x.data_ptr(), L.ptr(y), gy.data_ptr(), rows, rows_global, C, L.ptr(weight), L.ptr(bias), mean.data_ptr(),
+                invstd.data_ptr(), a_bit, act_range, variant, int(relu), gx.data_ptr(), L.ptr(gr), L.ptr(gw), L.ptr(gb),
+                ws.data_ptr(), counter.data_ptr(), peer.ptrs_dev, peer.seq.data_ptr(), peer.rank, peer.world, L.stream_ptr()),
+                "alignq_bn_act_bwd_peer")
+        return gx, gw, gb, None, None, None, None, None, gr, None
+
+
 def _sync_world():
     """(group, world) of the data-parallel SyncBN mode, or (None, 1)."""
     if not args.sync_bn:
@@ -152,7 +224,11 @@ def bn_act(bn, actq, x, relu: bool, residual=None):
                                                        and residual.dtype == torch.float32
                                                        and residual.data_ptr() % 16 == 0)):
         group, world = _sync_world()
-        if world > 1 and bn.training:                      # global-batch statistics, still the fused kernels
+        if world > 1 and bn.training and args.sync_bn == "peer" and world <= 8:
+            # global-batch statistics exchanged inside the kernels over NVLink peer memory
+            return _PeerBnActFn.apply(x, bn.weight, bn.bias, bn, actq.a_bit, float(args.act_range),
+                                      L.VARIANT_ID[actq.variant], relu, residual, PeerExchange.get(group, x.device))
+        if world > 1 and bn.training:                      # global-batch statistics through an NCCL all-reduce
             return _SyncBnActFn.apply(x, bn.weight, bn.bias, bn, actq.a_bit, float(args.act_range),
                                       L.VARIANT_ID[actq.variant], relu, residual, group, world)
         return _BnActFn.apply(x, bn.weight, bn.bias, bn, actq.a_bit, float(args.act_range),

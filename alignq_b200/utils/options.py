@@ -15,8 +15,9 @@ BatchNorm -> activation quantizer -> ReLU as one fused kernel pair on channels_l
 (it applies closed-form Z/U updates, optimizer.py:97-124).  Data-parallel (one process per GPU): ``dp_gram``
 = 'replica' (every rank its own [b, b] Gram and ADMM(b): the reference at train_batch_size = b) or 'feature'
 (global-batch Gram: all-to-all to feature slices, partial sums, one all-reduce -- utils/dp_gram.py);
-``sync_bn`` makes the fused BatchNorm -> act-quant kernels all-reduce their fp64 (sum, sum of squares)
-accumulators so the batch statistics are those of the global batch (model/fused.py).
+``sync_bn`` (False | True / "nccl" | "peer") gives the fused BatchNorm -> act-quant kernels the batch statistics of
+the GLOBAL batch: their fp64 (sum, sum of squares) accumulators are all-reduced with NCCL between the two launches,
+or -- "peer" -- exchanged inside the kernels through NVLink peer-mapped memory (model/fused.py).
 """
 from __future__ import annotations
 

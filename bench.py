@@ -142,6 +142,99 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def dp_parity_block(args, world, rank, dev, make_model, batch, img_hw, ncls, fuse):
+    """N ranks vs ONE device on the same global batch: every rank runs forward + backward on its shard
+    with the global-batch modes on (fused-kernel SyncBN; dp_gram as requested), gradients are summed over ranks and
+    divided by N; then every rank runs the SAME model on the gathered global batch alone and compares.  Relative errors
+    of the loss, trans_loss, the first ADMM layer's D and the flat parameter gradient.  (Quantisation is discrete: a BN
+    output on a rounding tie may flip a code between the two runs; see DESIGN.md 2 for the bands.)"""
+    import torch
+    import torch.distributed as dist
+    import torch.nn.functional as F_
+    import alignq_b200 as aq
+    from alignq_b200.utils.admm import ADMM
+    fmt = torch.contiguous_format if args.nchw else torch.channels_last
+    g = torch.Generator().manual_seed(777 + rank)
+    x = torch.randn(batch, 3, img_hw, img_hw, generator=g).to(dev).contiguous(memory_format=fmt)
+    t = torch.randint(0, ncls, (batch,), generator=g).to(dev)
+    xs = [torch.empty_like(x) for _ in range(world)]
+    ts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(xs, x)
+    dist.all_gather(ts, t)
+    xg, tg = torch.cat(xs).contiguous(memory_format=fmt), torch.cat(ts)
+    saved = {k: getattr(aq.args, k) for k in ("sync_bn", "dp_gram", "train_batch_size", "fuse_bn_act")}
+    # heuristic (not auto-tuned) fp32 convolutions for both passes: with cudnn.benchmark the two batch sizes may get
+    # different algorithms, whose last-bit differences the 21 quantized layers amplify (the 1e-7 band below)
+    saved_backend = (torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = False, False, False
+    feature = args.dp_gram == "feature"
+    out = {}
+
+    def run(model, xx, tt, tl_scale):
+        for p in model.parameters():
+            p.grad = None
+        o = model(xx)
+        logits, tl = o if isinstance(o, tuple) else (o, None)
+        ce = F_.cross_entropy(logits, tt)
+        total = ce if not torch.is_tensor(tl) else ce + tl * tl_scale
+        total.backward()
+        flat = torch.cat([p.grad.reshape(-1) for n, p in model.named_parameters()
+                          if p.grad is not None and "alterD" not in n and "gamma" not in n])
+        D = next((m.D.clone() for m in model.modules() if isinstance(m, ADMM) and getattr(m, "D", None) is not None), None)
+        return ce.detach(), (tl.detach() if torch.is_tensor(tl) else None), D, flat
+
+    # N-rank pass
+    aq.set_args(sync_bn=args.sync_bn_impl, dp_gram=args.dp_gram, fuse_bn_act=fuse, train_batch_size=(batch * world if feature else batch))
+    torch.manual_seed(0)
+    m_dp = make_model().to(dev).train()
+    if not fuse_effective(args, fuse):
+        m_dp = torch.nn.SyncBatchNorm.convert_sync_batchnorm(m_dp)
+    if fmt is torch.channels_last:
+        m_dp = m_dp.to(memory_format=torch.channels_last)
+    ce, tl, D, flat = run(m_dp, x, t, float(world) if feature else 1.0)
+    dist.all_reduce(flat)
+    flat /= world
+    cem = ce.clone()
+    dist.all_reduce(cem)
+    cem /= world
+    # single-device pass on the gathered global batch (only meaningful for the global-batch modes)
+    aq.set_args(sync_bn=False, dp_gram="replica", train_batch_size=(batch * world if feature else batch))
+    torch.manual_seed(0)
+    m_sd = make_model().to(dev).train()
+    if fmt is torch.channels_last:
+        m_sd = m_sd.to(memory_format=torch.channels_last)
+    has_admm = any(isinstance(m, ADMM) for m in m_sd.modules())
+    if has_admm and not feature:                            # replica mode: the per-rank [b,b] Gram is NOT the global one
+        out["note"] = "dp_gram=replica: each rank = the reference at batch b; global-batch parity needs --dp-gram feature"
+    else:
+        ce1, tl1, D1, flat1 = run(m_sd, xg, tg, 1.0)
+        rel = lambda a, b: float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+        out.update(ce_rel_err=abs(float(cem) - float(ce1)) / abs(float(ce1)), grad_rel_norm_err=rel(flat, flat1))
+        with torch.no_grad():                               # the model's own sensitivity: the same single-device pass started
+            for p in m_sd.parameters():                     # 1e-7 away (rounding ties of the 21 quantized layers flip)
+                p.mul_(1.0 + 1e-7)
+        ce2, _, _, flat2 = run(m_sd, xg, tg, 1.0)
+        out.update(band_ce_rel_1e7_perturbation=abs(float(ce2) - float(ce1)) / abs(float(ce1)),
+                   band_grad_rel_norm_1e7_perturbation=rel(flat2, flat1))
+        if tl1 is not None:
+            out.update(trans_loss_rel_err=abs(float(tl) - float(tl1)) / abs(float(tl1)),
+                       D_first_layer_err_over_max=float((D - D1).abs().max() / D1.abs().max()))
+    out.update(world=world, per_gpu_batch=batch, global_batch=batch * world,
+               what="N-rank step (global-batch BN statistics%s) vs the same model on the gathered global batch on one GPU"
+                    % (", feature-sharded global Gram" if feature else ""))
+    aq.set_args(**saved)
+    torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved_backend
+    del m_dp, m_sd
+    torch.cuda.empty_cache()
+    return out
+
+
+def fuse_effective(args, fuse):
+    """True when every BatchNorm -> act-quant pair of the workload runs in the fused kernels (which carry their own
+    global-batch statistics exchange); the ADMM workloads and --nchw / --no-fuse use separate modules."""
+    return fuse and args.workload in ("resnet20", "mobilenetv2", "densenet40")
+
+
 def fused_code_mismatch(dev):
     """Fraction of activation codes of the fused BatchNorm -> act-quant -> ReLU kernels that differ (by one level: a BN
     output on a rounding tie) from cuDNN BatchNorm + the stand-alone quantizer kernel, on the three layer shapes of the
@@ -241,12 +334,17 @@ def run_product(args):
                 fuse_bn_act=fuse)
     torch.manual_seed(0)                                   # identical replicas on every rank
     batch, img_hw, ncls, forward_loss = BATCH, 32, 10, None
+    # ADMM(dim): the GLOBAL batch in dp_gram='feature' mode (weak scaling: per-GPU batch x ranks), else the per-GPU batch
+    admm_dim = lambda b: b * world if (args.dp_gram == "feature" and world > 1 and not args.strong) else b
+    make_model = None
     if args.workload == "resnet20":
-        model = resnet20_quant(8, 8, "second")
+        make_model = lambda: resnet20_quant(8, 8, "second")
+        model = make_model()
     elif args.workload == "resnet56_admm":                 # configs[1]: QB, W8A8 + ADMM correlation preservation
         from alignq_b200.model.resnet import resnet56_quant
-        aq.set_args(variant="B", gram_mode=args.gram_mode, fuse_bn_act=False)
-        model = resnet56_quant(8, 8, "second")
+        aq.set_args(variant="B", gram_mode=args.gram_mode, fuse_bn_act=False, train_batch_size=admm_dim(BATCH))
+        make_model = lambda: resnet56_quant(8, 8, "second")
+        model = make_model()
         CONFIG.update(workload=f"resnet56_quant W8A8 (QB) + ADMM, gram_mode={args.gram_mode}, CIFAR-10 synthetic, QAT step", variant="B")
     elif args.workload == "mobilenetv2":                   # configs[2]: W4A4, depthwise convs, batch 256
         from alignq_b200.model.mobilenetV2 import mobile_v2
@@ -257,7 +355,7 @@ def run_product(args):
     elif args.workload == "resnet50_dann":                 # configs[4]: QC, Office-31 shaped 224x224, batch 28 per GPU,
         from alignq_b200.model.dann import resnet50_dann   # source + target forward per iteration (main.py:372-385)
         batch = 28
-        aq.set_args(variant="C", gram_mode=args.gram_mode, fuse_bn_act=False, train_batch_size=batch)
+        aq.set_args(variant="C", gram_mode=args.gram_mode, fuse_bn_act=False, train_batch_size=admm_dim(batch))
         model = resnet50_dann(8, 8, "second")
         CONFIG.update(workload=f"resnet50_dann W8A8 (QC) + ADMM, gram_mode={args.gram_mode}, Office-31 synthetic 224x224, "
                                "source+target forward, QAT step", variant="C", per_gpu_batch=batch)
@@ -278,10 +376,19 @@ def run_product(args):
         if batch % world:
             raise SystemExit(f"--strong: global batch {batch} is not divisible by {world} ranks")
         batch //= world
-        aq.set_args(train_batch_size=batch)
+        if not (args.dp_gram == "feature" and world > 1):  # feature mode keeps ADMM(dim = global batch)
+            aq.set_args(train_batch_size=batch)
         CONFIG.update(per_gpu_batch=batch)
     model = model.to(dev).train()
-    if world > 1 and args.sync_bn:
+    sync_bn = world > 1 and not args.local_bn
+    if world > 1:
+        from alignq_b200.utils import dp_gram
+        dp_gram.configure()                                # process group of the global-batch modes
+        aq.set_args(sync_bn=(args.sync_bn_impl if sync_bn else False), dp_gram=args.dp_gram)
+        if args.dp_gram == "feature":                      # ADMM dim = GLOBAL batch (the model was built with it below)
+            CONFIG.update(dp_gram="feature: global-batch Gram (all-to-all + partial sums + one all-reduce per layer)")
+    if sync_bn and not fuse_effective(args, fuse):
+        # layers the fused bn-act kernels do not cover (ADMM variants, NCHW): torch's SyncBatchNorm
         model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
     step = QATStep(model, lr=0.04, momentum=0.9, weight_decay=1e-4, world_size=world, channels_last=not args.nchw,
                    single_backward=True, forward_loss=forward_loss)
@@ -456,6 +563,13 @@ def run_product(args):
                 except Exception as e:                      # pragma: no cover - a baseline, never fatal
                     cpu["gpu_eager_port"] = {"error": str(e)[:200]}
 
+    dp_parity = None
+    if world > 1 and make_model is not None and not args.no_dp_parity and (sync_bn or args.dp_gram == "feature"):
+        try:
+            dp_parity = dp_parity_block(args, world, rank, dev, make_model, batch, img_hw, ncls, fuse)
+        except Exception as e:                              # pragma: no cover - evidence block, never fatal
+            dp_parity = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+
     fused_parity = no_fuse = None
     if rank == 0 and world == 1 and fuse and args.workload == "resnet20":
         fused_parity = fused_code_mismatch(dev)
@@ -479,14 +593,18 @@ def run_product(args):
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": dict(CONFIG, global_batch=batch * world, parallelism=f"dp{world}", cuda_graph=graphed,
                                activation_layout="nchw" if args.nchw else "channels_last", fused_bn_act=fuse,
-                               sync_bn=bool(args.sync_bn and world > 1),
+                               sync_bn=bool(sync_bn),
+                               sync_bn_impl=(None if not sync_bn else (
+                                   ("fused bn-act kernels, fp64 (sum, sumsq) exchanged inside the kernels over NVLink peer memory"
+                                    if args.sync_bn_impl == "peer" else "fused bn-act kernels, fp64 (sum, sumsq) NCCL all-reduce")
+                                   if fuse_effective(args, fuse) else "torch.nn.SyncBatchNorm")),
                                l2="flushed between timed steps (256 MiB memset, outside the event pairs)"),
                 "e2e": {"value": e2e, "unit": "img/s", "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": nimg * 3 * img_hw * img_hw * 4 + batch * 8, "d2h_bytes_per_step": 4},
                 "gpu_launches": int(launches_per_step) * args.steps,
                 "gpu_launches_per_step": int(launches_per_step),
                 "clocks": clocks, "roofline": roofline, "gram_tensor_roofline": gram, "cpu_baseline": cpu,
-                "fused_bn_act_parity": fused_parity, "no_fuse": no_fuse}
+                "fused_bn_act_parity": fused_parity, "no_fuse": no_fuse, "dp_parity": dp_parity}
         print(json.dumps(line), flush=True)
     if world > 1:
         # Tear down without NCCL's communicator destructor: with captured NCCL kernels still referenced
@@ -512,8 +630,16 @@ def main():
     ap.add_argument("--strong", action="store_true", help="strong scaling: the GLOBAL batch stays 128 (per-GPU batch 128/N); "
                     "default is weak scaling (per-GPU batch 128)")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying a CUDA graph")
-    ap.add_argument("--sync-bn", action="store_true", help="N>1: SyncBatchNorm (global-batch BN statistics)")
+    ap.add_argument("--sync-bn", action="store_true", help="(default for N>1) global-batch BatchNorm statistics")
+    ap.add_argument("--sync-bn-impl", type=str, default="peer", choices=["peer", "nccl"],
+                    help="how the fused bn-act kernels exchange their global-batch sums: inside the kernels over NVLink peer "
+                    "memory (default) or with an NCCL all-reduce between the launches")
+    ap.add_argument("--local-bn", action="store_true", help="N>1: per-rank BatchNorm statistics (plain DDP semantics) "
+                    "instead of the default global-batch statistics")
+    ap.add_argument("--dp-gram", type=str, default="replica", choices=["replica", "feature"],
+                    help="N>1, ADMM workloads: per-rank [b,b] Gram (reference at batch b) or the global-batch Gram")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dp-parity", action="store_true", help="N>1: skip the N-rank vs single-device parity block")
     ap.add_argument("--no-fuse", action="store_true", help="run BatchNorm / quantizer / ReLU as separate kernels "
                     "(default with channels_last: the fused bn->act-quant->relu kernels, SURVEY 8f-1)")
     ap.add_argument("--nchw", action="store_true", help="keep activations NCHW-contiguous (default: channels_last, "

@@ -235,6 +235,28 @@ int alignq_bn_act_sync_bwd_apply(const float* x, const float* y, const float* gy
                                  const float* save_invstd, int a_bit, float act_range, int variant, int relu,
                                  const double* sums, float* gx, float* g_residual, double* ws, alignq_stream_t stream);
 
+/* The same exchange done INSIDE the kernels over NVLink peer memory -- no collective call, no extra launch: the last
+ * block of the statistics (backward: reduce) kernel stores this rank's [2 C] fp64 sums into every rank's peer-mapped
+ * buffer and releases a flag; every block of the apply kernel that follows waits for all ranks' flags in its own
+ * buffer and adds the world's sums in rank order (bit-identical on every rank).
+ * peer_bufs: DEVICE array of `world` (<= 8) base pointers, entry r = rank r's buffer of alignq_bn_act_peer_bytes()
+ * bytes, zero-initialised, mapped into this process (e.g. torch symmetric memory); peer_seq: TWO zero-initialised
+ * uint32 in local device memory (the exchange counter, advanced by the kernels: CUDA-graph replayable; and the word
+ * on which the blocks of a consumer kernel wait for its block 0).  Every rank
+ * must issue the same sequence of peer calls on ONE stream.  C <= 1024; rows_global = rows summed over the ranks.  */
+size_t alignq_bn_act_peer_bytes(void);
+int alignq_bn_act_fwd_peer(const float* x, int64_t rows, int64_t rows_global, int C, const float* gamma,
+                           const float* beta, float* running_mean, float* running_var, float momentum, float bn_eps,
+                           int a_bit, float act_range, int variant, int relu, const float* residual, float* y,
+                           float* save_mean, float* save_invstd, double* ws, uint32_t* counter,
+                           int64_t* num_batches_tracked, const void* const* peer_bufs, uint32_t* peer_seq, int rank,
+                           int world, alignq_stream_t stream);
+int alignq_bn_act_bwd_peer(const float* x, const float* y, const float* gy, int64_t rows, int64_t rows_global, int C,
+                           const float* gamma, const float* beta, const float* save_mean, const float* save_invstd,
+                           int a_bit, float act_range, int variant, int relu, float* gx, float* g_residual,
+                           float* ggamma, float* gbeta, double* ws, uint32_t* counter, const void* const* peer_bufs,
+                           uint32_t* peer_seq, int rank, int world, alignq_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

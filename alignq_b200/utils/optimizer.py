@@ -45,6 +45,27 @@ class SGD(Optimizer):
             group.setdefault("nesterov", False)
         self._table_key = None
 
+    def state_dict(self):
+        """The reference's checkpoint format (``'optimizer_t': optimizer_t.state_dict()``, main.py:143): per-parameter
+        state is exactly ``{'momentum_buffer': tensor}``.  The bookkeeping flag of this implementation is dropped,
+        and a buffer that was allocated but never written (no step yet) is not saved at all."""
+        sd = super().state_dict()
+        state = {}
+        for k, st in sd["state"].items():
+            if st.get("alignq_first", False):
+                continue
+            state[k] = {n: v for n, v in st.items() if n != "alignq_first"}
+        sd["state"] = state
+        return sd
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        for st in self.state.values():                     # buffers from a checkpoint are initialised
+            if "momentum_buffer" in st:
+                st["alignq_first"] = False
+                st["momentum_buffer"] = st["momentum_buffer"].contiguous() if not L.is_dense(st["momentum_buffer"]) else st["momentum_buffer"]
+        self._table_key = None
+
     def _entries(self, idx, w_cdf, w_pdf):
         idx = list(idx) if idx is not None else []
         use_sur = args.bitW < 32

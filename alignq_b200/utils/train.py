@@ -3,9 +3,10 @@ drop-in modules (cdf_alignment/resnet-20-cifar-10/main.py:269-313; cdf_alignment
 resnet-56-cifar-10/main.py:286-379), B200-first:
 
   * ``zero_grad`` is ``p.grad = None`` (autograd hands over its buffers, no accumulate kernels); the
-    data-parallel exchange gathers the gradients into ONE flat fp32 buffer (physical order), runs ONE
-    NCCL all-reduce and re-points every ``p.grad`` at its slice; the 1/world mean is folded into the
-    multi-tensor SGD kernel, which reads everything through a device pointer table;
+    data-parallel exchange all-reduces the weight bank's flat gradient buffer in place and gathers only the
+    few small remaining gradients into a second flat buffer (two NCCL all-reduces per step, no copy of the
+    weights' gradients); the 1/world mean is folded into the multi-tensor SGD kernel, which reads everything
+    through a device pointer table;
   * the whole iteration (forward, both backward passes, SGD.step, ADMM_OPT.step) can be captured
     in a CUDA graph and replayed: ResNet-20 at batch 128 is launch-bound, not bandwidth-bound
     (SURVEY.md 7.3), so replay removes the Python + launch overhead of ~600 small kernels.
@@ -68,7 +69,7 @@ class QATStep:
 
     def __init__(self, model, lr=0.04, momentum=0.9, weight_decay=1e-4, lam=None, lam2=None,
                  trans_loss_offset=0.5, process_group=None, world_size=1, bank_weights=True,
-                 channels_last=False, fast_admm=True, single_backward=False, forward_loss=None):
+                 channels_last=False, fast_admm=True, single_backward=False, forward_loss=None, keep_logits=False):
         self.model = model
         if channels_last:                      # NHWC weights: cuDNN needs no layout conversion kernels
             for p in model.parameters():
@@ -98,6 +99,7 @@ class QATStep:
         # optional custom forward: (model, x, t) -> (task_loss, trans_loss | None), e.g. the two DANN passes of
         # cdf_alignment_admm/dann_office/main.py:372-385
         self.forward_loss = forward_loss
+        self.keep_logits, self.logits = keep_logits, None       # the training driver reads the step's logits (accuracy)
         self.pg, self.world = process_group, world_size
         self.all_params = self.params + self.admm_params
         dev = self.params[0].device
@@ -119,6 +121,10 @@ class QATStep:
             out = self.model(x)
             logits, trans_loss = out if isinstance(out, tuple) else (out, None)
             ce = F.cross_entropy(logits, t)
+            if self.keep_logits:
+                if self.logits is None or self.logits.shape != logits.shape:
+                    self.logits = torch.empty_like(logits)
+                self.logits.copy_(logits.detach())
         if torch.is_tensor(trans_loss) and self.world > 1 and args.dp_gram == "feature":
             # global-batch trans_loss is the SAME scalar on every rank and each rank holds the gradient of its own
             # rows only: the mean over ranks (grad_scale = 1/world below) must see it world times
@@ -131,17 +137,25 @@ class QATStep:
         else:
             self._backward(ce)
         scale = 1.0
-        if self.world > 1:                                         # ONE collective per step over NVLink:
+        if self.world > 1:                                         # gradient exchange over NVLink
             owners = [p for p in self.params if p.grad is not None]
+            if self.bank is not None and self.bank.batched_backward:
+                # the weight bank's gradients already ARE one flat buffer (gw_flat; p.grad are views of it): it is
+                # all-reduced in place, and only the few small remaining gradients (BatchNorm, first conv, classifier)
+                # are gathered -- no torch.cat over the model's weights, no re-pointing of their p.grad
+                banked = {id(p) for p, g in zip(self.bank.params, self.bank.gw) if p.grad is g}
+                allreduce_sum_(self.bank.gw_flat, self.pg)
+                owners = [p for p in owners if id(p) not in banked]
             for p in owners:                                       # gather (physical order) -> all-reduce -> views
                 if p.grad.stride() != p.stride():
                     p.grad = torch.empty_like(p).copy_(p.grad)
-            flat = torch.cat([L.phys(p.grad) for p in owners])
-            allreduce_sum_(flat, self.pg)
-            off = 0
-            for p in owners:
-                p.grad = torch.as_strided(flat, p.shape, p.stride(), off)
-                off += p.numel()
+            if owners:
+                flat = torch.cat([L.phys(p.grad) for p in owners])
+                allreduce_sum_(flat, self.pg)
+                off = 0
+                for p in owners:
+                    p.grad = torch.as_strided(flat, p.shape, p.stride(), off)
+                    off += p.numel()
             scale = 1.0 / self.world                               # the mean is folded into the SGD kernel
         idx, w_cdf, w_pdf = collect_sgd_args(self.model, self.params)
         self.opt.step(idx, w_cdf, w_pdf, self.lam, self.lam2, grad_scale=scale)

@@ -3,6 +3,7 @@
 GPU-eager on the same box.  Quantisation is discrete: a weight/activation code that sits on a
 rounding tie may flip between the two paths (cuDNN vs CPU conv summation order, 1-ulp stats), so the
 model-level bars are norm-relative, stated per assert."""
+import json
 import os
 
 import numpy as np
@@ -256,3 +257,50 @@ def test_admm_dual_update_runs_for_ragged_last_batch_and_partial_forward():
     # (see test_training_iterations_vs_oracle_trainer_on_gpu): same band as the other model-level checks
     assert relnorm(res[True][3], res[False][3]) <= 2e-2 and relnorm(res[True][4], res[False][4]) <= 2e-2
     assert relnorm(res[True][5], res[False][5]) <= 2e-2
+
+
+@pytest.mark.parametrize("variant", ["A", "B"])
+def test_driver_trains_checkpoints_and_resumes(variant, tmp_path):
+    """epoch loop + MultiStepLR stepped by epoch number + the reference's checkpoint keys
+    (main.py:125-151; cdf_alignment_admm/.../main.py:138-150) + --resume (main.py:101-113)."""
+    from alignq_b200.utils.driver import Trainer
+    B = 16
+    aq.reset_args()
+    aq.set_args(variant=variant, train_batch_size=B, bitW=8, abitW=8, act_range=2, method="ours", gram_mode="tf32x3")
+    g = torch.Generator().manual_seed(0)
+    train = [(torch.randn(B, 3, 32, 32, generator=g), torch.randint(0, 10, (B,), generator=g)) for _ in range(3)]
+    train.append((torch.randn(11, 3, 32, 32, generator=g), torch.randint(0, 10, (11,), generator=g)))     # ragged last batch
+    # eval batches must not exceed the ADMM dim = train_batch_size (reference quirk, SURVEY.md A.5 #4)
+    test = [(torch.randn(12, 3, 32, 32, generator=g), torch.randint(0, 10, (12,), generator=g)) for _ in range(2)]
+
+    def build():
+        m = resnet.resnet20_quant(8, 8, "second")
+        m.load_state_dict(MO.deterministic_fill(m.state_dict(), seed=21))
+        return m.to(DEV)
+    cfg = dict(job_dir=str(tmp_path / "run"), num_epochs=2, lr=0.04, momentum=0.9, weight_decay=1e-4, lr_decay_steps=[1],
+               lr_gamma=0.1, print_freq=0)
+    tr = Trainer(build(), cfg)
+    hist = tr.fit(train, test)
+    assert [h["lr"] for h in hist] == [0.04, pytest.approx(0.004)]                   # s.step(epoch): decayed AT epoch 1
+    ck1 = torch.load(tmp_path / "run" / "checkpoint" / "model_1.pt", map_location=DEV, weights_only=False)
+    want = {"state_dict_t", "best_prec1", "best_prec5", "optimizer_t", "scheduler_t", "epoch"} | ({"optimizer_admm"} if variant == "B" else set())
+    assert set(ck1) == want and ck1["epoch"] == 1
+    assert (tmp_path / "run" / "checkpoint" / "model_2.pt").exists() and (tmp_path / "run" / "checkpoint" / "model_best.pt").exists()
+    keys = json.load(open(os.path.join(GOLDEN, f"model_keys_resnet20_{variant}.json")))["state_dict"]
+    assert list(ck1["state_dict_t"].keys()) == list(keys)                                  # loadable by the reference's model
+    st0 = ck1["optimizer_t"]["state"]
+    assert all(set(v.keys()) == {"momentum_buffer"} for v in st0.values()) and len(st0) > 0
+    if variant == "B":                                                                # Z/U moved (ragged batch included)
+        fresh = build()
+        assert not torch.equal(ck1["state_dict_t"]["admm0.alterD"], fresh.state_dict()["admm0.alterD"])
+    # resume from epoch 1: identical restored state, then one more epoch at the decayed learning rate
+    tr2 = Trainer(build(), dict(cfg, resume=str(tmp_path / "run" / "checkpoint" / "model_1.pt"), job_dir=str(tmp_path / "run2")))
+    assert tr2.start_epoch == 1 and tr2.best_prec1 == ck1["best_prec1"]
+    sd2 = tr2.model.state_dict()
+    assert all(torch.equal(sd2[k], ck1["state_dict_t"][k]) for k in sd2)
+    p0 = tr2.step.params[0]
+    assert torch.equal(tr2.optimizer_t.state[p0]["momentum_buffer"], list(st0.values())[0]["momentum_buffer"].view_as(p0))
+    hist2 = tr2.fit(train, test)
+    assert len(hist2) == 1 and hist2[0]["epoch"] == 1 and hist2[0]["lr"] == pytest.approx(0.004)
+    # the resumed epoch tracks the uninterrupted one (same data, same restored state; cuDNN wgrad order may differ)
+    assert abs(hist2[0]["train_loss"] - hist[1]["train_loss"]) <= 2e-2 * abs(hist[1]["train_loss"])

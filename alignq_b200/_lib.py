@@ -20,6 +20,7 @@ ABI_VERSION = 1
 CHUNK = 4096
 VARIANT_ID = {"A": 0, "B": 1, "C": 2}
 GRAM_MODE_ID = {"fp32": 0, "tf32x3": 1, "bf16": 2}
+CONV_MODE_ID = {"tf32": 0, "tf32x3": 1}
 
 
 class SgdTensor(C.Structure):
@@ -67,6 +68,10 @@ SIGNATURES = {
     "alignq_bn_act_peer_bytes": (_Z, []),
     "alignq_bn_act_fwd_peer": (_I, [_P, _L, _L, _I, _P, _P, _P, _P, _F, _F, _I, _F, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "alignq_bn_act_bwd_peer": (_I, [_P, _P, _P, _L, _L, _I, _P, _P, _P, _P, _I, _F, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
+    "alignq_conv3x3_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "alignq_conv3x3_bwd_data": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "alignq_conv3x3_ws_bytes": (_Z, [_I]),
+    "alignq_conv3x3_bwd_weight": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _Z, _P]),
     "alignq_sgd_step": (_I, [_P, _P, _P, _I, _L, _F, _F, _I, _F, _P]),
 }
 

@@ -45,8 +45,8 @@ __device__ __forceinline__ void store_chunk(uint8_t* dst, int l_offset, const fl
   if (SPLIT) *reinterpret_cast<uint4*>(dst + l_offset) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-// The same for NS = 1 or 3 bf16 terms per value: tiles at dst, dst + stride, dst + 2 stride hold H, M, L with
-// v = H + M + L to 24 mantissa bits (M = bf16(v - H), L = bf16(v - H - M); both subtractions are exact in fp32).
+// The same for NS = 1, 2 or 3 bf16 terms per value: tiles at dst, dst + stride, dst + 2 stride hold H, M, L with
+// v = H + M (+ L) to 16 (24) mantissa bits (M = bf16(v - H), L = bf16(v - H - M); both subtractions are exact in fp32).
 template <int NS>
 __device__ __forceinline__ void store_chunk_n(uint8_t* dst, int stride, const float (&c)[8]) {
   uint32_t h[4], m[4], l[4];
@@ -54,19 +54,19 @@ __device__ __forceinline__ void store_chunk_n(uint8_t* dst, int stride, const fl
   for (int p = 0; p < 4; ++p) {
     const __nv_bfloat162 hh = __floats2bfloat162_rn(c[2 * p], c[2 * p + 1]);
     h[p] = *reinterpret_cast<const uint32_t*>(&hh);
-    if (NS == 3) {
+    if (NS >= 2) {
       const float r0 = c[2 * p] - __uint_as_float(h[p] << 16), r1 = c[2 * p + 1] - __uint_as_float(h[p] & 0xFFFF0000u);
       const __nv_bfloat162 mm = __floats2bfloat162_rn(r0, r1);
       m[p] = *reinterpret_cast<const uint32_t*>(&mm);
-      const __nv_bfloat162 ll = __floats2bfloat162_rn(r0 - __uint_as_float(m[p] << 16), r1 - __uint_as_float(m[p] & 0xFFFF0000u));
-      l[p] = *reinterpret_cast<const uint32_t*>(&ll);
+      if (NS == 3) {
+        const __nv_bfloat162 ll = __floats2bfloat162_rn(r0 - __uint_as_float(m[p] << 16), r1 - __uint_as_float(m[p] & 0xFFFF0000u));
+        l[p] = *reinterpret_cast<const uint32_t*>(&ll);
+      }
     }
   }
   *reinterpret_cast<uint4*>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
-  if (NS == 3) {
-    *reinterpret_cast<uint4*>(dst + stride) = make_uint4(m[0], m[1], m[2], m[3]);
-    *reinterpret_cast<uint4*>(dst + 2 * stride) = make_uint4(l[0], l[1], l[2], l[3]);
-  }
+  if (NS >= 2) *reinterpret_cast<uint4*>(dst + stride) = make_uint4(m[0], m[1], m[2], m[3]);
+  if (NS == 3) *reinterpret_cast<uint4*>(dst + 2 * stride) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 }  // namespace tcsmall

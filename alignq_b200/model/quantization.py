@@ -424,6 +424,10 @@ def conv2d_Q_fn(w_bit, stage, variant=None):
 
         def forward(self, input, order=None):
             weight_q = self.quantize_fn(self.weight)
+            if args.own_conv != "off":
+                from . import conv_tc
+                if conv_tc.applies(input, weight_q, self.stride, self.padding, self.dilation, self.groups, self.bias):
+                    return conv_tc.conv3x3(input, weight_q)           # hand-written tcgen05 kernels
             return F.conv2d(input, weight_q, self.bias, self.stride, self.padding, self.dilation, self.groups)
 
     return Conv2d_Q

@@ -18,6 +18,8 @@ BatchNorm -> activation quantizer -> ReLU as one fused kernel pair on channels_l
 ``sync_bn`` (False | True / "nccl" | "peer") gives the fused BatchNorm -> act-quant kernels the batch statistics of
 the GLOBAL batch: their fp64 (sum, sum of squares) accumulators are all-reduced with NCCL between the two launches,
 or -- "peer" -- exchanged inside the kernels through NVLink peer-mapped memory (model/fused.py).
+``own_conv`` ("off" | "tf32" | "tf32x3") runs the 3x3 / stride-1 / Cin == Cout quantized convolutions on the
+hand-written tcgen05 kernels (model/conv_tc.py) instead of the library convolution.
 """
 from __future__ import annotations
 
@@ -28,7 +30,7 @@ _DEFAULTS = dict(
     gpus=[0], bitW=2, abitW=2, act_range=2, lam=1.0, lam2=4.0, method="ours", stage="second",
     train_batch_size=128, eval_batch_size=100, lr=0.04, momentum=0.9, weight_decay=1e-4,
     variant="A", gram_mode="fp32", store_weight_attrs=True, fuse_bn_act=False, admm_param_grads=True,
-    dp_gram="replica", sync_bn=False,
+    dp_gram="replica", sync_bn=False, own_conv="off",
 )
 
 args = SimpleNamespace(**_DEFAULTS)
@@ -43,6 +45,8 @@ def set_args(**kw):
             raise ValueError("variant must be 'A', 'B' or 'C'")
         if k == "gram_mode" and v not in ("fp32", "tf32x3", "bf16"):
             raise ValueError("gram_mode must be 'fp32', 'tf32x3' or 'bf16'")
+        if k == "own_conv" and v not in ("off", "tf32", "tf32x3"):
+            raise ValueError("own_conv must be 'off', 'tf32' or 'tf32x3'")
         if k == "dp_gram" and v not in ("replica", "feature"):
             raise ValueError("dp_gram must be 'replica' (per-rank [b,b] Gram) or 'feature' (global-batch Gram)")
         setattr(args, k, v)

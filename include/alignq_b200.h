@@ -213,6 +213,26 @@ int alignq_bn_act_bwd(const float* x, const float* y, const float* gy, int64_t r
                       float* g_residual, float* ggamma, float* gbeta, double* ws, uint32_t* counter,
                       alignq_stream_t stream);
 
+/* ---- 3x3 convolution of the quantized conv layers on the tensor cores (tcgen05) ------------------------------
+ * `F.conv2d(input, weight_q, None, 1, 1)` of Conv2d_Q.forward (QA:116-120), its data gradient and its weight gradient,
+ * for stride 1, padding 1, Cin == Cout == C in {16, 32, 64}, NHWC (channels_last) fp32:
+ *   x, y, gy, gx: [N, H, W, C] physical;  w, gw: [C_out, 3, 3, C_in] physical (a channels_last [Cout, Cin, 3, 3]).
+ * Implicit GEMM over shifted views of one staged tile (no im2col), accumulators in TMEM; every pointer 16-byte aligned.
+ * mode: ALIGNQ_CONV_TF32 -- tf32 operands, one MMA pass (what cuDNN runs under torch's default allow_tf32 = True;
+ * ~5e-4 relative to an fp32 convolution); ALIGNQ_CONV_TF32X3 -- operands split H + L, three passes, fp32 parity (1e-5).
+ * Returns ALIGNQ_ERANGE for a shape / mode the kernels do not cover (e.g. C == 64 forward in TF32X3 mode: the split
+ * weights do not fit in shared memory) -- the caller then uses its library convolution.
+ * bwd_weight: ws = alignq_conv3x3_ws_bytes(C) bytes of scratch (split-K partials, summed in a fixed order);
+ * accumulate != 0 adds into gw.                                                                                   */
+enum { ALIGNQ_CONV_TF32 = 0, ALIGNQ_CONV_TF32X3 = 1 };
+int alignq_conv3x3_fwd(const float* x, const float* w, float* y, int N, int H, int W, int C, int mode,
+                       alignq_stream_t stream);
+int alignq_conv3x3_bwd_data(const float* gy, const float* w, float* gx, int N, int H, int W, int C, int mode,
+                            alignq_stream_t stream);
+size_t alignq_conv3x3_ws_bytes(int C);
+int alignq_conv3x3_bwd_weight(const float* x, const float* gy, float* gw, int N, int H, int W, int C, int mode,
+                              int accumulate, void* ws, size_t ws_bytes, alignq_stream_t stream);
+
 /* Data-parallel SyncBN inside the fused kernels (BASELINE.json north_star (3): "(sum, sum-of-squares) ... combined with
  * NCCL all-reduce ... so global statistics match the single-device reference"): the same kernels, cut where the ranks'
  * fp64 sums are exchanged.  The caller all-reduces `sums` ([2 C] doubles: per-channel sum and sum of squares forward;

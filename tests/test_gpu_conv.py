@@ -1,0 +1,80 @@
+"""GPU: the tcgen05 3x3 convolution kernels (csrc/conv_tc.cu) against F.conv2d in fp32 (TF32 off):
+forward, data gradient and weight gradient.  Bars: TF32X3 mode (three passes on H + L split operands) 1e-5 relative
+to the output's magnitude -- fp32 parity; TF32 mode (one pass, the numerics cuDNN uses under torch's default
+allow_tf32 = True) 2e-3, with cuDNN's own TF32 error on the same inputs printed beside it."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import alignq_b200 as aq
+from alignq_b200 import _lib as L
+from alignq_b200.model import conv_tc
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+SHAPES = [(2, 8, 8, 16), (128, 32, 32, 16), (128, 16, 16, 32), (128, 8, 8, 64), (3, 5, 7, 32), (1, 32, 32, 16), (5, 3, 3, 16),
+          (7, 14, 14, 64), (130, 32, 32, 16)]
+
+
+@pytest.fixture(autouse=True)
+def _fp32_reference():
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32 = old
+    aq.reset_args()
+
+
+def relmax(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max())
+
+
+@pytest.mark.parametrize("mode,tol", [("tf32x3", 1e-5), ("tf32", 2e-3)])
+@pytest.mark.parametrize("N,H,W,C", SHAPES)
+def test_conv3x3_forward_backward_vs_fp32_conv2d(mode, tol, N, H, W, C):
+    if C == 64 and mode == "tf32x3":
+        pytest.skip("C = 64 in TF32X3 mode is not covered (split weights exceed shared memory): library convolution")
+    torch.manual_seed(50)
+    aq.set_args(own_conv=mode)
+    x0 = torch.randn(N, C, H, W, device=DEV).contiguous(memory_format=torch.channels_last)
+    w0 = (torch.randn(C, C, 3, 3, device=DEV) * (2.0 / (9 * C)) ** 0.5).contiguous(memory_format=torch.channels_last)
+    gy = torch.randn(N, C, H, W, device=DEV).contiguous(memory_format=torch.channels_last)
+    assert conv_tc.applies(x0, w0, (1, 1), (1, 1), (1, 1), 1, None)
+    x, w = x0.clone().requires_grad_(True), w0.clone().requires_grad_(True)
+    y = conv_tc.conv3x3(x, w)
+    (y * gy).sum().backward()
+    xr, wr = x0.double().clone().requires_grad_(True), w0.double().clone().requires_grad_(True)
+    yr = F.conv2d(xr, wr, None, 1, 1)
+    (yr * gy.double()).sum().backward()
+    x32, w32 = x0.clone().requires_grad_(True), w0.clone().requires_grad_(True)
+    y32 = F.conv2d(x32, w32, None, 1, 1)
+    (y32 * gy).sum().backward()
+    e = (relmax(y, yr), relmax(x.grad, xr.grad), relmax(w.grad, wr.grad))
+    f = (relmax(y32, yr), relmax(x32.grad, xr.grad), relmax(w32.grad, wr.grad))
+    print(f"conv3x3 {mode} N={N} {H}x{W} C={C}: max|d|/max|ref| fwd {e[0]:.1e} dgrad {e[1]:.1e} wgrad {e[2]:.1e}   "
+          f"(cuDNN fp32: {f[0]:.1e} {f[1]:.1e} {f[2]:.1e})")
+    assert y.is_contiguous(memory_format=torch.channels_last) and x.grad.shape == x0.shape and w.grad.stride() == w0.stride()
+    assert e[0] <= tol and e[1] <= tol and e[2] <= tol
+
+
+def test_conv2d_q_uses_the_kernels_when_it_applies_and_the_library_otherwise():
+    torch.manual_seed(51)
+    aq.set_args(variant="A", bitW=8, own_conv="tf32x3")
+    lib = L.load()
+    conv = aq.conv2d_Q_fn(8, "second")(32, 32, 3, padding=1, bias=False).to(DEV)
+    conv.weight.data = conv.weight.data.contiguous(memory_format=torch.channels_last)
+    x = torch.randn(8, 32, 16, 16, device=DEV).contiguous(memory_format=torch.channels_last)
+    n0 = lib.alignq_launch_count()
+    y = conv(x)
+    assert lib.alignq_launch_count() - n0 >= 3                        # weight quantizer (2) + own conv
+    aq.set_args(own_conv="off")
+    y_lib = conv(x)
+    assert relmax(y, y_lib) <= 1e-5
+    aq.set_args(own_conv="tf32x3")
+    for bad in (torch.randn(8, 32, 16, 16, device=DEV),                # NCHW input
+                ):
+        n1 = lib.alignq_launch_count()
+        conv(bad)
+        assert lib.alignq_launch_count() - n1 == 2                    # only the weight quantizer: library convolution
+    strided = aq.conv2d_Q_fn(8, "second")(32, 32, 3, stride=2, padding=1, bias=False).to(DEV)
+    assert not conv_tc.applies(x, strided.weight, strided.stride, strided.padding, strided.dilation, 1, None)

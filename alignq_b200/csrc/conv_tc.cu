@@ -54,49 +54,59 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// Stage `npt` positions starting at global position g0 of an NHWC tensor into planes.  AS_OUTPUT: position g is the
-// OUTPUT pixel (yy, xx) (valid for yy < H, xx < W); otherwise the zero-padded INPUT pixel (yy - 1, xx - 1).
-// NS = 1: one tile of tf32-rounded values; NS = 2: H tile and, `lo_off` bytes further, the L = v - H tile.
-template <int C, int NS, bool AS_OUTPUT>
-__device__ __forceinline__ void stage_planes(const float* __restrict__ src, const Geo& G, int g0, int npt, uint8_t* planes,
-                                             int PS, int lo_off) {
-  constexpr int C4 = C / 4, STEP = NT / C4;
-  const int c4 = threadIdx.x % C4;
-  int j = threadIdx.x / C4;
-  int g = g0 + j;
+// Software pipeline of the staging: FETCH (global -> registers; issued right after the MMAs of the previous tile, so
+// the DRAM latency hides behind them) and DEPOSIT (registers -> converted operand planes in shared memory, once those
+// MMAs have retired).  Item i of thread t: unit = t % UNITS, position j = t / UNITS + i * (NT / UNITS); QW float4 per
+// item (QW = 1: 4 channels, tf32 planes; QW = 2: 8 channels, bf16 planes).  AS_OUTPUT: global position g is the OUTPUT
+// pixel (yy, xx) (valid for yy < H, xx < W); otherwise the zero-padded INPUT pixel (yy - 1, xx - 1).
+template <int C, int QW, bool AS_OUTPUT, int MAXI>
+__device__ __forceinline__ void fetch_items(const float* __restrict__ src, const Geo& G, int g0, int npt, float4 (&v)[MAXI][QW]) {
+  constexpr int UNITS = C / (4 * QW), STEP = NT / UNITS;
+  const int u0 = threadIdx.x % UNITS;
+  const int j0 = threadIdx.x / UNITS;
+  int g = g0 + j0;
   int n = g / G.per;
   int q = g - n * G.per;
   int yy = q / G.Wp;
   int xx = q - yy * G.Wp;
-  uint8_t* dst = planes + c4 * PS;
-  constexpr int U = 4;
-  for (; j < npt; j += U * STEP) {
-    float4 v[U];
-    int jj[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      jj[u] = j + u * STEP;
-      const int iy = AS_OUTPUT ? yy : yy - 1, ix = AS_OUTPUT ? xx : xx - 1;
-      const bool ok = jj[u] < npt && n < G.N && iy >= 0 && iy < G.H && ix >= 0 && ix < G.W;
-      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (ok) v[u] = __ldg(reinterpret_cast<const float4*>(src + ((int64_t)(n * G.H + iy) * G.W + ix) * C + 4 * c4));
-      xx += STEP;                                            // advance the decoded position by STEP
-      while (xx >= G.Wp) { xx -= G.Wp; ++yy; }
-      while (yy >= G.Hp) { yy -= G.Hp; ++n; }
+  for (int i = 0; i < MAXI; ++i) {
+    const int j = j0 + i * STEP;
+    const int iy = AS_OUTPUT ? yy : yy - 1, ix = AS_OUTPUT ? xx : xx - 1;
+    const bool ok = j < npt && n < G.N && iy >= 0 && iy < G.H && ix >= 0 && ix < G.W;
+#pragma unroll
+    for (int k = 0; k < QW; ++k) v[i][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ok) {
+      const float4* p = reinterpret_cast<const float4*>(src + ((int64_t)(n * G.H + iy) * G.W + ix) * C + 4 * QW * u0);
+#pragma unroll
+      for (int k = 0; k < QW; ++k) v[i][k] = __ldg(p + k);
     }
+    xx += STEP;                                              // advance the decoded position by STEP
+    while (xx >= G.Wp) { xx -= G.Wp; ++yy; }
+    while (yy >= G.Hp) { yy -= G.Hp; ++n; }
+  }
+}
+
+// tf32 planes: NS = 1: one tile of tf32-rounded values; NS = 2: H tile and, `lo_off` bytes further, the L = v - H tile.
+template <int C, int NS, int MAXI>
+__device__ __forceinline__ void deposit_tf32(const float4 (&v)[MAXI][1], int npt, uint8_t* planes, int PS, int lo_off) {
+  constexpr int C4 = C / 4, STEP = NT / C4;
+  uint8_t* dst = planes + (threadIdx.x % C4) * PS;
+  const int j0 = threadIdx.x / C4;
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (jj[u] >= npt) continue;
-      uint8_t* d = dst + jj[u] * 16;
-      if (NS == 1) {
-        *reinterpret_cast<uint4*>(d) = make_uint4(cvt_tf32(v[u].x), cvt_tf32(v[u].y), cvt_tf32(v[u].z), cvt_tf32(v[u].w));
-      } else {
-        const uint4 h = make_uint4(__float_as_uint(v[u].x) & 0xFFFFE000u, __float_as_uint(v[u].y) & 0xFFFFE000u,
-                                   __float_as_uint(v[u].z) & 0xFFFFE000u, __float_as_uint(v[u].w) & 0xFFFFE000u);
-        *reinterpret_cast<uint4*>(d) = h;
-        *reinterpret_cast<float4*>(d + lo_off) = make_float4(v[u].x - __uint_as_float(h.x), v[u].y - __uint_as_float(h.y),
-                                                             v[u].z - __uint_as_float(h.z), v[u].w - __uint_as_float(h.w));
-      }
+  for (int i = 0; i < MAXI; ++i) {
+    const int j = j0 + i * STEP;
+    if (j >= npt) continue;
+    uint8_t* d = dst + j * 16;
+    const float4 t = v[i][0];
+    if (NS == 1) {
+      *reinterpret_cast<uint4*>(d) = make_uint4(cvt_tf32(t.x), cvt_tf32(t.y), cvt_tf32(t.z), cvt_tf32(t.w));
+    } else {
+      const uint4 h = make_uint4(__float_as_uint(t.x) & 0xFFFFE000u, __float_as_uint(t.y) & 0xFFFFE000u,
+                                 __float_as_uint(t.z) & 0xFFFFE000u, __float_as_uint(t.w) & 0xFFFFE000u);
+      *reinterpret_cast<uint4*>(d) = h;
+      *reinterpret_cast<float4*>(d + lo_off) = make_float4(t.x - __uint_as_float(h.x), t.y - __uint_as_float(h.y),
+                                                           t.z - __uint_as_float(h.z), t.w - __uint_as_float(h.w));
     }
   }
 }
@@ -122,7 +132,7 @@ struct FwdCfg {
   static constexpr int W_TAP = C * C * 4;                          // one tap's weight tile, dense K-major
 };
 
-template <int C, int NS, bool FLIP>
+template <int C, int NS, bool FLIP, int MAXI>
 __global__ void __launch_bounds__(NT)
 conv3x3_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, float* __restrict__ out, Geo G, int ntiles,
                    int npt, int PS) {
@@ -173,11 +183,13 @@ conv3x3_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, fl
   const uint32_t tmem_base = *tmem_slot;
   constexpr uint32_t IDESC = make_idesc(2u /*tf32*/, 128u, (uint32_t)C);
 
+  float4 fv[MAXI][1];
+  if ((int)blockIdx.x < ntiles) fetch_items<C, 1, false, MAXI>(in, G, blockIdx.x * F::MT, npt, fv);
   int it = 0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
     const int g0 = tile * F::MT;
-    // ---- 1. stage the input positions g0 .. g0 + MT + 2 Wp + 2 --------------------------------------------------
-    stage_planes<C, NS, false>(in, G, g0, npt, planes, PS, tile_bytes);
+    // ---- 1. deposit the fetched input positions g0 .. g0 + MT + 2 Wp + 2 (the planes are free: last tile's MMAs retired)
+    deposit_tf32<C, NS, MAXI>(fv, npt, planes, PS, tile_bytes);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -208,9 +220,11 @@ conv3x3_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, fl
       }
       umma_commit(bar);
     }
+    // ---- 3. next tile's positions -> registers while the tensor core works -----------------------------------------
+    if (tile + (int)gridDim.x < ntiles) fetch_items<C, 1, false, MAXI>(in, G, (tile + gridDim.x) * F::MT, npt, fv);
     mbar_wait(bar, (uint32_t)(it & 1));
     tc_fence_after();
-    // ---- 3. epilogue: warp w -> M tile w / 4, TMEM lanes 32 (w % 4) .. +31; one output position per thread ---------
+    // ---- 4. epilogue: warp w -> M tile w / 4, TMEM lanes 32 (w % 4) .. +31; one output position per thread ---------
     {
       const int mt = warp >> 2;
       const int j = mt * 128 + (warp & 3) * 32 + lane;             // position inside the tile
@@ -252,17 +266,21 @@ conv3x3_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, fl
 // Weight gradient:  dW[co][kh][kw][ci] = sum_pos gy[pos, co] * x[pos + kh Wp + kw, ci]       (split-K over CTAs)
 // Both operands are MN-major here (MN = channels, K = positions).  kind::tf32 does not take MN-major operands in the
 // un-swizzled layout (measured: the MMA returns zeros), so the operands are bf16 TERMS of the fp32 values, 8 channels
-// per 16-byte unit, plane c8 = channels 8 c8 .. 8 c8 + 7:   byte address = plane_base + c8 * PS + position * 16.
+// per 16-byte unit:   byte address = plane_base + unit * PS + position * 16.
 //   NSB = 2 (mode TF32):   v = H + M, 16 mantissa bits (more than tf32's 11), products H H | H M + M H     (3 MMAs)
 //   NSB = 3 (mode TF32X3): v = H + M + L, 24 bits, products H H | H M + M H + H L + L H + M M               (6 MMAs)
 // (the large product in the main accumulator, the small ones in a second one: the tensor core truncates when it adds
-// into the fp32 accumulator).  A = gy planes (M = 64 rows of which C are real), B = x planes with the start address
-// moved by the tap shift, M = 64, N = C, K = 16 positions per MMA.  Tap t accumulates in TMEM columns t * C (+ TAPS * C
-// for the cross terms); accumulator row m is TMEM lane (m % 16) + 32 (m / 16).  Every CTA writes its partial
-// [C][TAPS * C] to the workspace; conv3x3_wgrad_reduce_kernel sums them in a fixed order.
+// into the fp32 accumulator).
+// A tcgen05.mma costs ~50 clocks to issue whatever its size (measured: a first version with one M = 64, N = C, K = 16
+// MMA per tap and k-step spent 88 us on [128, 16, 32, 32], all of it MMA issue), so the taps are folded into N: the
+// x operand is staged as an im2col-in-shared-memory of TAPS shifted copies, unit u = tap * (C/8) + c8, and ONE
+// M = 64, N = TAPS * C, K = 16 MMA per k-step and product covers all the CTA's taps.  A = gy planes (M = 64 rows of
+// which C are real; the units past C/8 read whatever follows -- rows of D that are never stored).  Accumulator row m
+// is TMEM lane (m % 16) + 32 (m / 16), columns tap * C + ci (+ TAPS * C for the cross terms).  Every CTA writes its
+// partial [C][TAPS * C] to the workspace; conv3x3_wgrad_reduce_kernel sums them in a fixed order.
 template <int C>
 struct WgCfg {
-  static constexpr int KT = 256;                                   // positions (K) per tile
+  static constexpr int KT = 128;                                   // positions (K) per tile
 };
 
 __host__ __device__ constexpr int plane_stride_bf16(int C, int npt) {
@@ -272,65 +290,58 @@ __host__ __device__ constexpr int plane_stride_bf16(int C, int npt) {
   return ps;
 }
 
-// like stage_planes, but 8 channels per thread and position, converted to NSB bf16 terms (tiles `term_off` bytes apart)
-template <int C, int NSB, bool AS_OUTPUT>
-__device__ __forceinline__ void stage_planes_bf16(const float* __restrict__ src, const Geo& G, int g0, int npt,
-                                                  uint8_t* planes, int PS, int term_off) {
+// bf16-term planes (tiles `term_off` bytes apart) from fetched 8-channel items.
+// IM2COL = false: unit c8, position j.   IM2COL = true (the x operand; npt = KT + 2 Wp + 2 halo positions were fetched):
+// source position j is written to unit (tap, c8) at position j - shift(tap) for every tap of the CTA that needs it.
+template <int C, int NSB, bool IM2COL, int TAPS, int MAXI>
+__device__ __forceinline__ void deposit_bf16(const float4 (&v)[MAXI][2], const Geo& G, int npt, int kt, int tap0,
+                                             uint8_t* planes, int PS, int term_off) {
   constexpr int C8 = C / 8, STEP = NT / C8;
   const int c8 = threadIdx.x % C8;
-  int j = threadIdx.x / C8;
-  int g = g0 + j;
-  int n = g / G.per;
-  int q = g - n * G.per;
-  int yy = q / G.Wp;
-  int xx = q - yy * G.Wp;
-  uint8_t* dst = planes + c8 * PS;
-  constexpr int U = 2;
-  for (; j < npt; j += U * STEP) {
-    float4 v[U][2];
-    int jj[U];
+  const int j0 = threadIdx.x / C8;
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      jj[u] = j + u * STEP;
-      const int iy = AS_OUTPUT ? yy : yy - 1, ix = AS_OUTPUT ? xx : xx - 1;
-      const bool ok = jj[u] < npt && n < G.N && iy >= 0 && iy < G.H && ix >= 0 && ix < G.W;
-      v[u][0] = v[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (ok) {
-        const float4* p = reinterpret_cast<const float4*>(src + ((int64_t)(n * G.H + iy) * G.W + ix) * C + 8 * c8);
-        v[u][0] = __ldg(p);
-        v[u][1] = __ldg(p + 1);
+  for (int i = 0; i < MAXI; ++i) {
+    const int j = j0 + i * STEP;
+    if (j >= npt) continue;
+    const float c[8] = {v[i][0].x, v[i][0].y, v[i][0].z, v[i][0].w, v[i][1].x, v[i][1].y, v[i][1].z, v[i][1].w};
+    if (!IM2COL) {
+      tcsmall::store_chunk_n<NSB>(planes + c8 * PS + j * 16, term_off, c);
+    } else {
+      uint4 t[NSB];
+      tcsmall::split_chunk_n<NSB>(c, t);
+#pragma unroll
+      for (int tt = 0; tt < TAPS; ++tt) {
+        const int tap = tap0 + tt;
+        const int jd = j - ((tap / 3) * G.Wp + (tap % 3));
+        if (jd >= 0 && jd < kt) {
+          uint8_t* d = planes + (tt * C8 + c8) * PS + jd * 16;
+#pragma unroll
+          for (int k = 0; k < NSB; ++k) *reinterpret_cast<uint4*>(d + k * term_off) = t[k];
+        }
       }
-      xx += STEP;
-      while (xx >= G.Wp) { xx -= G.Wp; ++yy; }
-      while (yy >= G.Hp) { yy -= G.Hp; ++n; }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (jj[u] >= npt) continue;
-      const float c[8] = {v[u][0].x, v[u][0].y, v[u][0].z, v[u][0].w, v[u][1].x, v[u][1].y, v[u][1].z, v[u][1].w};
-      tcsmall::store_chunk_n<NSB>(dst + jj[u] * 16, term_off, c);
     }
   }
 }
 
-template <int C, int NSB, int TAPS>
+template <int C, int NSB, int TAPS, bool CROSS, int MAXG, int MAXX>
 __global__ void __launch_bounds__(NT)
 conv3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ partials, Geo G,
-                     int ntiles, int npx, int PSX, int PSG) {
+                     int ntiles, int npx, int PS) {
   using K = WgCfg<C>;
+  constexpr int C8 = C / 8;
   extern __shared__ __align__(128) uint8_t smem[];
-  // gy planes first: the M = 64 descriptor walks 8 MN units of PSG bytes; units >= C/8 read whatever follows (rows of D
-  // that are never stored), which must stay inside this CTA's allocation -- the launcher sizes it accordingly
-  uint8_t* gplanes = smem;                                         // [NSB][C/8][KT]
-  const int gtile = (C / 8) * PSG, xtile = (C / 8) * PSX;
-  uint8_t* xplanes = smem + NSB * gtile;                           // [NSB][C/8][npx]
+  uint8_t* gplanes = smem;                                         // [NSB][C8 units][KT]
+  const int gtile = C8 * PS, xtile = TAPS * C8 * PS;
+  uint8_t* xplanes = smem + NSB * gtile;                           // [NSB][TAPS * C8 units][KT]
   uint64_t* bar = reinterpret_cast<uint64_t*>(xplanes + NSB * xtile);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int ACC = TAPS * C;                                    // columns of one accumulator set
-  constexpr int NEED = 2 * ACC;                                    // main + cross
+  constexpr int ACC = TAPS * C;                                    // columns of one accumulator set = MMA N
+  // CROSS: the small products get their own accumulator (fp32-parity mode); without it everything shares one, which
+  // halves the TMEM columns so that two CTAs fit on an SM (a second 512-column allocation would wait for the first)
+  constexpr int NEED = CROSS ? 2 * ACC : ACC;
   constexpr int TCOLS = NEED <= 32 ? 32 : NEED <= 64 ? 64 : NEED <= 128 ? 128 : NEED <= 256 ? 256 : 512;
-  static_assert(NEED <= 512, "weight-gradient accumulators exceed TMEM");
+  static_assert(NEED <= 512 && ACC <= 256 && ACC % 8 == 0, "weight-gradient MMA shape");
   const int tap0 = blockIdx.y * TAPS;
 
   if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
@@ -340,45 +351,48 @@ conv3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ gy, 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // bf16 operands, both MN-major (bits 15, 16)
-  constexpr uint32_t IDESC = make_idesc(1u /*bf16*/, 64u, (uint32_t)C) | (1u << 15) | (1u << 16);
+  constexpr uint32_t IDESC = make_idesc(1u /*bf16*/, 64u, (uint32_t)ACC) | (1u << 15) | (1u << 16);
 
+  float4 fg[MAXG][2], fx[MAXX][2];
+  if ((int)blockIdx.x < ntiles) {
+    fetch_items<C, 2, true, MAXG>(gy, G, blockIdx.x * K::KT, K::KT, fg);
+    fetch_items<C, 2, false, MAXX>(x, G, blockIdx.x * K::KT, npx, fx);
+  }
   int it = 0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-    const int g0 = tile * K::KT;
-    stage_planes_bf16<C, NSB, true>(gy, G, g0, K::KT, gplanes, PSG, gtile);     // zero at pad positions: they add nothing
-    stage_planes_bf16<C, NSB, false>(x, G, g0, npx, xplanes, PSX, xtile);
+    deposit_bf16<C, NSB, false, 1, MAXG>(fg, G, K::KT, K::KT, 0, gplanes, PS, gtile);       // gy is zero at pad positions
+    deposit_bf16<C, NSB, true, TAPS, MAXX>(fx, G, npx, K::KT, tap0, xplanes, PS, xtile);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     if (threadIdx.x == 0) {
       tc_fence_after();
       const uint32_t sg = smem_u32(gplanes), sx = smem_u32(xplanes);
-#pragma unroll 1
-      for (int t = 0; t < TAPS; ++t) {
-        const int tap = tap0 + t;
-        const uint32_t shift = (uint32_t)((tap / 3) * G.Wp + (tap % 3)) * 16u;
-        const uint32_t d_main = tmem_base + t * C, d_cross = tmem_base + ACC + t * C;
-#pragma unroll 2
-        for (int ks = 0; ks < K::KT / 16; ++ks) {
-          const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
-          // MN-major: LBO = stride of the 8-position K groups (128 B: K is linear in the position), SBO = plane stride
-          const uint32_t ga = sg + ks * 256, xa = sx + shift + ks * 256;
-          const uint64_t ah = make_desc(ga, 128, PSG), bh = make_desc(xa, 128, PSX);
-          const uint64_t am = make_desc(ga + gtile, 128, PSG), bm = make_desc(xa + xtile, 128, PSX);
-          umma<false>(d_main, ah, bh, IDESC, acc);                           // H H
-          umma<false>(d_cross, ah, bm, IDESC, acc);                          // the small products
-          umma<false>(d_cross, am, bh, IDESC, 1u);
-          if (NSB == 3) {
-            const uint64_t al = make_desc(ga + 2 * gtile, 128, PSG), bl = make_desc(xa + 2 * xtile, 128, PSX);
-            umma<false>(d_cross, ah, bl, IDESC, 1u);
-            umma<false>(d_cross, al, bh, IDESC, 1u);
-            umma<false>(d_cross, am, bm, IDESC, 1u);
-          }
+      const uint32_t d_main = tmem_base, d_cross = CROSS ? tmem_base + ACC : tmem_base;
+#pragma unroll
+      for (int ks = 0; ks < K::KT / 16; ++ks) {
+        const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
+        // MN-major: LBO = stride of the 8-position K groups (128 B: K is linear in the position), SBO = unit stride
+        const uint32_t ga = sg + ks * 256, xa = sx + ks * 256;
+        const uint64_t ah = make_desc(ga, 128, PS), bh = make_desc(xa, 128, PS);
+        const uint64_t am = make_desc(ga + gtile, 128, PS), bm = make_desc(xa + xtile, 128, PS);
+        umma<false>(d_main, ah, bh, IDESC, acc);                             // H H
+        umma<false>(d_cross, ah, bm, IDESC, CROSS ? acc : 1u);               // the small products
+        umma<false>(d_cross, am, bh, IDESC, 1u);
+        if (NSB == 3) {
+          const uint64_t al = make_desc(ga + 2 * gtile, 128, PS), bl = make_desc(xa + 2 * xtile, 128, PS);
+          umma<false>(d_cross, ah, bl, IDESC, 1u);
+          umma<false>(d_cross, al, bh, IDESC, 1u);
+          umma<false>(d_cross, am, bm, IDESC, 1u);
         }
       }
       umma_commit(bar);
     }
-    mbar_wait(bar, (uint32_t)(it & 1));                            // the planes are rewritten by the next tile
+    if (tile + (int)gridDim.x < ntiles) {                          // next tile -> registers while the tensor core works
+      fetch_items<C, 2, true, MAXG>(gy, G, (tile + gridDim.x) * K::KT, K::KT, fg);
+      fetch_items<C, 2, false, MAXX>(x, G, (tile + gridDim.x) * K::KT, npx, fx);
+    }
+    mbar_wait(bar, (uint32_t)(it & 1));                            // the planes are rewritten by the next deposit
     tc_fence_after();
     tc_fence_before();
     __syncthreads();
@@ -392,13 +406,18 @@ conv3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ gy, 
     const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
     for (int c0 = 0; c0 < ACC; c0 += 16) {
-      uint32_t v[16], x2[16];
+      uint32_t v[16];
       float r[16];
       if (it > 0) {
         tmem_ld16(ta + c0, v);
-        tmem_ld16(ta + ACC + c0, x2);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) r[e] = __uint_as_float(v[e]) + __uint_as_float(x2[e]);
+        for (int e = 0; e < 16; ++e) r[e] = __uint_as_float(v[e]);
+        if (CROSS) {
+          uint32_t x2[16];
+          tmem_ld16(ta + ACC + c0, x2);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) r[e] += __uint_as_float(x2[e]);
+        }
       } else {
 #pragma unroll
         for (int e = 0; e < 16; ++e) r[e] = 0.f;                    // a CTA without tiles contributes zeros
@@ -414,19 +433,32 @@ conv3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ gy, 
   if (warp == 0) tmem_dealloc(tmem_base, TCOLS);
 }
 
-// gw[co][kh][kw][ci] (+)= sum over the CTAs' partials [grp][cta][co][TAPS * C], fixed order
-__global__ void __launch_bounds__(256)
+// gw[co][kh][kw][ci] (+)= sum over the CTAs' partials [grp][cta][co][TAPS * C], fixed order.  Block = 32 elements x
+// 32 part lanes: lane pl sums parts pl, pl + 32, ...; the 32 lane sums are then added in a fixed order.  (A first
+// version with one thread per element walking all ~300 partials took 26 us -- longer than the MMA kernel itself.)
+__global__ void __launch_bounds__(1024)
 conv3x3_wgrad_reduce_kernel(const float* __restrict__ partials, int nparts, int C, int taps, float* __restrict__ gw,
                             int accumulate) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;            // index into [co][9][ci]
-  if (e >= C * 9 * C) return;
-  const int ci = e % C, tap = (e / C) % 9, co = e / (9 * C);
-  const int grp = tap / taps, t = tap - grp * taps;
-  const int acc = taps * C;
-  const float* p = partials + ((size_t)grp * nparts * C + co) * acc + t * C + ci;
+  __shared__ float sm[32][33];
+  const int e = blockIdx.x * 32 + threadIdx.x;                    // index into [co][9][ci]
+  const int pl = threadIdx.y;
+  const int total = C * 9 * C;
   float s = 0.f;
-  for (int k = 0; k < nparts; ++k) s += p[(size_t)k * C * acc];
-  gw[e] = accumulate ? gw[e] + s : s;
+  if (e < total) {
+    const int ci = e % C, tap = (e / C) % 9, co = e / (9 * C);
+    const int grp = tap / taps, t = tap - grp * taps;
+    const int acc = taps * C;
+    const float* p = partials + ((size_t)grp * nparts * C + co) * acc + t * C + ci;
+    for (int k = pl; k < nparts; k += 32) s += p[(size_t)k * C * acc];
+  }
+  sm[pl][threadIdx.x] = s;
+  __syncthreads();
+  if (pl == 0 && e < total) {
+    float r = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) r += sm[k][threadIdx.x];
+    gw[e] = accumulate ? gw[e] + r : r;
+  }
 }
 
 inline Geo make_geo(int N, int H, int W) {
@@ -446,27 +478,32 @@ static int launch_fwd(const float* in, const float* w, float* out, int N, int H,
   const int PS = plane_stride(C, npt);
   const size_t smem = (size_t)NS * 9 * F::W_TAP + (size_t)NS * (C / 4) * PS + 64;
   if (smem > 227 * 1024) return ALIGNQ_ERANGE;
-  cudaError_t e = cudaFuncSetAttribute(conv3x3_fwd_kernel<C, NS, FLIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // staging registers: items per thread = ceil(npt / (NT / (C/4))); the instantiation covers rows up to W = 32 + 2
+  constexpr int STEP = NT / (C / 4);
+  constexpr int MAXI = (F::MT + 2 * 34 + 2 + STEP - 1) / STEP;
+  if (npt > MAXI * STEP) return ALIGNQ_ERANGE;                 // wider images: the caller's library convolution
+  cudaError_t e = cudaFuncSetAttribute(conv3x3_fwd_kernel<C, NS, FLIP, MAXI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
+  // persistent CTAs (the weights are staged once per CTA): two per SM overlap each other's deposit / MMA / epilogue phases
   int per_sm = (int)((227 * 1024) / (smem + 1024));
   if (per_sm < 1) per_sm = 1;
-  if (per_sm > 4) per_sm = 4;
+  if (per_sm > 2) per_sm = 2;
   int grid = ntiles < ALIGNQ_NUM_SMS * per_sm ? ntiles : ALIGNQ_NUM_SMS * per_sm;
-  conv3x3_fwd_kernel<C, NS, FLIP><<<grid, NT, smem, s>>>(in, w, out, G, ntiles, npt, PS);
+  conv3x3_fwd_kernel<C, NS, FLIP, MAXI><<<grid, NT, smem, s>>>(in, w, out, G, ntiles, npt, PS);
   ALIGNQ_LAUNCH_CHECK();
   return ALIGNQ_OK;
 }
 
-template <int C, int NSB, int TAPS>
+template <int C, int NSB, int TAPS, bool CROSS>
 static int launch_wgrad(const float* x, const float* gy, float* gw, int N, int H, int W, int accumulate, float* ws,
                         size_t ws_bytes, cudaStream_t s) {
   using K = WgCfg<C>;
   const Geo G = make_geo(N, H, W);
   const int ntiles = (G.npos + K::KT - 1) / K::KT;
   const int npx = K::KT + 2 * G.Wp + 2;
-  const int PSX = plane_stride_bf16(C, npx), PSG = plane_stride_bf16(C, K::KT);
-  size_t smem = (size_t)NSB * (C / 8) * PSG + (size_t)NSB * (C / 8) * PSX + 64;
-  const size_t reach = (size_t)(NSB - 1) * (C / 8) * PSG + 8 * (size_t)PSG;   // what the M = 64 descriptors may touch
+  const int PS = plane_stride_bf16(C, K::KT);
+  size_t smem = (size_t)NSB * (C / 8) * PS * (1 + TAPS) + 64;
+  const size_t reach = (size_t)(NSB - 1) * (C / 8) * PS + 8 * (size_t)PS + K::KT * 16;   // what the M = 64 descriptors may touch
   if (smem < reach + 64) smem = reach + 64;
   if (smem > 227 * 1024) return ALIGNQ_ERANGE;
   const int groups = 9 / TAPS;
@@ -478,11 +515,15 @@ static int launch_wgrad(const float* x, const float* gy, float* gw, int N, int H
   if (grid < 1) grid = 1;
   const size_t need = (size_t)groups * grid * C * TAPS * C * sizeof(float);
   if (ws_bytes < need) return ALIGNQ_ENOSPACE;
-  cudaError_t e = cudaFuncSetAttribute(conv3x3_wgrad_kernel<C, NSB, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  constexpr int STEP = NT / (C / 8);
+  constexpr int MAXG = (K::KT + STEP - 1) / STEP, MAXX = (K::KT + 2 * 34 + 2 + STEP - 1) / STEP;
+  if (npx > MAXX * STEP) return ALIGNQ_ERANGE;                  // wider images: the caller's library convolution
+  cudaError_t e = cudaFuncSetAttribute(conv3x3_wgrad_kernel<C, NSB, TAPS, CROSS, MAXG, MAXX>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  conv3x3_wgrad_kernel<C, NSB, TAPS><<<dim3(grid, groups), NT, smem, s>>>(x, gy, ws, G, ntiles, npx, PSX, PSG);
+  conv3x3_wgrad_kernel<C, NSB, TAPS, CROSS, MAXG, MAXX><<<dim3(grid, groups), NT, smem, s>>>(x, gy, ws, G, ntiles, npx, PS);
   ALIGNQ_LAUNCH_CHECK();
-  conv3x3_wgrad_reduce_kernel<<<(C * 9 * C + 255) / 256, 256, 0, s>>>(ws, grid, C, TAPS, gw, accumulate);
+  conv3x3_wgrad_reduce_kernel<<<(C * 9 * C + 31) / 32, dim3(32, 32), 0, s>>>(ws, grid, C, TAPS, gw, accumulate);
   ALIGNQ_LAUNCH_CHECK();
   return ALIGNQ_OK;
 }
@@ -547,11 +588,11 @@ extern "C" int alignq_conv3x3_bwd_weight(const float* x, const float* gy, float*
   float* wsf = reinterpret_cast<float*>(ws);
   // bf16 terms per value: 2 (16 bits, >= tf32) or 3 (24 bits); taps per CTA so that main + cross accumulators fit TMEM
   if (mode == ALIGNQ_CONV_TF32) {
-    if (C == 16) return launch_wgrad<16, 2, 9>(x, gy, gw, N, H, W, accumulate, wsf, ws_bytes, s);
-    if (C == 32) return launch_wgrad<32, 2, 3>(x, gy, gw, N, H, W, accumulate, wsf, ws_bytes, s);
-    return launch_wgrad<64, 2, 3>(x, gy, gw, N, H, W, accumulate, wsf, ws_bytes, s);
+    if (C == 16) return launch_wgrad<16, 2, 9, false>(x, gy, gw, N, H, W, accumulate, wsf, ws_bytes, s);
+    if (C == 32) return launch_wgrad<32, 2, 3, false>(x, gy, gw, N, H, W, accumulate, wsf, ws_bytes, s);
+    return launch_wgrad<64, 2, 3, false>(x, gy, gw, N, H, W, accumulate, wsf, ws_bytes, s);
   }
-  if (C == 16) return launch_wgrad<16, 3, 9>(x, gy, gw, N, H, W, accumulate, wsf, ws_bytes, s);
-  if (C == 32) return launch_wgrad<32, 3, 3>(x, gy, gw, N, H, W, accumulate, wsf, ws_bytes, s);
-  return launch_wgrad<64, 3, 3>(x, gy, gw, N, H, W, accumulate, wsf, ws_bytes, s);
+  if (C == 16) return launch_wgrad<16, 3, 9, true>(x, gy, gw, N, H, W, accumulate, wsf, ws_bytes, s);
+  if (C == 32) return launch_wgrad<32, 3, 3, true>(x, gy, gw, N, H, W, accumulate, wsf, ws_bytes, s);
+  return launch_wgrad<64, 3, 3, true>(x, gy, gw, N, H, W, accumulate, wsf, ws_bytes, s);
 }

@@ -69,5 +69,28 @@ __device__ __forceinline__ void store_chunk_n(uint8_t* dst, int stride, const fl
   if (NS == 3) *reinterpret_cast<uint4*>(dst + 2 * stride) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// the same split without the stores: t[0..NS-1] = the 16-byte H (, M (, L)) chunks of 8 values
+template <int NS>
+__device__ __forceinline__ void split_chunk_n(const float (&c)[8], uint4 (&t)[NS]) {
+  uint32_t h[4], m[4], l[4];
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const __nv_bfloat162 hh = __floats2bfloat162_rn(c[2 * p], c[2 * p + 1]);
+    h[p] = *reinterpret_cast<const uint32_t*>(&hh);
+    if (NS >= 2) {
+      const float r0 = c[2 * p] - __uint_as_float(h[p] << 16), r1 = c[2 * p + 1] - __uint_as_float(h[p] & 0xFFFF0000u);
+      const __nv_bfloat162 mm = __floats2bfloat162_rn(r0, r1);
+      m[p] = *reinterpret_cast<const uint32_t*>(&mm);
+      if (NS == 3) {
+        const __nv_bfloat162 ll = __floats2bfloat162_rn(r0 - __uint_as_float(m[p] << 16), r1 - __uint_as_float(m[p] & 0xFFFF0000u));
+        l[p] = *reinterpret_cast<const uint32_t*>(&ll);
+      }
+    }
+  }
+  t[0] = make_uint4(h[0], h[1], h[2], h[3]);
+  if (NS >= 2) t[1] = make_uint4(m[0], m[1], m[2], m[3]);
+  if (NS == 3) t[NS - 1] = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
 }  // namespace tcsmall
 }  // namespace alignq

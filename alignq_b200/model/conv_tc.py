@@ -33,7 +33,7 @@ def applies(x, weight, stride, padding, dilation, groups, bias) -> bool:
     if weight.dim() != 4 or tuple(weight.shape[2:]) != (3, 3) or weight.shape[0] != weight.shape[1]:
         return False
     C = weight.shape[0]
-    if C not in (16, 32, 64) or (C == 64 and args.own_conv == "tf32x3"):
+    if C not in (16, 32, 64) or C not in tuple(args.own_conv_channels) or (C == 64 and args.own_conv == "tf32x3"):
         return False
     return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] == C
             and x.is_contiguous(memory_format=torch.channels_last) and x.data_ptr() % 16 == 0

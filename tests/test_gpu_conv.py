@@ -35,7 +35,7 @@ def test_conv3x3_forward_backward_vs_fp32_conv2d(mode, tol, N, H, W, C):
     if C == 64 and mode == "tf32x3":
         pytest.skip("C = 64 in TF32X3 mode is not covered (split weights exceed shared memory): library convolution")
     torch.manual_seed(50)
-    aq.set_args(own_conv=mode)
+    aq.set_args(own_conv=mode, own_conv_channels=(16, 32, 64))
     x0 = torch.randn(N, C, H, W, device=DEV).contiguous(memory_format=torch.channels_last)
     w0 = (torch.randn(C, C, 3, 3, device=DEV) * (2.0 / (9 * C)) ** 0.5).contiguous(memory_format=torch.channels_last)
     gy = torch.randn(N, C, H, W, device=DEV).contiguous(memory_format=torch.channels_last)
@@ -59,7 +59,7 @@ def test_conv3x3_forward_backward_vs_fp32_conv2d(mode, tol, N, H, W, C):
 
 def test_conv2d_q_uses_the_kernels_when_it_applies_and_the_library_otherwise():
     torch.manual_seed(51)
-    aq.set_args(variant="A", bitW=8, own_conv="tf32x3")
+    aq.set_args(variant="A", bitW=8, own_conv="tf32x3", own_conv_channels=(16, 32))
     lib = L.load()
     conv = aq.conv2d_Q_fn(8, "second")(32, 32, 3, padding=1, bias=False).to(DEV)
     conv.weight.data = conv.weight.data.contiguous(memory_format=torch.channels_last)

@@ -79,3 +79,115 @@ class _Conv3x3Fn(torch.autograd.Function):
 def conv3x3(x, weight):
     """3x3 / stride 1 / padding 1 convolution on the tcgen05 kernels; call ``applies`` first."""
     return _Conv3x3Fn.apply(x, weight, L.CONV_MODE_ID[args.own_conv])
+
+
+# ------------------------------------------------------------------------------------------------
+# Weight gradients off the critical path.  In the backward pass of a conv layer only the DATA gradient feeds the next
+# layer; the WEIGHT gradient is not needed before the optimizer runs.  With ``args.async_wgrad`` (switched on by
+# QATStep together with the weight bank's batched backward, which is the only consumer of these gradients and runs
+# after ``join()``) every quantized convolution computes its weight gradient on a side stream -- own tcgen05 kernel or
+# the library's -- so the ~40 small, latency-bound weight-gradient kernels of a step overlap the main chain of
+# BatchNorm / quantizer / data-gradient kernels instead of sitting in it.  Fork and join are plain CUDA events, so the
+# whole pattern is captured into the step's CUDA graph as parallel branches.
+class WgradStream:
+    _inst = {}
+
+    def __init__(self, device):
+        self.side = torch.cuda.Stream(device=device)
+        self.keep = []                                # tensors the side stream still reads
+        self.dirty = False
+
+    @classmethod
+    def get(cls, device):
+        key = device.index
+        if key not in cls._inst:
+            cls._inst[key] = cls(device)
+        return cls._inst[key]
+
+    def fork(self, *tensors):
+        main = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self.side.wait_event(ev)
+        self.keep.extend(tensors)
+        self.dirty = True
+        return self.side
+
+    def join(self):
+        """Make the current stream wait for every weight gradient issued so far (call before they are consumed)."""
+        if self.dirty:
+            torch.cuda.current_stream().wait_stream(self.side)
+            self.keep.clear()
+            self.dirty = False
+
+
+def join_wgrads(device=None):
+    for inst in list(WgradStream._inst.values()):
+        inst.join()
+
+
+class _ConvQFn(torch.autograd.Function):
+    """Any bias-free Conv2d_Q convolution with the weight gradient on the side stream."""
+
+    @staticmethod
+    def forward(ctx, x, w, stride, padding, dilation, groups, own, mode):
+        if own:
+            N, C, H, W = x.shape
+            wc = w if w.is_contiguous(memory_format=torch.channels_last) else w.contiguous(memory_format=torch.channels_last)
+            y = torch.empty_like(x)
+            with torch.cuda.device_of(x):
+                L.check(L.load().alignq_conv3x3_fwd(x.data_ptr(), wc.data_ptr(), y.data_ptr(), N, H, W, C, mode, L.stream_ptr()),
+                        "alignq_conv3x3_fwd")
+        else:
+            wc = w
+            y = torch.ops.aten.convolution(x, w, None, stride, padding, dilation, False, (0, 0), groups)
+        ctx.save_for_backward(x, wc)
+        ctx.cfg = (tuple(stride), tuple(padding), tuple(dilation), groups, own, mode)
+        ctx.w_like = w
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, wc = ctx.saved_tensors
+        stride, padding, dilation, groups, own, mode = ctx.cfg
+        lib = L.load()
+        gx = gw = None
+        if own:
+            gy = L.like_layout(gy, x, "grad of conv output")
+        else:
+            gy = gy if gy.is_contiguous(memory_format=torch.channels_last) or gy.is_contiguous() else gy.contiguous()
+        if ctx.needs_input_grad[1]:                   # weight gradient first: it runs beside everything that follows
+            ws_ = WgradStream.get(x.device)
+            side = ws_.fork(x, gy, wc)
+            with torch.cuda.stream(side):
+                if own:
+                    N, C, H, W = x.shape
+                    gw = torch.empty_like(wc)
+                    wsp = _workspace(C, x.device)     # keyed by the side stream: successive launches there are ordered
+                    L.check(lib.alignq_conv3x3_bwd_weight(x.data_ptr(), gy.data_ptr(), gw.data_ptr(), N, H, W, C, mode, 0,
+                                                          wsp.data_ptr(), wsp.numel(), L.stream_ptr()), "alignq_conv3x3_bwd_weight")
+                    if gw.stride() != ctx.w_like.stride():
+                        gw = torch.empty_like(ctx.w_like).copy_(gw)
+                else:
+                    _, gw, _ = torch.ops.aten.convolution_backward(gy, x, wc, None, stride, padding, dilation, False, (0, 0),
+                                                                   groups, (False, True, False))
+                    if gw.stride() != ctx.w_like.stride():           # any layout fix-up belongs on the side stream too
+                        gw = torch.empty_like(ctx.w_like).copy_(gw)
+            ws_.keep.append(gw)
+        if ctx.needs_input_grad[0]:
+            if own:
+                N, C, H, W = x.shape
+                gx = torch.empty_like(x)
+                with torch.cuda.device_of(x):
+                    L.check(lib.alignq_conv3x3_bwd_data(gy.data_ptr(), wc.data_ptr(), gx.data_ptr(), N, H, W, C, mode,
+                                                        L.stream_ptr()), "alignq_conv3x3_bwd_data")
+            else:
+                gx, _, _ = torch.ops.aten.convolution_backward(gy, x, wc, None, stride, padding, dilation, False, (0, 0),
+                                                               groups, (True, False, False))
+        return gx, gw, None, None, None, None, None, None
+
+
+def conv_async_wgrad(x, weight, stride, padding, dilation, groups):
+    own = applies(x, weight, stride, padding, dilation, groups, None)
+    return _ConvQFn.apply(x, weight, tuple(stride), tuple(padding), tuple(dilation), groups, own,
+                          L.CONV_MODE_ID[args.own_conv] if own else 0)

@@ -424,6 +424,9 @@ def conv2d_Q_fn(w_bit, stage, variant=None):
 
         def forward(self, input, order=None):
             weight_q = self.quantize_fn(self.weight)
+            if args.async_wgrad and self.bias is None and input.is_cuda and self.padding_mode == "zeros":
+                from . import conv_tc                                 # weight gradient on a side stream (QATStep joins)
+                return conv_tc.conv_async_wgrad(input, weight_q, self.stride, self.padding, self.dilation, self.groups)
             if args.own_conv != "off":
                 from . import conv_tc
                 if conv_tc.applies(input, weight_q, self.stride, self.padding, self.dilation, self.groups, self.bias):

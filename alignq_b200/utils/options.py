@@ -32,7 +32,7 @@ _DEFAULTS = dict(
     gpus=[0], bitW=2, abitW=2, act_range=2, lam=1.0, lam2=4.0, method="ours", stage="second",
     train_batch_size=128, eval_batch_size=100, lr=0.04, momentum=0.9, weight_decay=1e-4,
     variant="A", gram_mode="fp32", store_weight_attrs=True, fuse_bn_act=False, admm_param_grads=True,
-    dp_gram="replica", sync_bn=False, own_conv="off", own_conv_channels=(16,),
+    dp_gram="replica", sync_bn=False, own_conv="off", own_conv_channels=(16,), async_wgrad=False,
 )
 
 args = SimpleNamespace(**_DEFAULTS)

@@ -69,7 +69,8 @@ class QATStep:
 
     def __init__(self, model, lr=0.04, momentum=0.9, weight_decay=1e-4, lam=None, lam2=None,
                  trans_loss_offset=0.5, process_group=None, world_size=1, bank_weights=True,
-                 channels_last=False, fast_admm=True, single_backward=False, forward_loss=None, keep_logits=False):
+                 channels_last=False, fast_admm=True, single_backward=False, forward_loss=None, keep_logits=False,
+                 async_wgrad=True):
         self.model = model
         if channels_last:                      # NHWC weights: cuDNN needs no layout conversion kernels
             for p in model.parameters():
@@ -100,6 +101,9 @@ class QATStep:
         # cdf_alignment_admm/dann_office/main.py:372-385
         self.forward_loss = forward_loss
         self.keep_logits, self.logits = keep_logits, None       # the training driver reads the step's logits (accuracy)
+        # conv weight gradients on a side stream (model/conv_tc.py): only with the bank's batched backward, the one
+        # consumer of those gradients, which runs after the join in _backward()
+        self.async_wgrad = bool(async_wgrad and self.bank is not None)
         self.pg, self.world = process_group, world_size
         self.all_params = self.params + self.admm_params
         dev = self.params[0].device
@@ -109,6 +113,13 @@ class QATStep:
 
     # -- one eager iteration -------------------------------------------------------------------
     def _iteration(self, x, t):
+        args.async_wgrad = self.async_wgrad                        # read by Conv2d_Q.forward of THIS step's model
+        try:
+            return self._iteration_body(x, t)
+        finally:
+            args.async_wgrad = False
+
+    def _iteration_body(self, x, t):
         for p in self.all_params:                                  # optimizer.zero_grad(): autograd then hands
             p.grad = None                                          # over its gradient buffers without an add
         if self.bank is not None:
@@ -173,6 +184,9 @@ class QATStep:
 
     def _backward(self, loss, retain_graph=False):
         loss.backward(retain_graph=retain_graph)
+        if self.async_wgrad:
+            from ..model.conv_tc import join_wgrads
+            join_wgrads()                                          # side-stream weight gradients -> visible to this stream
         if self.bank is not None:
             self.bank.flush_backward()                             # all weight-quantizer backwards, one launch pair
 

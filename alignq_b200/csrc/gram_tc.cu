@@ -25,12 +25,15 @@
 //       the small cross products have their own accumulator and both are flushed into the fp32 partials every
 //       FLUSH_TILES tiles: fp32-level accuracy independent of F (tested to 1e-5 relative).
 //   ALIGNQ_GRAM_BF16:   kind::f16 with bf16 operands, one MMA per k-step (tested to 1e-2 relative).
+#include <cooperative_groups.h>
 #include <cuda_bf16.h>
 
 #include "common.cuh"
 #include "gram_common.cuh"
 #include "tc_common.cuh"
 #include "../../include/alignq_b200.h"
+
+namespace cg = cooperative_groups;
 
 namespace alignq {
 int gram_tc_small_partials(const float* x, int B, int64_t F, float eps, ActQ q, int fused, float* y, float* partials,
@@ -70,7 +73,12 @@ struct Cfg {
   static constexpr int FLUSH_TILES = TF32 ? 16 : 0;
   static constexpr int STAGE_BYTES = NOPER * TILE_BYTES;
   static constexpr int RED_BYTES = (NW + 1) * KB * 4 * (int)sizeof(float);   // per-warp partials + finished column stats
-  static constexpr int EPI_BYTES = NW * 32 * 33 * (int)sizeof(float);    // per-warp transpose tiles of the epilogue
+  // epilogue scratch: per-warp transpose tiles (global-partials path), or -- tf32 modes, cluster path -- this CTA's whole
+  // accumulators [NACC][128][129] fp32, which the other CTAs of the cluster read through distributed shared memory
+  static constexpr int CL_LD = 129;
+  static constexpr int CL_BYTES = NACC * 128 * CL_LD * (int)sizeof(float);
+  static constexpr bool CLUSTER_OK = TF32;                 // bf16 mode's operand stages are too small to host the tile
+  static constexpr int EPI_BYTES = CLUSTER_OK ? CL_BYTES : NW * 32 * 33 * (int)sizeof(float);
   static constexpr int OPER_BYTES = (2 * STAGE_BYTES > EPI_BYTES) ? 2 * STAGE_BYTES : EPI_BYTES;
   // STAGED: ring of raw x tiles filled by cp.async (16 B, zero-filling) several tiles ahead, so that
   // >= 48 KB per SM are in flight (one register-prefetched tile is only 16 KB: latency-bound at ~1.3 TB/s)
@@ -90,7 +98,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 template <int MODE, bool FUSED, bool STAGED>
 __global__ void __launch_bounds__(NT, 1)
 gram_tc_kernel(const float* __restrict__ x, int B, int64_t F, float eps, ActQ q, float* __restrict__ y,
-               float* __restrict__ partials, int64_t ntiles, double* __restrict__ zero_acc) {
+               float* __restrict__ partials, int64_t ntiles, double* __restrict__ zero_acc, int ncl) {
   using C = Cfg<MODE, FUSED, STAGED>;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* stage_base = smem;
@@ -322,7 +330,51 @@ gram_tc_kernel(const float* __restrict__ x, int B, int64_t F, float eps, ActQ q,
   if (threadIdx.x == 0) umma_commit(&bars[2]);
   mbar_wait(&bars[2], (uint32_t)(nflush & 1));
   tc_fence_after();
-  dump(nflush > 0);
+  if (C::CLUSTER_OK && ncl > 1) {
+    // Split-K reduction INSIDE the cluster (distributed shared memory) instead of through HBM: every CTA parks its
+    // accumulators in its own shared memory, then CTA r of the cluster adds rows [128 r / ncl, 128 (r+1) / ncl) of all
+    // ncl CTAs and writes that slice of ONE partial set per cluster.  With clusters of 8 the partials written (and
+    // re-read by the finish kernel) drop from 128 sets = 16.8 MB to 16 sets = 2.1 MB per layer.  (Only used when the
+    // CTA never flushed mid-way: nflush == 0.)
+    cg::cluster_group cluster = cg::this_cluster();
+    float* mine = reinterpret_cast<float*>(smem);
+    {
+      const int qd = warp & 3, cb = warp >> 2;
+#pragma unroll 1
+      for (int a = 0; a < C::NACC; ++a) {
+#pragma unroll 1
+        for (int col0 = cb * 32; col0 < 128; col0 += (NW / 4) * 32) {
+          uint32_t v[32], w[32];
+          tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + a * C::ACC_COLS + col0, v);
+          tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + a * C::ACC_COLS + 128 + col0, w);
+          float* o = mine + ((size_t)a * 128 + qd * 32 + lane) * C::CL_LD + col0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]) + __uint_as_float(w[j]);
+        }
+      }
+    }
+    tc_fence_before();
+    cluster.sync();                                        // every CTA's tile is complete (and every CTA is resident)
+    const int rank = (int)cluster.block_rank();
+    const int rows = 128 / ncl;
+    float* out = partials + (size_t)(blockIdx.x / ncl) * C::NACC * B * B;
+    for (int e = threadIdx.x; e < C::NACC * rows * 128; e += NT) {
+      const int col = e & 127, rr = (e >> 7) % rows, a = e / (rows * 128);
+      const int row = rank * rows + rr;
+      if (row >= B || col >= B) continue;
+      const size_t off = ((size_t)a * 128 + row) * C::CL_LD + col;
+      float part[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) part[r] = (r < ncl) ? *cluster.map_shared_rank(mine + off, r) : 0.f;   // all loads in flight
+      float sum = 0.f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) sum += part[r];                                        // fixed order: deterministic
+      out[((size_t)a * B + row) * B + col] = sum;
+    }
+    cluster.sync();                                        // nobody leaves while its shared memory is still being read
+  } else {
+    dump(nflush > 0);
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, C::TMEM_COLS);
@@ -476,9 +528,57 @@ static int launch_impl(const float* x, int B, int64_t F, float eps, ActQ q, floa
   cudaError_t e = cudaFuncSetAttribute(gram_tc_kernel<MODE, FUSED, STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
   if (e != cudaSuccess) return (int)e;
   double* zero_acc = (fin && FUSED) ? reinterpret_cast<double*>(ws) : nullptr;
-  gram_tc_kernel<MODE, FUSED, STAGED><<<(unsigned)grid, NT, C::SMEM_BYTES, s>>>(x, B, F, eps, q, y, partials, ntiles, zero_acc);
+  // In-cluster split-K reduction (tf32 modes): clusters of 8 CTAs when no CTA flushes mid-way and the grid divides.
+  int ncl = 1;
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  if (C::CLUSTER_OK && grid >= 16 && (C::FLUSH_TILES == 0 || (ntiles + grid - 1) / grid <= C::FLUSH_TILES)) {
+    // the largest cluster size whose clusters are ALL co-resident (one wave): a cluster needs its SMs inside one GPC,
+    // and with ~220 KB of shared memory per CTA (one CTA per SM) a second wave would double the kernel's time
+    static int best_ncl[2] = {0, 0};                              // per FUSED instantiation (smem differs); benign race
+    int& cached = best_ncl[FUSED ? 1 : 0];
+    if (cached == 0) {
+      cached = 1;
+      for (int cand = 8; cand >= 2; cand >>= 1) {
+        cfg.gridDim = dim3((unsigned)(ALIGNQ_NUM_SMS / cand * cand));
+        cfg.blockDim = dim3(NT);
+        cfg.dynamicSmemBytes = C::SMEM_BYTES;
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = cand; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        int nclusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&nclusters, gram_tc_kernel<MODE, FUSED, STAGED>, &cfg) == cudaSuccess &&
+            nclusters * cand >= 128) { cached = cand; break; }
+        (void)cudaGetLastError();
+      }
+    }
+    ncl = cached;
+    grid -= grid % ncl;                                           // a multiple of the cluster size; tiles are strided over the grid
+  }
+  int nparts = (int)grid;
+  if (ncl > 1) {
+    cfg = cudaLaunchConfig_t{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(NT);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = s;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = ncl;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, gram_tc_kernel<MODE, FUSED, STAGED>, x, B, F, eps, q, y, partials, ntiles, zero_acc, ncl);
+    if (e != cudaSuccess) {                                       // clusters not schedulable here: the global-partials path
+      (void)cudaGetLastError();
+      ncl = 1;
+    } else {
+      nparts = (int)(grid / ncl);
+    }
+  }
+  if (ncl == 1) gram_tc_kernel<MODE, FUSED, STAGED><<<(unsigned)grid, NT, C::SMEM_BYTES, s>>>(x, B, F, eps, q, y, partials, ntiles, zero_acc, 1);
   ALIGNQ_LAUNCH_CHECK();
-  launch_finish_tc(partials, (int)grid, B, F, C::NACC, FUSED ? 1 : 0, G, D, fin, ws, s);
+  launch_finish_tc(partials, nparts, B, F, C::NACC, FUSED ? 1 : 0, G, D, fin, ws, s);
   ALIGNQ_LAUNCH_CHECK();
   return ALIGNQ_OK;
 }

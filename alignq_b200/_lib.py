@@ -69,6 +69,8 @@ SIGNATURES = {
     "alignq_bn_act_fwd_peer": (_I, [_P, _L, _L, _I, _P, _P, _P, _P, _F, _F, _I, _F, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "alignq_bn_act_bwd_peer": (_I, [_P, _P, _P, _L, _L, _I, _P, _P, _P, _P, _I, _F, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "alignq_conv3x3_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "alignq_conv3x3_fwd_bnstats": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P]),
+    "alignq_bn_act_apply": (_I, [_P, _L, _I, _P, _P, _P, _P, _I, _F, _I, _I, _P, _P, _P]),
     "alignq_conv3x3_bwd_data": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "alignq_conv3x3_ws_bytes": (_Z, [_I]),
     "alignq_conv3x3_bwd_weight": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _Z, _P]),

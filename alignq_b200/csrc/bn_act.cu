@@ -22,7 +22,7 @@ namespace alignq {
 
 constexpr int BN_MAX_THREADS = 256;
 constexpr int BN_MAX_GRID = 4 * ALIGNQ_NUM_SMS;
-constexpr int BN_SLOTS = 16;      // accumulator copies: same-address fp64 atomics serialise in L2 (~15 ns each)
+constexpr int BN_SLOTS = ALIGNQ_BN_SLOTS;      // accumulator copies: same-address fp64 atomics serialise in L2 (~15 ns each)
 
 struct BnQ {
   float n, inv_n, ar, gscale;
@@ -597,6 +597,19 @@ extern "C" int alignq_bn_act_fwd(const float* x, int64_t rows, int C, const floa
   ALIGNQ_LAUNCH_CHECK();
   bnq_apply_kernel<<<L.grid * 2, L.threads, 0, s>>>(x, rows, C, gamma, beta, save_mean, save_invstd,
                                                     make_bnq(a_bit, act_range, variant, relu), residual, y);
+  ALIGNQ_LAUNCH_CHECK();
+  return ALIGNQ_OK;
+}
+
+extern "C" int alignq_bn_act_apply(const float* x, int64_t rows, int C, const float* gamma, const float* beta,
+                                   const float* save_mean, const float* save_invstd, int a_bit, float act_range, int variant,
+                                   int relu, const float* residual, float* y, alignq_stream_t stream) {
+  int rc = bn_check(rows, C, a_bit, variant, x, y, residual);
+  if (rc) return rc;
+  if (!x || !y || !save_mean || !save_invstd) return ALIGNQ_EINVAL;
+  const BnLaunch L = bn_launch(rows, C);
+  bnq_apply_kernel<<<L.grid * 2, L.threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, rows, C, gamma, beta, save_mean, save_invstd, make_bnq(a_bit, act_range, variant, relu), residual, y);
   ALIGNQ_LAUNCH_CHECK();
   return ALIGNQ_OK;
 }

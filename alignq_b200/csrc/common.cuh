@@ -9,6 +9,7 @@
 #include <stdint.h>
 
 #define ALIGNQ_NUM_SMS 148
+#define ALIGNQ_BN_SLOTS 16      // copies of the per-channel fp64 accumulators of the fused BatchNorm kernels (bn_act.cu, conv_tc.cu)
 
 enum { ALIGNQ_OK = 0, ALIGNQ_EINVAL = -1, ALIGNQ_EALIGN = -2, ALIGNQ_ERANGE = -3, ALIGNQ_ENOSPACE = -4 };
 

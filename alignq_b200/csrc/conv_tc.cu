@@ -132,10 +132,27 @@ struct FwdCfg {
   static constexpr int W_TAP = C * C * 4;                          // one tap's weight tile, dense K-major
 };
 
-template <int C, int NS, bool FLIP, int MAXI>
+// Batch statistics of the FOLLOWING BatchNorm from the convolution's epilogue (the conv output is in registers there):
+// per-channel sum and sum of squares over the valid output positions, added to the BatchNorm layer's fp64 accumulator
+// copies with the layout of bn_act.cu (ws[(slot * C + c) * 2 + {0: sum, 1: sum of squares}]); the LAST CTA (ticket)
+// finishes mean / invstd / running statistics exactly as bnq_stats_kernel's last block does and re-arms everything.
+// The statistics launch of the fused bn-act forward (~8 us per layer, latency-bound) disappears.
+struct BnStat {
+  double* ws;                  // nullptr: no statistics
+  unsigned* counter;
+  float* running_mean;
+  float* running_var;
+  float* save_mean;
+  float* save_invstd;
+  long long* num_batches_tracked;
+  float momentum, eps;
+  double count;                // N * H * W
+};
+
+template <int C, int NS, bool FLIP, int MAXI, bool STATS>
 __global__ void __launch_bounds__(NT)
 conv3x3_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, float* __restrict__ out, Geo G, int ntiles,
-                   int npt, int PS) {
+                   int npt, int PS, BnStat bs) {
   using F = FwdCfg<C>;
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int W_BYTES = 9 * F::W_TAP;
@@ -185,6 +202,9 @@ conv3x3_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, fl
 
   float4 fv[MAXI][1];
   if ((int)blockIdx.x < ntiles) fetch_items<C, 1, false, MAXI>(in, G, blockIdx.x * F::MT, npt, fv);
+  float st_s[STATS ? C : 1], st_ss[STATS ? C : 1];                 // this thread's positions: per-channel sum, sum of squares
+#pragma unroll
+  for (int c = 0; c < (STATS ? C : 1); ++c) { st_s[c] = 0.f; st_ss[c] = 0.f; }
   int it = 0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
     const int g0 = tile * F::MT;
@@ -251,11 +271,67 @@ conv3x3_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, fl
         if (ok) {
 #pragma unroll
           for (int e = 0; e < 16; e += 4) *reinterpret_cast<float4*>(o + c0 + e) = make_float4(r[e], r[e + 1], r[e + 2], r[e + 3]);
+          if (STATS) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) { st_s[c0 + e] += r[e]; st_ss[c0 + e] = fmaf(r[e], r[e], st_ss[c0 + e]); }
+          }
         }
       }
     }
     tc_fence_before();
     __syncthreads();                                               // accumulators and planes are free again
+  }
+  if (STATS) {
+    // CTA totals: warp shuffles, then the 8 warps through shared memory (the planes are idle) in fp64, one atomic per value
+    double* red = reinterpret_cast<double*>(planes);               // [8 warps][2 C]
+    __shared__ unsigned last_flag;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      float a = st_s[c], b = st_ss[c];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+      if (lane == 0) { red[warp * 2 * C + 2 * c] = (double)a; red[warp * 2 * C + 2 * c + 1] = (double)b; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * C) {
+      double v = 0.0;
+#pragma unroll
+      for (int wv = 0; wv < NT / 32; ++wv) v += red[wv * 2 * C + threadIdx.x];
+      atomicAdd(bs.ws + (size_t)(blockIdx.x % ALIGNQ_BN_SLOTS) * C * 2 + threadIdx.x, v);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned t = atomicAdd(bs.counter, 1u);
+      last_flag = (t == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (last_flag) {
+      __threadfence();
+      for (int c = threadIdx.x; c < C; c += NT) {
+        double S = 0.0, SS = 0.0;
+#pragma unroll
+        for (int sl = 0; sl < ALIGNQ_BN_SLOTS; ++sl) {               // fixed order over the accumulator copies
+          double* a = bs.ws + ((size_t)sl * C + c) * 2;
+          S += __ldcg(a); SS += __ldcg(a + 1);
+          a[0] = 0.0; a[1] = 0.0;                                    // re-arm the accumulators
+        }
+        const double mean = S / bs.count;
+        double var = SS / bs.count - mean * mean;                  // biased: what BN normalises with
+        var = var < 0.0 ? 0.0 : var;
+        bs.save_mean[c] = (float)mean;
+        bs.save_invstd[c] = (float)(1.0 / sqrt(var + (double)bs.eps));
+        if (bs.running_mean) {
+          const double unbiased = bs.count > 1.0 ? var * bs.count / (bs.count - 1.0) : var;
+          bs.running_mean[c] = (float)((1.0 - bs.momentum) * bs.running_mean[c] + bs.momentum * mean);
+          bs.running_var[c] = (float)((1.0 - bs.momentum) * bs.running_var[c] + bs.momentum * unbiased);
+        }
+      }
+      if (threadIdx.x == 0) {
+        *bs.counter = 0u;                                          // re-arm for the next launch
+        if (bs.num_batches_tracked) *bs.num_batches_tracked += 1;
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -469,8 +545,8 @@ inline Geo make_geo(int N, int H, int W) {
   return G;
 }
 
-template <int C, int NS, bool FLIP>
-static int launch_fwd(const float* in, const float* w, float* out, int N, int H, int W, cudaStream_t s) {
+template <int C, int NS, bool FLIP, bool STATS = false>
+static int launch_fwd(const float* in, const float* w, float* out, int N, int H, int W, cudaStream_t s, BnStat bs = BnStat{}) {
   using F = FwdCfg<C>;
   const Geo G = make_geo(N, H, W);
   const int ntiles = (G.npos + F::MT - 1) / F::MT;
@@ -482,14 +558,15 @@ static int launch_fwd(const float* in, const float* w, float* out, int N, int H,
   constexpr int STEP = NT / (C / 4);
   constexpr int MAXI = (F::MT + 2 * 34 + 2 + STEP - 1) / STEP;
   if (npt > MAXI * STEP) return ALIGNQ_ERANGE;                 // wider images: the caller's library convolution
-  cudaError_t e = cudaFuncSetAttribute(conv3x3_fwd_kernel<C, NS, FLIP, MAXI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(conv3x3_fwd_kernel<C, NS, FLIP, MAXI, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   // persistent CTAs (the weights are staged once per CTA): two per SM overlap each other's deposit / MMA / epilogue phases
   int per_sm = (int)((227 * 1024) / (smem + 1024));
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 2) per_sm = 2;
   int grid = ntiles < ALIGNQ_NUM_SMS * per_sm ? ntiles : ALIGNQ_NUM_SMS * per_sm;
-  conv3x3_fwd_kernel<C, NS, FLIP, MAXI><<<grid, NT, smem, s>>>(in, w, out, G, ntiles, npt, PS);
+  bs.count = (double)N * H * W;
+  conv3x3_fwd_kernel<C, NS, FLIP, MAXI, STATS><<<grid, NT, smem, s>>>(in, w, out, G, ntiles, npt, PS, bs);
   ALIGNQ_LAUNCH_CHECK();
   return ALIGNQ_OK;
 }
@@ -560,6 +637,25 @@ extern "C" int alignq_conv3x3_fwd(const float* x, const float* w, float* y, int 
   CONV_DISPATCH(C, ns, CALL);
 #undef CALL
   return ALIGNQ_EINVAL;
+}
+
+extern "C" int alignq_conv3x3_fwd_bnstats(const float* x, const float* w, float* y, int N, int H, int W, int C, int mode,
+                                          float* running_mean, float* running_var, float momentum, float bn_eps,
+                                          float* save_mean, float* save_invstd, double* bn_ws, uint32_t* bn_counter,
+                                          int64_t* num_batches_tracked, alignq_stream_t stream) {
+  int rc = conv_args_ok(x, w, y, N, H, W, C, mode);
+  if (rc) return rc;
+  if (!save_mean || !save_invstd || !bn_ws || !bn_counter) return ALIGNQ_EINVAL;
+  if (C != 16 && C != 32) return ALIGNQ_ERANGE;               // per-thread channel accumulators: narrow layers only
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  BnStat bs{bn_ws, bn_counter, running_mean, running_var, save_mean, save_invstd,
+            reinterpret_cast<long long*>(num_batches_tracked), momentum, bn_eps, 0.0};
+  if (mode == ALIGNQ_CONV_TF32X3) {
+    if (C == 16) return launch_fwd<16, 2, false, true>(x, w, y, N, H, W, s, bs);
+    return launch_fwd<32, 2, false, true>(x, w, y, N, H, W, s, bs);
+  }
+  if (C == 16) return launch_fwd<16, 1, false, true>(x, w, y, N, H, W, s, bs);
+  return launch_fwd<32, 1, false, true>(x, w, y, N, H, W, s, bs);
 }
 
 extern "C" int alignq_conv3x3_bwd_data(const float* gy, const float* w, float* gx, int N, int H, int W, int C, int mode,

@@ -130,26 +130,40 @@ class _ConvQFn(torch.autograd.Function):
     """Any bias-free Conv2d_Q convolution with the weight gradient on the side stream."""
 
     @staticmethod
-    def forward(ctx, x, w, stride, padding, dilation, groups, own, mode):
+    def forward(ctx, x, w, stride, padding, dilation, groups, own, mode, bn=None, bn_ws=None, sync=True):
+        mean = invstd = None
         if own:
             N, C, H, W = x.shape
             wc = w if w.is_contiguous(memory_format=torch.channels_last) else w.contiguous(memory_format=torch.channels_last)
             y = torch.empty_like(x)
             with torch.cuda.device_of(x):
-                L.check(L.load().alignq_conv3x3_fwd(x.data_ptr(), wc.data_ptr(), y.data_ptr(), N, H, W, C, mode, L.stream_ptr()),
-                        "alignq_conv3x3_fwd")
+                if bn is None:
+                    L.check(L.load().alignq_conv3x3_fwd(x.data_ptr(), wc.data_ptr(), y.data_ptr(), N, H, W, C, mode,
+                                                        L.stream_ptr()), "alignq_conv3x3_fwd")
+                else:             # batch statistics of the following BatchNorm from the convolution's epilogue
+                    mean = torch.empty(C, dtype=torch.float32, device=x.device)
+                    invstd = torch.empty(C, dtype=torch.float32, device=x.device)
+                    ws, counter = bn_ws
+                    L.check(L.load().alignq_conv3x3_fwd_bnstats(
+                        x.data_ptr(), wc.data_ptr(), y.data_ptr(), N, H, W, C, mode, L.ptr(bn.running_mean),
+                        L.ptr(bn.running_var), float(bn.momentum), float(bn.eps), mean.data_ptr(), invstd.data_ptr(),
+                        ws.data_ptr(), counter.data_ptr(), L.ptr(bn.num_batches_tracked), L.stream_ptr()),
+                        "alignq_conv3x3_fwd_bnstats")
         else:
             wc = w
             y = torch.ops.aten.convolution(x, w, None, stride, padding, dilation, False, (0, 0), groups)
         ctx.save_for_backward(x, wc)
-        ctx.cfg = (tuple(stride), tuple(padding), tuple(dilation), groups, own, mode)
+        ctx.cfg = (tuple(stride), tuple(padding), tuple(dilation), groups, own, mode, bool(sync))
         ctx.w_like = w
-        return y
+        if bn is None:
+            return y
+        ctx.mark_non_differentiable(mean, invstd)
+        return y, mean, invstd
 
     @staticmethod
-    def backward(ctx, gy):
+    def backward(ctx, gy, *_unused):
         x, wc = ctx.saved_tensors
-        stride, padding, dilation, groups, own, mode = ctx.cfg
+        stride, padding, dilation, groups, own, mode, on_side = ctx.cfg
         lib = L.load()
         gx = gw = None
         if own:
@@ -158,7 +172,7 @@ class _ConvQFn(torch.autograd.Function):
             gy = gy if gy.is_contiguous(memory_format=torch.channels_last) or gy.is_contiguous() else gy.contiguous()
         if ctx.needs_input_grad[1]:                   # weight gradient first: it runs beside everything that follows
             ws_ = WgradStream.get(x.device)
-            side = ws_.fork(x, gy, wc)
+            side = ws_.fork(x, gy, wc) if on_side else torch.cuda.current_stream()
             with torch.cuda.stream(side):
                 if own:
                     N, C, H, W = x.shape
@@ -173,7 +187,8 @@ class _ConvQFn(torch.autograd.Function):
                                                                    groups, (False, True, False))
                     if gw.stride() != ctx.w_like.stride():           # any layout fix-up belongs on the side stream too
                         gw = torch.empty_like(ctx.w_like).copy_(gw)
-            ws_.keep.append(gw)
+            if on_side:
+                ws_.keep.append(gw)
         if ctx.needs_input_grad[0]:
             if own:
                 N, C, H, W = x.shape
@@ -184,10 +199,17 @@ class _ConvQFn(torch.autograd.Function):
             else:
                 gx, _, _ = torch.ops.aten.convolution_backward(gy, x, wc, None, stride, padding, dilation, False, (0, 0),
                                                                groups, (True, False, False))
-        return gx, gw, None, None, None, None, None, None
+        return gx, gw, None, None, None, None, None, None, None, None, None
 
 
 def conv_async_wgrad(x, weight, stride, padding, dilation, groups):
     own = applies(x, weight, stride, padding, dilation, groups, None)
     return _ConvQFn.apply(x, weight, tuple(stride), tuple(padding), tuple(dilation), groups, own,
                           L.CONV_MODE_ID[args.own_conv] if own else 0)
+
+
+def conv_with_bn_stats(x, weight, bn, bn_ws):
+    """Own 3x3 convolution whose epilogue also produces the batch statistics of ``bn`` (training mode): returns
+    (conv output, save_mean, save_invstd).  The weight gradient goes to the side stream when ``args.async_wgrad``."""
+    return _ConvQFn.apply(x, weight, (1, 1), (1, 1), (1, 1), 1, True, L.CONV_MODE_ID[args.own_conv], bn, bn_ws,
+                          bool(args.async_wgrad))

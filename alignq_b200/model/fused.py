@@ -31,21 +31,28 @@ def _bn_ws(bn, C: int, device):
 
 class _BnActFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, bn, a_bit, act_range, variant, relu, residual=None):
+    def forward(ctx, x, weight, bias, bn, a_bit, act_range, variant, relu, residual=None, mean=None, invstd=None):
         B, C, H, W = x.shape
         rows = B * H * W
         training = bool(bn.training or bn.running_mean is None)
         y = torch.empty_like(x)
-        mean = torch.empty(C, dtype=torch.float32, device=x.device)
-        invstd = torch.empty(C, dtype=torch.float32, device=x.device)
+        have_stats = mean is not None          # the producing convolution's epilogue already reduced them
+        if not have_stats:
+            mean = torch.empty(C, dtype=torch.float32, device=x.device)
+            invstd = torch.empty(C, dtype=torch.float32, device=x.device)
         ws, counter = _bn_ws(bn, C, x.device)
         ctx.bn = bn
         with torch.cuda.device_of(x):
-            L.check(L.load().alignq_bn_act_fwd(
-                x.data_ptr(), rows, C, L.ptr(weight), L.ptr(bias), L.ptr(bn.running_mean), L.ptr(bn.running_var),
-                float(bn.momentum), float(bn.eps), int(training), a_bit, act_range, variant, int(relu),
-                L.ptr(residual), y.data_ptr(), mean.data_ptr(), invstd.data_ptr(), ws.data_ptr(), counter.data_ptr(),
-                L.ptr(bn.num_batches_tracked) if training else 0, L.stream_ptr()), "alignq_bn_act_fwd")
+            if have_stats:
+                L.check(L.load().alignq_bn_act_apply(
+                    x.data_ptr(), rows, C, L.ptr(weight), L.ptr(bias), mean.data_ptr(), invstd.data_ptr(), a_bit, act_range,
+                    variant, int(relu), L.ptr(residual), y.data_ptr(), L.stream_ptr()), "alignq_bn_act_apply")
+            else:
+                L.check(L.load().alignq_bn_act_fwd(
+                    x.data_ptr(), rows, C, L.ptr(weight), L.ptr(bias), L.ptr(bn.running_mean), L.ptr(bn.running_var),
+                    float(bn.momentum), float(bn.eps), int(training), a_bit, act_range, variant, int(relu),
+                    L.ptr(residual), y.data_ptr(), mean.data_ptr(), invstd.data_ptr(), ws.data_ptr(), counter.data_ptr(),
+                    L.ptr(bn.num_batches_tracked) if training else 0, L.stream_ptr()), "alignq_bn_act_fwd")
         # y is only needed for the ReLU mask; without ReLU the model files go on to modify it in place
         # (`out += shortcut`, resnet.py:77), so it must not be saved
         ctx.save_for_backward(x, y if relu else None, weight, bias, mean, invstd)
@@ -67,7 +74,7 @@ class _BnActFn(torch.autograd.Function):
                 x.data_ptr(), L.ptr(y), gy.data_ptr(), rows, C, L.ptr(weight), L.ptr(bias), mean.data_ptr(),
                 invstd.data_ptr(), int(training), a_bit, act_range, variant, int(relu), gx.data_ptr(), L.ptr(gr),
                 L.ptr(gw), L.ptr(gb), ws.data_ptr(), counter.data_ptr(), L.stream_ptr()), "alignq_bn_act_bwd")
-        return gx, gw, gb, None, None, None, None, None, gr
+        return gx, gw, gb, None, None, None, None, None, gr, None, None
 
 
 class _SyncBnActFn(torch.autograd.Function):
@@ -215,6 +222,29 @@ def can_fuse(bn, actq, x) -> bool:
             and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
             and x.shape[1] % 4 == 0 and x.shape[1] <= 1024
             and x.is_contiguous(memory_format=torch.channels_last) and x.data_ptr() % 16 == 0)
+
+
+def conv_bn_act(conv, bn, actq, x, relu: bool, residual=None):
+    """``relu(actq(bn(conv(x))) [+ residual])``: when the convolution runs on the own tcgen05 kernels and the bn-act pair is
+    fused, the BatchNorm batch statistics come out of the convolution's epilogue (no statistics launch)."""
+    if (args.own_conv != "off" and bn.training and conv.bias is None and not args.sync_bn
+            and getattr(actq, "opt", None) is None and 1 <= actq.a_bit < 32 and type(bn) is nn.BatchNorm2d
+            and bn.momentum is not None and bool(args.fuse_bn_act) and conv.out_channels in (16, 32)):
+        from . import conv_tc
+        weight_q = conv.quantize_fn(conv.weight)
+        if (conv_tc.applies(x, weight_q, conv.stride, conv.padding, conv.dilation, conv.groups, None)
+                and (residual is None or (residual.shape == x.shape and residual.stride() == x.stride()
+                                          and residual.dtype == torch.float32 and residual.data_ptr() % 16 == 0))):
+            y_conv, mean, invstd = conv_tc.conv_with_bn_stats(x, weight_q, bn, _bn_ws(bn, conv.out_channels, x.device))
+            return _BnActFn.apply(y_conv, bn.weight, bn.bias, bn, actq.a_bit, float(args.act_range),
+                                  L.VARIANT_ID[actq.variant], relu, residual, mean, invstd)
+        # weight_q is already computed: finish the un-fused way without quantizing the weight twice
+        if args.async_wgrad and x.is_cuda and conv.padding_mode == "zeros":
+            y_conv = conv_tc.conv_async_wgrad(x, weight_q, conv.stride, conv.padding, conv.dilation, conv.groups)
+        else:
+            y_conv = F.conv2d(x, weight_q, None, conv.stride, conv.padding, conv.dilation, conv.groups)
+        return bn_act(bn, actq, y_conv, relu, residual)
+    return bn_act(bn, actq, conv(x), relu, residual)
 
 
 def bn_act(bn, actq, x, relu: bool, residual=None):

@@ -12,7 +12,7 @@ import torch.nn.functional as F
 
 from ..utils.admm import ADMM
 from ..utils.options import args
-from .fused import bn_act
+from .fused import bn_act, conv_bn_act
 from .quantization import activation_quantize_fn, conv2d_Q_fn
 
 
@@ -51,8 +51,8 @@ class PreActBlock_conv_Q(nn.Module):
     def forward(self, x):
         if not self.with_admm:
             shortcut = x if self.skip_conv is None else bn_act(self.skip_bn, self.act_skip_q, self.skip_conv(x), False)
-            out = bn_act(self.bn0, self.act_q0, self.conv0(x), True)       # relu(act_q0(bn0(.)))
-            return bn_act(self.bn1, self.act_q1, self.conv1(out), True, residual=shortcut)   # relu(act_q1(.) + shortcut)
+            out = conv_bn_act(self.conv0, self.bn0, self.act_q0, x, True)      # relu(act_q0(bn0(conv0(x))))
+            return conv_bn_act(self.conv1, self.bn1, self.act_q1, out, True, residual=shortcut)   # relu(act_q1(.) + shortcut)
         trans_loss = 0.
         shortcut = x
         if self.skip_conv is not None:

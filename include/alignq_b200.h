@@ -229,6 +229,17 @@ int alignq_conv3x3_fwd(const float* x, const float* w, float* y, int N, int H, i
                        alignq_stream_t stream);
 int alignq_conv3x3_bwd_data(const float* gy, const float* w, float* gx, int N, int H, int W, int C, int mode,
                             alignq_stream_t stream);
+/* The forward convolution with the batch statistics of the FOLLOWING BatchNorm2d taken from its epilogue (C in {16, 32}):
+ * save_mean / save_invstd [C] out, running statistics updated (nullable), *num_batches_tracked += 1 (nullable); bn_ws /
+ * bn_counter are that BatchNorm layer's alignq_bn_act_* workspace (same accumulator layout, same last-block finalisation).
+ * Follow it with alignq_bn_act_apply (the apply pass alone) instead of alignq_bn_act_fwd.                              */
+int alignq_conv3x3_fwd_bnstats(const float* x, const float* w, float* y, int N, int H, int W, int C, int mode,
+                               float* running_mean, float* running_var, float momentum, float bn_eps, float* save_mean,
+                               float* save_invstd, double* bn_ws, uint32_t* bn_counter, int64_t* num_batches_tracked,
+                               alignq_stream_t stream);
+int alignq_bn_act_apply(const float* x, int64_t rows, int C, const float* gamma, const float* beta, const float* save_mean,
+                        const float* save_invstd, int a_bit, float act_range, int variant, int relu, const float* residual,
+                        float* y, alignq_stream_t stream);
 size_t alignq_conv3x3_ws_bytes(int C);
 int alignq_conv3x3_bwd_weight(const float* x, const float* gy, float* gw, int N, int H, int W, int C, int mode,
                               int accumulate, void* ws, size_t ws_bytes, alignq_stream_t stream);

@@ -78,3 +78,41 @@ def test_conv2d_q_uses_the_kernels_when_it_applies_and_the_library_otherwise():
         assert lib.alignq_launch_count() - n1 == 2                    # only the weight quantizer: library convolution
     strided = aq.conv2d_Q_fn(8, "second")(32, 32, 3, stride=2, padding=1, bias=False).to(DEV)
     assert not conv_tc.applies(x, strided.weight, strided.stride, strided.padding, strided.dilation, 1, None)
+
+
+@pytest.mark.parametrize("C,H", [(16, 32), (32, 16)])
+def test_conv_epilogue_bn_statistics_match_the_bn_act_statistics_pass(C, H):
+    """alignq_conv3x3_fwd_bnstats + alignq_bn_act_apply == alignq_conv3x3_fwd + alignq_bn_act_fwd: the BatchNorm batch
+    statistics taken from the convolution's epilogue (one launch fewer per layer) against the fused kernels' own statistics
+    pass -- save_mean / save_invstd / running statistics to fp32 round-off, activation codes equal up to BN-output ties."""
+    import copy
+    from alignq_b200.model.fused import bn_act, conv_bn_act
+    torch.manual_seed(52)
+    aq.set_args(variant="A", bitW=8, abitW=8, act_range=2, fuse_bn_act=True, own_conv="tf32x3", own_conv_channels=(16, 32),
+                method="none")
+    conv = aq.conv2d_Q_fn(8, "second")(C, C, 3, padding=1, bias=False).to(DEV)
+    conv.weight.data = conv.weight.data.contiguous(memory_format=torch.channels_last)
+    bn = torch.nn.BatchNorm2d(C).to(DEV).train()
+    with torch.no_grad():
+        bn.weight.copy_(1 + 0.2 * torch.randn(C))
+        bn.bias.copy_(0.1 * torch.randn(C))
+    bn2, conv2 = copy.deepcopy(bn), copy.deepcopy(conv)
+    q = aq.activation_quantize_fn(8, "second")
+    x0 = torch.randn(64, C, H, H, device=DEV).contiguous(memory_format=torch.channels_last)
+    r0 = torch.randn(64, C, H, H, device=DEV).contiguous(memory_format=torch.channels_last)
+    gy = torch.randn_like(x0)
+    x, r = x0.clone().requires_grad_(True), r0.clone().requires_grad_(True)
+    y = conv_bn_act(conv, bn, q, x, True, residual=r)                                # statistics from the conv epilogue
+    (y * gy).sum().backward()
+    x2, r2 = x0.clone().requires_grad_(True), r0.clone().requires_grad_(True)
+    y2 = bn_act(bn2, q, conv2(x2), True, residual=r2)                                # conv, then stats + apply launches
+    (y2 * gy).sum().backward()
+    assert torch.allclose(bn.running_mean, bn2.running_mean, rtol=1e-5, atol=1e-7)
+    assert torch.allclose(bn.running_var, bn2.running_var, rtol=1e-5, atol=1e-7)
+    assert int(bn.num_batches_tracked) == 1
+    bad = int(((y - y2).abs() > 1e-6).sum())
+    assert bad <= max(2, int(1e-5 * y.numel())), f"{bad} codes differ"
+    same = (y - y2).abs() <= 1e-6
+    assert relmax(x.grad, x2.grad) <= 1e-4 and relmax(conv.weight.grad, conv2.weight.grad) <= 1e-4
+    assert relmax(r.grad * same, r2.grad * same) <= 1e-6
+    assert relmax(bn.weight.grad, bn2.weight.grad) <= 1e-4

@@ -121,8 +121,10 @@ class WgradStream:
             self.dirty = False
 
 
-def join_wgrads(device=None):
+def join_wgrads(bank=None):
     for inst in list(WgradStream._inst.values()):
+        if bank is not None and inst.dirty:
+            bank.finish_dp_reduce(inst.side)
         inst.join()
 
 
@@ -155,6 +157,7 @@ class _ConvQFn(torch.autograd.Function):
         ctx.save_for_backward(x, wc)
         ctx.cfg = (tuple(stride), tuple(padding), tuple(dilation), groups, own, mode, bool(sync))
         ctx.w_like = w
+        ctx.gup = getattr(w, "_alignq_gup", None) if sync else None    # (WeightBank, layer index) or None
         if bn is None:
             return y
         ctx.mark_non_differentiable(mean, invstd)
@@ -173,10 +176,15 @@ class _ConvQFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:                   # weight gradient first: it runs beside everything that follows
             ws_ = WgradStream.get(x.device)
             side = ws_.fork(x, gy, wc) if on_side else torch.cuda.current_stream()
+            slot = None
+            if ctx.gup is not None:                   # the bank's flat upstream-gradient buffer: this layer's slice
+                slot = ctx.gup[0].gup[ctx.gup[1]]
+                if slot.shape != wc.shape or slot.stride() != wc.stride() or slot.data_ptr() % 16:
+                    slot = None
             with torch.cuda.stream(side):
                 if own:
                     N, C, H, W = x.shape
-                    gw = torch.empty_like(wc)
+                    gw = slot if slot is not None else torch.empty_like(wc)
                     wsp = _workspace(C, x.device)     # keyed by the side stream: successive launches there are ordered
                     L.check(lib.alignq_conv3x3_bwd_weight(x.data_ptr(), gy.data_ptr(), gw.data_ptr(), N, H, W, C, mode, 0,
                                                           wsp.data_ptr(), wsp.numel(), L.stream_ptr()), "alignq_conv3x3_bwd_weight")
@@ -185,8 +193,12 @@ class _ConvQFn(torch.autograd.Function):
                 else:
                     _, gw, _ = torch.ops.aten.convolution_backward(gy, x, wc, None, stride, padding, dilation, False, (0, 0),
                                                                    groups, (False, True, False))
-                    if gw.stride() != ctx.w_like.stride():           # any layout fix-up belongs on the side stream too
+                    if slot is not None:
+                        gw = slot.copy_(gw)
+                    elif gw.stride() != ctx.w_like.stride():         # any layout fix-up belongs on the side stream too
                         gw = torch.empty_like(ctx.w_like).copy_(gw)
+                if slot is not None:                  # data parallel: this bucket's all-reduce may start right here
+                    ctx.gup[0].wgrad_deposited(ctx.gup[1])
             if on_side:
                 ws_.keep.append(gw)
         if ctx.needs_input_grad[0]:

@@ -32,6 +32,13 @@ def WeightBank_applies(model) -> bool:
     return bool(qs) and len({(q.w_bit, q.variant) for q in qs}) == 1
 
 
+def single_backward_ok(step) -> bool:
+    """The side-stream all-reduce of the upstream weight gradients assumes ONE backward pass per step (with two, e.g.
+    CE.backward(retain_graph=True) then trans_loss.backward(), a bucket would be reduced after the first pass only)."""
+    has_admm = bool(step.admm_params)
+    return (not has_admm) or step.single_backward
+
+
 def quantized_convs(model):
     """Conv2d_Q / Linear_Q modules in registration order."""
     return [m for m in model.modules() if hasattr(m, "quantize_fn") and hasattr(m, "weight")]
@@ -105,6 +112,16 @@ class QATStep:
         # consumer of those gradients, which runs after the join in _backward()
         self.async_wgrad = bool(async_wgrad and self.bank is not None)
         self.pg, self.world = process_group, world_size
+        # data parallel + side-stream weight gradients: the bank's upstream gradients are all-reduced on the side stream,
+        # bucket by bucket, while the backward chain is still running (WeightBank.enable_dp_overlap)
+        # NOT together with the in-kernel peer exchange of the BatchNorm sums: parallel branches of a CUDA graph (and
+        # streams sharing a hardware queue) may be serialised by the driver, and then rank A's NCCL kernel, queued in front
+        # of its BatchNorm kernel k, waits for rank B's NCCL kernel, which is queued behind B's BatchNorm kernel k that
+        # spins for A's: a cross-GPU deadlock (seen on 2 GPUs: the bounded spin trapped).  Kernels that wait for another
+        # GPU must all sit in ONE stream order.
+        self.dp_overlap = bool(self.world > 1 and self.async_wgrad and single_backward_ok(self) and args.sync_bn != "peer")
+        if self.dp_overlap:
+            self.bank.enable_dp_overlap(self.pg, self.world)
         self.all_params = self.params + self.admm_params
         dev = self.params[0].device
         self.graph = None
@@ -155,7 +172,8 @@ class QATStep:
                 # all-reduced in place, and only the few small remaining gradients (BatchNorm, first conv, classifier)
                 # are gathered -- no torch.cat over the model's weights, no re-pointing of their p.grad
                 banked = {id(p) for p, g in zip(self.bank.params, self.bank.gw) if p.grad is g}
-                allreduce_sum_(self.bank.gw_flat, self.pg)
+                if not self.dp_overlap:                            # (overlap mode: already summed over the ranks on the side
+                    allreduce_sum_(self.bank.gw_flat, self.pg)     #  stream, before the quantizer backward, which is linear)
                 owners = [p for p in owners if id(p) not in banked]
             for p in owners:                                       # gather (physical order) -> all-reduce -> views
                 if p.grad.stride() != p.stride():
@@ -186,7 +204,7 @@ class QATStep:
         loss.backward(retain_graph=retain_graph)
         if self.async_wgrad:
             from ..model.conv_tc import join_wgrads
-            join_wgrads()                                          # side-stream weight gradients -> visible to this stream
+            join_wgrads(self.bank if self.dp_overlap else None)    # side-stream weight gradients -> visible to this stream
         if self.bank is not None:
             self.bank.flush_backward()                             # all weight-quantizer backwards, one launch pair
 

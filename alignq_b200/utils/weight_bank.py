@@ -28,7 +28,11 @@ class _BankSliceFn(torch.autograd.Function):
         ctx.set_materialize_grads(False)
         # a fresh alias: autograd attaches grad_fn to the returned object, and attaching it to the bank's
         # persistent view would keep every iteration's graph (and its AccumulateGrad nodes) alive
-        return bank.wq[i].detach()
+        out = bank.wq[i].detach()
+        # where a side-stream weight-gradient kernel may deposit d loss / d weight_q of this layer directly (its slice
+        # of the bank's flat upstream-gradient buffer), and whom to tell (model/conv_tc.py:_ConvQFn)
+        out._alignq_gup = (bank, i)
+        return out
 
     @staticmethod
     def backward(ctx, g):
@@ -98,8 +102,73 @@ class WeightBank:
         self.gw_flat = torch.zeros_like(self.flat)
         self.gw = view(self.gw_flat)
         self.bwd_ws = torch.empty(2 * self.nchunks, dtype=torch.float64, device=dev)
+        # upstream gradients d loss / d weight_q, one flat buffer with the bank's segmentation: the conv layers' weight-
+        # gradient kernels write their slices on the side stream, and in data-parallel runs the slices are all-reduced
+        # THERE, bucket by bucket while the main backward chain is still running (the quantizer backward is linear in the
+        # upstream gradient and the weights are replicated, so reducing before or after it is the same sum)
+        self.gup_flat = torch.zeros_like(self.flat)
+        self.gup = view(self.gup_flat)
+        self.dp_group, self.dp_world = None, 1
+        self.buckets, self.bucket_of = [], []
+        self.done = [False] * len(params)
+        self.reduced = [False] * 0
         for i, q in enumerate(self.fns):
             q._bank = (self, i)
+
+    def enable_dp_overlap(self, group, world, nbuckets=3):
+        """Data parallel: all-reduce the upstream weight gradients on the side stream in `nbuckets` contiguous layer
+        ranges of roughly equal size, each as soon as all of its layers have deposited."""
+        self.dp_group, self.dp_world = group, int(world)
+        n = len(self.params)
+        total = self.flat.numel()
+        self.buckets, self.bucket_of = [], [0] * n
+        lo = 0
+        for b in range(nbuckets):
+            target = total * (b + 1) // nbuckets
+            hi = lo
+            while hi < n and (self.seg_off_host[hi + 1] <= target or hi == lo):
+                hi += 1
+            if b == nbuckets - 1:
+                hi = n
+            if hi > lo:
+                self.buckets.append((lo, hi))
+                for i in range(lo, hi):
+                    self.bucket_of[i] = len(self.buckets) - 1
+            lo = hi
+        self.reduced = [False] * len(self.buckets)
+
+    def begin_step(self):
+        self.done = [False] * len(self.params)
+        self.reduced = [False] * len(self.buckets)
+
+    def _reduce_bucket(self, b):
+        import torch.distributed as dist
+        lo, hi = self.buckets[b]
+        a, e = self.seg_off_host[lo], self.seg_off_host[hi]
+        dist.all_reduce(self.gup_flat[a:e], op=dist.ReduceOp.SUM, group=self.dp_group)
+        self.reduced[b] = True
+
+    def wgrad_deposited(self, i):
+        """Called on the SIDE stream right after layer i's weight-gradient kernel was enqueued there."""
+        self.done[i] = True
+        if self.dp_world > 1 and self.buckets:
+            b = self.bucket_of[i]
+            lo, hi = self.buckets[b]
+            if not self.reduced[b] and all(self.done[lo:hi]):
+                self._reduce_bucket(b)
+
+    def finish_dp_reduce(self, side_stream):
+        """Before the join: buckets whose layers did not all run through the side stream (e.g. a layer without gradient)
+        are reduced now, on the side stream; slices of layers that never deposited are zero."""
+        if self.dp_world > 1 and self.buckets:
+            with torch.cuda.stream(side_stream):
+                for b in range(len(self.buckets)):
+                    if not self.reduced[b]:
+                        lo, hi = self.buckets[b]
+                        for i in range(lo, hi):
+                            if not self.done[i]:
+                                self.gup[i].zero_()
+                        self._reduce_bucket(b)
 
     def quantize_all(self):
         """One multi-tensor launch pair for every weight of the model (call before the forward)."""
@@ -111,6 +180,7 @@ class WeightBank:
                 self.cdf_flat.data_ptr() if want else 0, self.pdf_flat.data_ptr() if want else 0, 0,
                 self.stats.data_ptr(), self.ws.data_ptr(), L.stream_ptr()), "alignq_wq_forward (bank)")
         self.fresh = True
+        self.begin_step()
         if self.batched_backward:
             self.gw_flat.zero_()                           # flush_backward() always accumulates
 

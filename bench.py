@@ -571,6 +571,26 @@ def run_product(args):
         except Exception as e:                              # pragma: no cover - evidence block, never fatal
             dp_parity = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
 
+    local_bn = None
+    if world > 1 and sync_bn and args.workload == "resnet20" and not args.no_local_bn_line:
+        # the same data-parallel step with PER-RANK BatchNorm statistics (plain DDP semantics: every rank = the reference
+        # at batch 128) and the gradient all-reduce overlapped with the backward -- beside the global-batch number above
+        aq.set_args(sync_bn=False)
+        torch.manual_seed(0)
+        m3 = make_model().to(dev).train()
+        st3 = QATStep(m3, lr=0.04, momentum=0.9, weight_decay=1e-4, world_size=world, channels_last=not args.nchw,
+                      single_backward=True)
+        if graphed:
+            st3.capture(dev_x[0], dev_t[0], warmup=3)
+        k3 = min(args.steps, 100)
+        ms3, _ = timed(k3, 5, host_inputs=False, st=st3)
+        t3 = torch.tensor([ms3], dtype=torch.float64, device=dev)
+        dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+        local_bn = {"value": world * batch * k3 / (float(t3[0]) * 1e-3), "unit": "img/s", "ms_per_step": float(t3[0]) / k3, "steps": k3,
+                    "what": "same N-GPU step with per-rank BatchNorm statistics (no statistics exchange) and the gradient "
+                            "all-reduce overlapped with the backward on the side stream"}
+        aq.set_args(sync_bn=args.sync_bn_impl)
+
     fused_parity = no_fuse = None
     if rank == 0 and world == 1 and fuse and args.workload == "resnet20":
         fused_parity = fused_code_mismatch(dev)
@@ -607,7 +627,7 @@ def run_product(args):
                 "gpu_launches": int(launches_per_step) * args.steps,
                 "gpu_launches_per_step": int(launches_per_step),
                 "clocks": clocks, "roofline": roofline, "gram_tensor_roofline": gram, "cpu_baseline": cpu,
-                "fused_bn_act_parity": fused_parity, "no_fuse": no_fuse, "dp_parity": dp_parity}
+                "fused_bn_act_parity": fused_parity, "no_fuse": no_fuse, "dp_parity": dp_parity, "local_bn": local_bn}
         print(json.dumps(line), flush=True)
     if world > 1:
         # Tear down without NCCL's communicator destructor: with captured NCCL kernels still referenced
@@ -646,6 +666,7 @@ def main():
                     "of cuDNN under torch's default allow_tf32), tf32x3 (fp32 parity) or off (cuDNN everywhere)")
     ap.add_argument("--own-conv-channels", type=str, default="16", help="channel counts (Cin == Cout) routed to the own kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-local-bn-line", action="store_true", help="N>1: skip the extra timing with per-rank BatchNorm statistics")
     ap.add_argument("--no-dp-parity", action="store_true", help="N>1: skip the N-rank vs single-device parity block")
     ap.add_argument("--no-fuse", action="store_true", help="run BatchNorm / quantizer / ReLU as separate kernels "
                     "(default with channels_last: the fused bn->act-quant->relu kernels, SURVEY 8f-1)")

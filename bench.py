@@ -50,7 +50,7 @@ def peaks():
 def ncu_traffic_bytes():
     """DRAM bytes of one fwd + one bwd launch from the committed `ncu --set full` capture (or None)."""
     try:
-        rows = json.load(open(os.path.join(REPO, "profiles", "r01_ncu_full_act_kernels.json")))
+        rows = json.load(open(os.path.join(REPO, "profiles", "r02_ncu_full_act_kernels.json")))
         tot = 0.0
         for r in rows:
             for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
@@ -519,7 +519,7 @@ def run_product(args):
         peak, how = peaks()
         achieved = 20.0 * n / ((tf + tb) * 1e-3) / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": ncu_traffic_bytes(), "traffic_source": "profiles/r01_ncu_full_act_kernels.json "
+                    "traffic": ncu_traffic_bytes(), "traffic_source": "profiles/r02_ncu_full_act_kernels.json "
                     "(dram__bytes_read.sum + dram__bytes_write.sum of one fwd + one bwd launch on this input; "
                     "algorithmic = 5.369e9 B)", "peak_source": how,
                     "kernel": "act_fwd_vec_kernel + act_bwd_vec_kernel (CDF quantizer fwd + fused STE bwd)",

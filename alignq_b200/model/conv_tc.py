@@ -91,10 +91,14 @@ def conv3x3(x, weight):
 # whole pattern is captured into the step's CUDA graph as parallel branches.
 class WgradStream:
     _inst = {}
+    NSTREAMS = 3          # round-robin: the weight-gradient kernels of neighbouring layers also overlap EACH OTHER, which
+                          # shortens the tail left when the main backward chain ends (the largest ones are issued last)
 
     def __init__(self, device):
-        self.side = torch.cuda.Stream(device=device)
-        self.keep = []                                # tensors the side stream still reads
+        self.sides = [torch.cuda.Stream(device=device) for _ in range(self.NSTREAMS)]
+        self.side = self.sides[0]                     # the stream data-parallel bucket reductions are issued on
+        self.next = 0
+        self.keep = []                                # tensors the side streams still read
         self.dirty = False
 
     @classmethod
@@ -104,21 +108,26 @@ class WgradStream:
             cls._inst[key] = cls(device)
         return cls._inst[key]
 
-    def fork(self, *tensors):
+    def fork(self, *tensors, single=False):
         main = torch.cuda.current_stream()
         ev = torch.cuda.Event()
         ev.record(main)
-        self.side.wait_event(ev)
+        side = self.sides[0] if single else self.sides[self.next % self.NSTREAMS]
+        self.next += 1
+        side.wait_event(ev)
         self.keep.extend(tensors)
         self.dirty = True
-        return self.side
+        return side
 
     def join(self):
         """Make the current stream wait for every weight gradient issued so far (call before they are consumed)."""
         if self.dirty:
-            torch.cuda.current_stream().wait_stream(self.side)
+            main = torch.cuda.current_stream()
+            for sd in self.sides:
+                main.wait_stream(sd)
             self.keep.clear()
             self.dirty = False
+            self.next = 0
 
 
 def join_wgrads(bank=None):
@@ -175,7 +184,9 @@ class _ConvQFn(torch.autograd.Function):
             gy = gy if gy.is_contiguous(memory_format=torch.channels_last) or gy.is_contiguous() else gy.contiguous()
         if ctx.needs_input_grad[1]:                   # weight gradient first: it runs beside everything that follows
             ws_ = WgradStream.get(x.device)
-            side = ws_.fork(x, gy, wc) if on_side else torch.cuda.current_stream()
+            # (data-parallel bucket reductions are issued behind the deposits: those layers all use side stream 0)
+            dp = ctx.gup is not None and ctx.gup[0].dp_world > 1 and bool(ctx.gup[0].buckets)
+            side = ws_.fork(x, gy, wc, single=dp) if on_side else torch.cuda.current_stream()
             slot = None
             if ctx.gup is not None:                   # the bank's flat upstream-gradient buffer: this layer's slice
                 slot = ctx.gup[0].gup[ctx.gup[1]]

@@ -244,6 +244,19 @@ size_t alignq_conv3x3_ws_bytes(int C);
 int alignq_conv3x3_bwd_weight(const float* x, const float* gy, float* gw, int N, int H, int W, int C, int mode,
                               int accumulate, void* ws, size_t ws_bytes, alignq_stream_t stream);
 
+/* ---- LMMD loss of the DSAN head (cdf_alignment_admm/dsan_office/utils/mmd.py:9-41) ------------------------------
+ * total = cat(source, target) [n, d] fp32; W [n, n] = [[w_ss, -w_st], [-w_st^T, w_tt]] (the label weights of
+ * utils/Weight.py:10-59, signed and assembled by the caller): loss = sum_ij W_ij K_ij with K the sum of kernel_num
+ * Gaussian kernels of the pairwise squared distances (bandwidth = mean distance, a constant; fix_sigma > 0 overrides),
+ * and 0 when K contains a NaN (mmd.py:33-34).  coef [n, n] out: what alignq_lmmd_bwd needs;
+ * ws: alignq_lmmd_ws_bytes(n) bytes whose first 32 bytes are ZERO on entry (kept for the backward).
+ * Backward: g_total = *gloss * d loss / d total (gloss a DEVICE scalar, NULL = 1).                                  */
+size_t alignq_lmmd_ws_bytes(int n);
+int alignq_lmmd_fwd(const float* total, int n, int d, const float* W, float kernel_mul, int kernel_num, float fix_sigma,
+                    float* loss, float* coef, void* ws, size_t ws_bytes, alignq_stream_t stream);
+int alignq_lmmd_bwd(const float* total, int n, int d, const float* coef, const float* gloss, const void* ws,
+                    float* g_total, alignq_stream_t stream);
+
 /* Data-parallel SyncBN inside the fused kernels (BASELINE.json north_star (3): "(sum, sum-of-squares) ... combined with
  * NCCL all-reduce ... so global statistics match the single-device reference"): the same kernels, cut where the ranks'
  * fp64 sums are exchanged.  The caller all-reduces `sums` ([2 C] doubles: per-channel sum and sum of squares forward;

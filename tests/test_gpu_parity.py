@@ -761,3 +761,33 @@ def test_linear_q_forward_backward_vs_oracle(variant):
         assert lin.w_bit == 8 and lin.quantize_fn.weight_pdf.shape == lin.weight.shape
     finally:
         torch.backends.cuda.matmul.allow_tf32 = old
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_lmmd_golden_and_fp64_autograd(tag):
+    """lmmd (cdf_alignment_admm/dsan_office/utils/mmd.py:24-41) on the CUDA kernels: loss vs the reference's golden value,
+    gradients vs the oracle's fp64 autograd at north_star's 1e-5 (with the reference's own fp32 floor)."""
+    import os
+    from alignq_b200.utils import mmd as M
+    from oracle import mmd_oracle as MO
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mmd.npz"))
+    src0, tgt0 = t(g[f"{tag}_src"]).to(DEV), t(g[f"{tag}_tgt"]).to(DEV)
+    s_label, t_prob = t(g[f"{tag}_s_label"]).to(DEV), t(g[f"{tag}_t_prob"]).to(DEV)
+    src, tgt = src0.clone().requires_grad_(True), tgt0.clone().requires_grad_(True)
+    loss = M.lmmd(src, tgt, s_label, t_prob)
+    assert loss.shape == (1,)
+    (loss * 1.7).sum().backward()
+    ref = float(t(g[f"{tag}_loss"]))
+    if tag == "c":                                               # no class shared by source labels and target predictions
+        assert float(loss) == 0.0 and float(src.grad.abs().max()) == 0.0
+        return
+    s64c, t64c = src0.double().cpu().clone().requires_grad_(True), tgt0.double().cpu().clone().requires_grad_(True)
+    l64 = MO.lmmd(s64c, t64c, s_label.cpu(), t_prob.cpu())
+    (l64 * 1.7).sum().backward()
+    assert abs(float(loss.detach()) - float(l64.detach())) <= 1e-5 * abs(float(l64.detach())) + 1e-7
+    assert abs(float(loss.detach()) - ref) <= 2e-5 * abs(ref) + 1e-6       # the golden is the reference's fp32 CPU value
+    grad_close(src.grad.cpu(), s64c.grad, t(g[f"{tag}_gs"]), what=f"lmmd g_source {tag}")
+    grad_close(tgt.grad.cpu(), t64c.grad, t(g[f"{tag}_gt"]), what=f"lmmd g_target {tag}")
+    K = M.guassian_kernel(src0, tgt0)
+    rel_close(K.cpu(), t(g[f"{tag}_K"]), rtol=1e-5, atol_frac=1e-6, what="guassian_kernel")

@@ -91,12 +91,13 @@ lmmd_bwd_kernel(const float* __restrict__ total, int n, int d, const float* __re
   const int i = blockIdx.x;
   for (int j = threadIdx.x; j < n; j += blockDim.x) crow[j] = coef[(size_t)i * n + j];
   __syncthreads();
-  const float g = (ws[1] != 0.0) ? 0.f : 2.0f * (gloss ? __ldg(gloss) : 1.0f);
+  const bool dead = ws[1] != 0.0;
+  const float g = 2.0f * (gloss ? __ldg(gloss) : 1.0f);
   for (int k = threadIdx.x; k < d; k += blockDim.x) {
     const float ti = total[(size_t)i * d + k];
     float s = 0.f;
     for (int j = 0; j < n; ++j) s = fmaf(crow[j], ti - total[(size_t)j * d + k], s);
-    g_total[(size_t)i * d + k] = g * s;
+    g_total[(size_t)i * d + k] = dead ? 0.f : g * s;
   }
 }
 

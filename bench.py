@@ -447,6 +447,50 @@ def run_product(args):
         step.step(dev_x[0], dev_t[0])
         launches_per_step = lib.alignq_launch_count() - c0
 
+    if args.timeline:                                      # dev aid: CUPTI timeline of graph replays (real overlap, real gaps), then exit
+        import collections
+        from torch.profiler import profile, ProfilerActivity
+        for _ in range(5):
+            flush.zero_()
+            step.step(dev_x[0], dev_t[0])
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(3):
+                flush.zero_()
+                step.step(dev_x[0], dev_t[0])
+                torch.cuda.synchronize()
+        evs = sorted(((e.time_range.start, e.time_range.end, e.name) for e in prof.events()
+                      if getattr(e.device_type, "name", "") == "CUDA"), key=lambda r: r[0])
+        # split at the L2-flush fills (the only 256 MiB FillFunctor<unsigned char> launches)
+        steps_, cur = [], []
+        for a, b, n in evs:
+            if "FillFunctor<unsigned char>" in n:
+                if cur:
+                    steps_.append(cur)
+                cur = []
+            elif "Memcpy" not in n and "Memset" not in n:
+                cur.append((a, b, n))
+        if cur:
+            steps_.append(cur)
+        last = steps_[-1]
+        t0, t1 = last[0][0], max(b for _, b, _ in last)
+        busy, cover_end, agg = 0.0, t0, collections.defaultdict(lambda: [0, 0.0])
+        for a, b, n in last:
+            if b > cover_end:
+                busy += b - max(a, cover_end)
+                cover_end = b
+            agg[n[:90]][0] += 1
+            agg[n[:90]][1] += b - a
+        lines = [f"# {args.workload}: one graph replay under CUPTI: span {t1 - t0:.1f} us, device busy (union over streams) {busy:.1f} us, "
+                 f"idle {t1 - t0 - busy:.1f} us, sum of kernel durations {sum(v[1] for v in agg.values()):.1f} us, {len(last)} kernels"]
+        lines += [f"{d:9.1f} us x{c:4d}  {k}" for k, (c, d) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]]
+        lines.append("# timeline (start us, dur us, name)")
+        lines += [f"{a - t0:9.1f} {b - a:7.1f}  {n[:100]}" for a, b, n in last]
+        os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)
+        open(os.path.join(REPO, "gpurun_out", f"timeline_{args.workload}.txt"), "w").write("\n".join(lines) + "\n")
+        print("\n".join(lines[:50]), file=sys.stderr)
+        os._exit(0)
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -649,6 +693,7 @@ def main():
                     help="default resnet20 = BASELINE.json configs[0] (the metric's workload); the others are configs[1..3], "
                     "for the record only (their JSON line says so in config.workload)")
     ap.add_argument("--gram-mode", type=str, default="tf32x3", choices=["fp32", "tf32x3", "bf16"])
+    ap.add_argument("--timeline", action="store_true", help="CUPTI timeline of one graph replay -> gpurun_out/timeline_<workload>.txt, exit")
     ap.add_argument("--kernel-shares", action="store_true", help="profile two eager steps, write gpurun_out/kernel_shares_<workload>.txt, exit")
     ap.add_argument("--strong", action="store_true", help="strong scaling: the GLOBAL batch stays 128 (per-GPU batch 128/N); "
                     "default is weak scaling (per-GPU batch 128)")

@@ -791,3 +791,17 @@ def test_lmmd_golden_and_fp64_autograd(tag):
     grad_close(tgt.grad.cpu(), t64c.grad, t(g[f"{tag}_gt"]), what=f"lmmd g_target {tag}")
     K = M.guassian_kernel(src0, tgt0)
     rel_close(K.cpu(), t(g[f"{tag}_K"]), rtol=1e-5, atol_frac=1e-6, what="guassian_kernel")
+
+
+def test_lmmd_nan_kernel_matrix_returns_zero_like_the_reference():
+    """mmd.py:35-36: identical features -> bandwidth 0 -> NaN kernels -> the reference returns loss 0 (no gradient)."""
+    from alignq_b200.utils import mmd as M
+    src = torch.full((6, 10), 0.25, device=DEV, requires_grad=True)
+    tgt = torch.full((6, 10), 0.25, device=DEV, requires_grad=True)
+    s_label = torch.tensor([0, 1, 2, 0, 1, 2], device=DEV)
+    t_prob = torch.softmax(torch.randn(6, 31, generator=torch.Generator().manual_seed(0)), 1).to(DEV)
+    t_prob[:, :3] += 1.0
+    loss = M.lmmd(src, tgt, s_label, t_prob)
+    loss.sum().backward()
+    assert float(loss.detach()) == 0.0
+    assert float(src.grad.abs().max()) == 0.0 and float(tgt.grad.abs().max()) == 0.0

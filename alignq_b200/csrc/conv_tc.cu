@@ -25,6 +25,7 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "tc_small_common.cuh"
+#include "bn_stat.cuh"
 #include "../../include/alignq_b200.h"
 
 namespace alignq {
@@ -130,23 +131,6 @@ template <int C>
 struct FwdCfg {
   static constexpr int MT = 256;                                   // output positions per tile (two M = 128 MMAs)
   static constexpr int W_TAP = C * C * 4;                          // one tap's weight tile, dense K-major
-};
-
-// Batch statistics of the FOLLOWING BatchNorm from the convolution's epilogue (the conv output is in registers there):
-// per-channel sum and sum of squares over the valid output positions, added to the BatchNorm layer's fp64 accumulator
-// copies with the layout of bn_act.cu (ws[(slot * C + c) * 2 + {0: sum, 1: sum of squares}]); the LAST CTA (ticket)
-// finishes mean / invstd / running statistics exactly as bnq_stats_kernel's last block does and re-arms everything.
-// The statistics launch of the fused bn-act forward (~8 us per layer, latency-bound) disappears.
-struct BnStat {
-  double* ws;                  // nullptr: no statistics
-  unsigned* counter;
-  float* running_mean;
-  float* running_var;
-  float* save_mean;
-  float* save_invstd;
-  long long* num_batches_tracked;
-  float momentum, eps;
-  double count;                // N * H * W
 };
 
 template <int C, int NS, bool FLIP, int MAXI, bool STATS>

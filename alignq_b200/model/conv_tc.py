@@ -167,6 +167,7 @@ class _ConvQFn(torch.autograd.Function):
         ctx.cfg = (tuple(stride), tuple(padding), tuple(dilation), groups, own, mode, bool(sync))
         ctx.w_like = w
         ctx.gup = getattr(w, "_alignq_gup", None) if sync else None    # (WeightBank, layer index) or None
+        ctx.set_materialize_grads(False)              # no zero-fill launches for the (non-differentiable) statistics outputs
         if bn is None:
             return y
         ctx.mark_non_differentiable(mean, invstd)
@@ -174,6 +175,8 @@ class _ConvQFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gy, *_unused):
+        if gy is None:
+            return (None,) * 11
         x, wc = ctx.saved_tensors
         stride, padding, dilation, groups, own, mode, on_side = ctx.cfg
         lib = L.load()
@@ -225,7 +228,103 @@ class _ConvQFn(torch.autograd.Function):
         return gx, gw, None, None, None, None, None, None, None, None, None
 
 
+_stem_ws = {}
+
+
+def _stem_workspace(Cout, device):
+    """fp64 accumulator copies + ticket of the stem weight gradient: zero before first use, re-armed by the kernel."""
+    key = (Cout, device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _stem_ws.get(key)
+    if ws is None:
+        ws = torch.zeros(int(L.load().alignq_conv3x3_stem_ws_bytes(Cout)), dtype=torch.uint8, device=device)
+        _stem_ws[key] = ws
+    return ws
+
+
+def applies_stem(x, weight, stride, padding, dilation, groups, bias) -> bool:
+    """First-layer convolution (image, Cin = 3 -> 16 / 32 channels, 3x3, stride 1, padding 1) on csrc/conv_stem.cu."""
+    if args.own_conv == "off" or not args.own_conv_stem or bias is not None or groups != 1:
+        return False
+    if tuple(stride) != (1, 1) or tuple(padding) != (1, 1) or tuple(dilation) != (1, 1):
+        return False
+    if weight.dim() != 4 or tuple(weight.shape[1:]) != (3, 3, 3) or weight.shape[0] not in (16, 32):
+        return False
+    return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] == 3 and not x.requires_grad
+            and x.is_contiguous(memory_format=torch.channels_last) and weight.dtype == torch.float32)
+
+
+class _StemConvFn(torch.autograd.Function):
+    """conv0: direct fp32 forward (optionally with the following BatchNorm's batch statistics) and weight gradient."""
+
+    @staticmethod
+    def forward(ctx, x, w, bn, bn_ws, on_side):
+        N, _, H, W = x.shape
+        Cout = w.shape[0]
+        wc = w if w.is_contiguous(memory_format=torch.channels_last) else w.contiguous(memory_format=torch.channels_last)
+        y = torch.empty((N, Cout, H, W), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
+        mean = invstd = None
+        with torch.cuda.device_of(x):
+            if bn is None:
+                L.check(L.load().alignq_conv3x3_stem_fwd(x.data_ptr(), wc.data_ptr(), y.data_ptr(), N, H, W, Cout, 0, 0, 0.0, 0.0,
+                                                         0, 0, 0, 0, 0, L.stream_ptr()), "alignq_conv3x3_stem_fwd")
+            else:
+                mean = torch.empty(Cout, dtype=torch.float32, device=x.device)
+                invstd = torch.empty(Cout, dtype=torch.float32, device=x.device)
+                ws, counter = bn_ws
+                L.check(L.load().alignq_conv3x3_stem_fwd(
+                    x.data_ptr(), wc.data_ptr(), y.data_ptr(), N, H, W, Cout, L.ptr(bn.running_mean), L.ptr(bn.running_var),
+                    float(bn.momentum), float(bn.eps), mean.data_ptr(), invstd.data_ptr(), ws.data_ptr(), counter.data_ptr(),
+                    L.ptr(bn.num_batches_tracked), L.stream_ptr()), "alignq_conv3x3_stem_fwd")
+        ctx.save_for_backward(x, wc)
+        ctx.w_like = w
+        ctx.on_side = bool(on_side)
+        ctx.gup = getattr(w, "_alignq_gup", None) if on_side else None
+        ctx.set_materialize_grads(False)
+        if bn is None:
+            return y
+        ctx.mark_non_differentiable(mean, invstd)
+        return y, mean, invstd
+
+    @staticmethod
+    def backward(ctx, gy, *_unused):
+        if gy is None or not ctx.needs_input_grad[1]:
+            return (None,) * 5
+        x, wc = ctx.saved_tensors
+        N, _, H, W = x.shape
+        Cout = wc.shape[0]
+        if not gy.is_contiguous(memory_format=torch.channels_last):
+            gy = gy.contiguous(memory_format=torch.channels_last)
+        ws_ = WgradStream.get(x.device)
+        dp = ctx.gup is not None and ctx.gup[0].dp_world > 1 and bool(ctx.gup[0].buckets)
+        side = ws_.fork(x, gy, wc, single=dp) if ctx.on_side else torch.cuda.current_stream()
+        slot = None
+        if ctx.gup is not None:
+            slot = ctx.gup[0].gup[ctx.gup[1]]
+            if slot.shape != wc.shape or slot.stride() != wc.stride():
+                slot = None
+        with torch.cuda.stream(side):
+            gw = slot if slot is not None else torch.empty_like(wc)
+            wsp = _stem_workspace(Cout, x.device)
+            L.check(L.load().alignq_conv3x3_stem_bwd_weight(x.data_ptr(), gy.data_ptr(), gw.data_ptr(), N, H, W, Cout,
+                                                            wsp.data_ptr(), wsp.numel(), L.stream_ptr()),
+                    "alignq_conv3x3_stem_bwd_weight")
+            if gw.stride() != ctx.w_like.stride():
+                gw = torch.empty_like(ctx.w_like).copy_(gw)
+            if slot is not None:
+                ctx.gup[0].wgrad_deposited(ctx.gup[1])
+        if ctx.on_side:
+            ws_.keep.append(gw)
+        return None, gw, None, None, None
+
+
+def stem_conv(x, weight, bn=None, bn_ws=None):
+    """conv0 on the own kernels; with ``bn`` (training mode) also returns that BatchNorm's (save_mean, save_invstd)."""
+    return _StemConvFn.apply(x, weight, bn, bn_ws, bool(args.async_wgrad))
+
+
 def conv_async_wgrad(x, weight, stride, padding, dilation, groups):
+    if applies_stem(x, weight, stride, padding, dilation, groups, None):
+        return stem_conv(x, weight)
     own = applies(x, weight, stride, padding, dilation, groups, None)
     return _ConvQFn.apply(x, weight, tuple(stride), tuple(padding), tuple(dilation), groups, own,
                           L.CONV_MODE_ID[args.own_conv] if own else 0)

@@ -232,6 +232,10 @@ def conv_bn_act(conv, bn, actq, x, relu: bool, residual=None):
             and bn.momentum is not None and bool(args.fuse_bn_act) and conv.out_channels in (16, 32)):
         from . import conv_tc
         weight_q = conv.quantize_fn(conv.weight)
+        if residual is None and conv_tc.applies_stem(x, weight_q, conv.stride, conv.padding, conv.dilation, conv.groups, None):
+            y_conv, mean, invstd = conv_tc.stem_conv(x, weight_q, bn, _bn_ws(bn, conv.out_channels, x.device))
+            return _BnActFn.apply(y_conv, bn.weight, bn.bias, bn, actq.a_bit, float(args.act_range),
+                                  L.VARIANT_ID[actq.variant], relu, None, mean, invstd)
         if (conv_tc.applies(x, weight_q, conv.stride, conv.padding, conv.dilation, conv.groups, None)
                 and (residual is None or (residual.shape == x.shape and residual.stride() == x.stride()
                                           and residual.dtype == torch.float32 and residual.data_ptr() % 16 == 0))):

@@ -431,6 +431,8 @@ def conv2d_Q_fn(w_bit, stage, variant=None):
                 from . import conv_tc
                 if conv_tc.applies(input, weight_q, self.stride, self.padding, self.dilation, self.groups, self.bias):
                     return conv_tc.conv3x3(input, weight_q)           # hand-written tcgen05 kernels
+                if conv_tc.applies_stem(input, weight_q, self.stride, self.padding, self.dilation, self.groups, self.bias):
+                    return conv_tc.stem_conv(input, weight_q)          # first layer: direct fp32 kernels
             return F.conv2d(input, weight_q, self.bias, self.stride, self.padding, self.dilation, self.groups)
 
     return Conv2d_Q

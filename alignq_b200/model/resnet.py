@@ -91,7 +91,7 @@ class PreActResNet(nn.Module):
 
     def forward(self, x):
         if not self.with_admm:
-            out = bn_act(self.bn, self.act_q0, self.conv0(x), True)
+            out = conv_bn_act(self.conv0, self.bn, self.act_q0, x, True)
             for layer in self.layers:
                 out = layer(out)
             return self.logit(self.avgpool(out).view(out.size(0), -1))

@@ -38,6 +38,8 @@ class SGD(Optimizer):
         self._chunk_dev = None
         self._chunk_key = None
         self._pinned = []
+        self._table_side = False
+        self.upload_fork = None                      # optional (torch.cuda.Event, torch.cuda.Stream), see step()
 
     def __setstate__(self, state):
         super().__setstate__(state)
@@ -127,8 +129,25 @@ class SGD(Optimizer):
             # re-reads this pinned buffer on replay, so the buffer is kept alive and never rewritten)
             host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).pin_memory()
             self._pinned.append(host)
-            self._table_dev = torch.empty(host.numel(), dtype=torch.uint8, device=dev)
-            self._table_dev.copy_(host, non_blocking=True)
+            if self.upload_fork is not None:
+                # (event recorded at the start of the iteration, side stream): the upload depends on nothing the
+                # iteration computes, so inside a captured graph the H2D node sits at the START of every replay, beside
+                # the forward, instead of ~15 us of PCIe latency between the last backward kernel and the update.
+                # The table is allocated ON the side stream: the caching allocator (graph-private pool included) hands a
+                # stream only blocks freed on that stream, so the hoisted copy can never land in memory that the main
+                # stream's activations occupy earlier in the iteration.
+                ev, side = self.upload_fork
+                side.wait_event(ev)
+                with torch.cuda.stream(side):
+                    if self._table_dev is None or self._table_dev.numel() != host.numel() or not self._table_side:
+                        self._table_dev = torch.empty(host.numel(), dtype=torch.uint8, device=dev)
+                        self._table_side = True
+                    self._table_dev.copy_(host, non_blocking=True)
+                torch.cuda.current_stream().wait_stream(side)
+            else:
+                self._table_dev = torch.empty(host.numel(), dtype=torch.uint8, device=dev)
+                self._table_side = False
+                self._table_dev.copy_(host, non_blocking=True)
             if self._chunk_dev is None or self._chunk_key != tuple(e[0].numel() for e in ents):
                 _, chunk_t, t_chunk0, nchunks = L.plan_chunks([e[0].numel() for e in ents])
                 self._chunk_key = tuple(e[0].numel() for e in ents)

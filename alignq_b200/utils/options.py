@@ -21,7 +21,9 @@ or -- "peer" -- exchanged inside the kernels through NVLink peer-mapped memory (
 ``own_conv`` ("off" | "tf32" | "tf32x3") runs the 3x3 / stride-1 / Cin == Cout quantized convolutions on the
 hand-written tcgen05 kernels (model/conv_tc.py) instead of the library convolution, for the channel counts in
 ``own_conv_channels`` (default (16,): the wide, shallow layers where they beat cuDNN by 1.4-2.5x; at C = 32 / 64 the
-kernels are correct but cuDNN's tiles are still faster -- profiles/r02_conv_bench.json).
+kernels are correct but cuDNN's tiles are still faster -- profiles/r02_conv_bench.json); ``own_conv_stem`` (default
+True, effective unless ``own_conv`` is "off") runs the first-layer convolution (3 -> 16 / 32 channels, 3x3, stride 1) on the
+direct fp32 kernels of csrc/conv_stem.cu.
 """
 from __future__ import annotations
 
@@ -32,7 +34,7 @@ _DEFAULTS = dict(
     gpus=[0], bitW=2, abitW=2, act_range=2, lam=1.0, lam2=4.0, method="ours", stage="second",
     train_batch_size=128, eval_batch_size=100, lr=0.04, momentum=0.9, weight_decay=1e-4,
     variant="A", gram_mode="fp32", store_weight_attrs=True, fuse_bn_act=False, admm_param_grads=True,
-    dp_gram="replica", sync_bn=False, own_conv="off", own_conv_channels=(16,), async_wgrad=False,
+    dp_gram="replica", sync_bn=False, own_conv="off", own_conv_channels=(16,), own_conv_stem=True, async_wgrad=False,
 )
 
 args = SimpleNamespace(**_DEFAULTS)

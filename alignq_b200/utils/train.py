@@ -127,6 +127,7 @@ class QATStep:
         self.graph = None
         self.static_x = self.static_t = None
         self.loss = torch.zeros((), device=dev)
+        self._aux = None
 
     # -- one eager iteration -------------------------------------------------------------------
     def _iteration(self, x, t):
@@ -137,6 +138,11 @@ class QATStep:
             args.async_wgrad = False
 
     def _iteration_body(self, x, t):
+        if self._aux is None and x.is_cuda:
+            self._aux = (torch.cuda.Event(), torch.cuda.Stream(device=x.device))
+        if self._aux is not None:                                  # host->device table uploads of the update step branch
+            self._aux[0].record()                                  # off HERE, not behind the backward (SGD.step)
+            self.opt.upload_fork = self._aux
         for p in self.all_params:                                  # optimizer.zero_grad(): autograd then hands
             p.grad = None                                          # over its gradient buffers without an add
         if self.bank is not None:

@@ -468,7 +468,7 @@ def run_product(args):
                 if cur:
                     steps_.append(cur)
                 cur = []
-            elif "Memcpy" not in n and "Memset" not in n:
+            else:
                 cur.append((a, b, n))
         if cur:
             steps_.append(cur)

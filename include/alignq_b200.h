@@ -244,6 +244,20 @@ size_t alignq_conv3x3_ws_bytes(int C);
 int alignq_conv3x3_bwd_weight(const float* x, const float* gy, float* gw, int N, int H, int W, int C, int mode,
                               int accumulate, void* ws, size_t ws_bytes, alignq_stream_t stream);
 
+/* ---- first-layer 3x3 convolution, Cin = 3 (conv0 of .../model/resnet.py:92 through quantization.py:116-120) ------------
+ * x [N, H, W, 3], y / gy [N, H, W, Cout] NHWC fp32, w / gw [Cout][3][3][3] (channels_last weight), stride 1, padding 1,
+ * Cout in {16, 32} (else ALIGNQ_ERANGE); direct fp32 FFMA kernels (exact fp32 products).
+ * fwd: save_mean != NULL additionally produces the batch statistics of the following BatchNorm from the epilogue (same
+ *      arguments and accumulator layout as alignq_conv3x3_fwd_bnstats; alignq_bn_act_apply follows); NULL: convolution only.
+ * bwd_weight: ws = alignq_conv3x3_stem_ws_bytes(Cout) bytes, ZERO before the first call (the kernel re-arms it).
+ * There is no data gradient (the image needs none). */
+size_t alignq_conv3x3_stem_ws_bytes(int Cout);
+int alignq_conv3x3_stem_fwd(const float* x, const float* w, float* y, int N, int H, int W, int Cout, float* running_mean,
+                            float* running_var, float momentum, float bn_eps, float* save_mean, float* save_invstd,
+                            double* bn_ws, uint32_t* bn_counter, int64_t* num_batches_tracked, alignq_stream_t stream);
+int alignq_conv3x3_stem_bwd_weight(const float* x, const float* gy, float* gw, int N, int H, int W, int Cout, void* ws,
+                                   size_t ws_bytes, alignq_stream_t stream);
+
 /* ---- LMMD loss of the DSAN head (cdf_alignment_admm/dsan_office/utils/mmd.py:9-41) ------------------------------
  * total = cat(source, target) [n, d] fp32; W [n, n] = [[w_ss, -w_st], [-w_st^T, w_tt]] (the label weights of
  * utils/Weight.py:10-59, signed and assembled by the caller): loss = sum_ij W_ij K_ij with K the sum of kernel_num

@@ -116,3 +116,82 @@ def test_conv_epilogue_bn_statistics_match_the_bn_act_statistics_pass(C, H):
     assert relmax(x.grad, x2.grad) <= 1e-4 and relmax(conv.weight.grad, conv2.weight.grad) <= 1e-4
     assert relmax(r.grad * same, r2.grad * same) <= 1e-6
     assert relmax(bn.weight.grad, bn2.weight.grad) <= 1e-4
+
+
+# ---- first-layer (Cin = 3) convolution: csrc/conv_stem.cu --------------------------------------------------------------
+@pytest.mark.parametrize("N,H,W,Cout", [(128, 32, 32, 16), (3, 32, 32, 32), (5, 28, 28, 16), (2, 17, 23, 16), (1, 3, 3, 32),
+                                         (7, 40, 70, 16), (300, 8, 8, 16)])
+def test_stem_conv_forward_and_weight_gradient_vs_fp64_conv2d(N, H, W, Cout):
+    """conv0 = Conv2d(3, Cout, 3, 1, 1) (model/resnet.py:92 through quantization.py:116-120): direct fp32 kernels, exact
+    fp32 products -- 2e-6 of max|ref| against the fp64 convolution (cuDNN's fp32 path printed beside it); repeated calls
+    exercise the re-armed fp64 accumulators of the weight gradient."""
+    torch.manual_seed(60)
+    aq.set_args(own_conv="tf32")
+    x0 = torch.randn(N, 3, H, W, device=DEV).contiguous(memory_format=torch.channels_last)
+    w0 = (torch.randn(Cout, 3, 3, 3, device=DEV) * (2.0 / 27) ** 0.5).contiguous(memory_format=torch.channels_last)
+    gy = torch.randn(N, Cout, H, W, device=DEV).contiguous(memory_format=torch.channels_last)
+    assert conv_tc.applies_stem(x0, w0, (1, 1), (1, 1), (1, 1), 1, None)
+    xr, wr = x0.double(), w0.double().clone().requires_grad_(True)
+    yr = F.conv2d(xr, wr, None, 1, 1)
+    (yr * gy.double()).sum().backward()
+    w32 = w0.clone().requires_grad_(True)
+    y32 = F.conv2d(x0, w32, None, 1, 1)
+    (y32 * gy).sum().backward()
+    for rep in range(3):
+        w = w0.clone().requires_grad_(True)
+        y = conv_tc.stem_conv(x0, w)
+        (y * gy).sum().backward()
+        e = (relmax(y, yr), relmax(w.grad, wr.grad))
+        assert y.shape == (N, Cout, H, W) and y.is_contiguous(memory_format=torch.channels_last)
+        assert w.grad.shape == w0.shape and w.grad.stride() == w0.stride()
+        assert e[0] <= 2e-6 and e[1] <= 2e-6, e
+    print(f"stem conv N={N} {H}x{W} Cout={Cout}: max|d|/max|ref| fwd {e[0]:.1e} wgrad {e[1]:.1e}   "
+          f"(cuDNN fp32: {relmax(y32, yr):.1e} {relmax(w32.grad, wr.grad):.1e})")
+
+
+def test_stem_conv_declines_what_it_does_not_cover():
+    aq.set_args(own_conv="tf32")
+    x = torch.randn(2, 3, 8, 8, device=DEV).contiguous(memory_format=torch.channels_last)
+    w = torch.randn(16, 3, 3, 3, device=DEV)
+    assert conv_tc.applies_stem(x, w, (1, 1), (1, 1), (1, 1), 1, None)
+    assert not conv_tc.applies_stem(x, w, (2, 2), (1, 1), (1, 1), 1, None)                       # strided
+    assert not conv_tc.applies_stem(x.clone().requires_grad_(True), w, (1, 1), (1, 1), (1, 1), 1, None)   # no data gradient
+    assert not conv_tc.applies_stem(x.contiguous(), w, (1, 1), (1, 1), (1, 1), 1, None)          # NCHW
+    assert not conv_tc.applies_stem(x, torch.randn(24, 3, 3, 3, device=DEV), (1, 1), (1, 1), (1, 1), 1, None)
+    aq.set_args(own_conv="off")
+    assert not conv_tc.applies_stem(x, w, (1, 1), (1, 1), (1, 1), 1, None)
+    lib = L.load()
+    assert lib.alignq_conv3x3_stem_fwd(x.data_ptr(), w.data_ptr(), x.data_ptr(), 2, 8, 8, 24, 0, 0, 0.0, 0.0, 0, 0, 0, 0, 0, 0) == -3      # ALIGNQ_ERANGE
+
+
+@pytest.mark.parametrize("Cout,H", [(16, 32), (32, 12)])
+def test_stem_conv_epilogue_bn_statistics(Cout, H):
+    """conv_bn_act on conv0: BatchNorm batch statistics from the stem kernel's epilogue vs the statistics launch."""
+    import copy
+    from alignq_b200.model.fused import bn_act, conv_bn_act
+    torch.manual_seed(61)
+    aq.set_args(variant="A", bitW=8, abitW=8, act_range=2, fuse_bn_act=True, own_conv="tf32", method="none")
+    conv = aq.conv2d_Q_fn(8, "second")(3, Cout, 3, padding=1, bias=False).to(DEV)
+    conv.weight.data = conv.weight.data.contiguous(memory_format=torch.channels_last)
+    bn = torch.nn.BatchNorm2d(Cout).to(DEV).train()
+    with torch.no_grad():
+        bn.weight.copy_(1 + 0.2 * torch.randn(Cout))
+        bn.bias.copy_(0.1 * torch.randn(Cout))
+    bn2, conv2 = copy.deepcopy(bn), copy.deepcopy(conv)
+    q = aq.activation_quantize_fn(8, "second")
+    x = torch.randn(64, 3, H, H, device=DEV).contiguous(memory_format=torch.channels_last)
+    gy = torch.randn(64, Cout, H, H, device=DEV).contiguous(memory_format=torch.channels_last)
+    for rep in range(2):
+        y = conv_bn_act(conv, bn, q, x, True)
+        (y * gy).sum().backward()
+    aq.set_args(own_conv="off")
+    for rep in range(2):
+        y2 = bn_act(bn2, q, conv2(x), True)
+        (y2 * gy).sum().backward()
+    assert int(bn.num_batches_tracked) == 2
+    assert torch.allclose(bn.running_mean, bn2.running_mean, rtol=1e-4, atol=1e-6)
+    assert torch.allclose(bn.running_var, bn2.running_var, rtol=1e-4, atol=1e-6)
+    bad = int(((y - y2).abs() > 1e-6).sum())
+    assert bad <= max(2, int(1e-4 * y.numel())), f"{bad} codes differ"      # BN-output rounding ties only (fp32 library arm)
+    assert relmax(conv.weight.grad, conv2.weight.grad) <= 1e-3
+    assert relmax(bn.weight.grad, bn2.weight.grad) <= 1e-3

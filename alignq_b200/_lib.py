@@ -73,6 +73,9 @@ SIGNATURES = {
     "alignq_bn_act_apply": (_I, [_P, _L, _I, _P, _P, _P, _P, _I, _F, _I, _I, _P, _P, _P]),
     "alignq_conv3x3_bwd_data": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "alignq_conv3x3_ws_bytes": (_Z, [_I]),
+    "alignq_head_ce_ws_bytes": (_Z, [_I]),
+    "alignq_head_ce_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _Z, _P]),
+    "alignq_head_ce_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "alignq_conv3x3_stem_ws_bytes": (_Z, [_I]),
     "alignq_conv3x3_stem_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P]),
     "alignq_conv3x3_stem_bwd_weight": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _Z, _P]),

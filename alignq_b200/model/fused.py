@@ -271,3 +271,70 @@ def bn_act(bn, actq, x, relu: bool, residual=None):
     if residual is not None:
         y = y + residual
     return F.relu(y) if relu else y
+
+
+# ---- classifier head + loss: avg_pool2d -> view -> linear -> cross_entropy in two launches (csrc/head_ce.cu) ---------------
+_head_ws = {}
+
+
+class _HeadCeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, weight, bias, target):
+        B, C, H, W_ = feat.shape
+        K = weight.shape[0]
+        wc = L.dev_f32(weight, "classifier weight")
+        bc = L.dev_f32(bias, "classifier bias") if bias is not None else None
+        dev = feat.device
+        key = (dev.index, B)                       # ticket + per-sample losses: one head at a time per device
+        ws = _head_ws.get(key)
+        if ws is None:
+            ws = torch.zeros(int(L.load().alignq_head_ce_ws_bytes(B)), dtype=torch.uint8, device=dev)
+            _head_ws[key] = ws
+        logits = torch.empty(B, K, dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        pooled = torch.empty(B, C, dtype=torch.float32, device=dev)
+        glog = torch.empty(B, K, dtype=torch.float32, device=dev)
+        with torch.cuda.device_of(feat):
+            L.check(L.load().alignq_head_ce_fwd(feat.data_ptr(), wc.data_ptr(), L.ptr(bc), target.data_ptr(), B, H * W_, C, K,
+                                                logits.data_ptr(), loss.data_ptr(), pooled.data_ptr(), glog.data_ptr(),
+                                                ws.data_ptr(), ws.numel(), L.stream_ptr()), "alignq_head_ce_fwd")
+        ctx.save_for_backward(wc, pooled, glog)
+        ctx.geom = (B, H, W_, C, K)
+        ctx.like = feat
+        ctx.has_bias = bias is not None
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(logits)
+        return loss, logits
+
+    @staticmethod
+    def backward(ctx, gloss, _glogits=None):
+        if gloss is None:
+            return None, None, None, None
+        wc, pooled, glog = ctx.saved_tensors
+        B, H, W_, C, K = ctx.geom
+        gl = L.dev_f32(gloss.reshape(1), "grad of the loss")
+        gf = torch.empty_like(ctx.like) if ctx.needs_input_grad[0] else None       # channels_last like feat
+        gw = torch.empty_like(wc) if ctx.needs_input_grad[1] else None
+        gb = torch.empty(K, dtype=torch.float32, device=wc.device) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        with torch.cuda.device_of(wc):
+            L.check(L.load().alignq_head_ce_bwd(wc.data_ptr(), pooled.data_ptr(), glog.data_ptr(), gl.data_ptr(), B, H * W_, C, K,
+                                                L.ptr(gf), L.ptr(gw), L.ptr(gb), L.stream_ptr()), "alignq_head_ce_bwd")
+        return gf, gw, gb, None
+
+
+def head_ce_applies(feat, linear, target) -> bool:
+    return (feat.is_cuda and feat.dtype == torch.float32 and feat.dim() == 4 and type(linear) is nn.Linear
+            and feat.shape[1] % 4 == 0 and feat.shape[1] <= 1024 and linear.out_features <= 1024
+            and linear.in_features == feat.shape[1] and feat.data_ptr() % 16 == 0
+            and (feat.is_contiguous(memory_format=torch.channels_last) or feat.shape[2] * feat.shape[3] == 1)
+            and target.dtype == torch.int64 and target.dim() == 1 and target.is_contiguous())
+
+
+def avgpool_linear_ce(feat, linear, target):
+    """``F.cross_entropy(linear(F.avg_pool2d(feat, feat.size(3)).view(B, -1)), target)`` (model/resnet.py:108-110 +
+    main.py:283-286) on the two kernels of csrc/head_ce.cu: returns (loss, logits); logits carry no gradient (they are
+    what the reference's accuracy meters read)."""
+    if head_ce_applies(feat, linear, target):
+        return _HeadCeFn.apply(feat, linear.weight, linear.bias, target)
+    logits = linear(F.adaptive_avg_pool2d(feat, 1).view(feat.size(0), -1))
+    return F.cross_entropy(logits, target), logits.detach()

@@ -12,7 +12,7 @@ import torch.nn.functional as F
 
 from ..utils.admm import ADMM
 from ..utils.options import args
-from .fused import bn_act, conv_bn_act
+from .fused import avgpool_linear_ce, bn_act, conv_bn_act
 from .quantization import activation_quantize_fn, conv2d_Q_fn
 
 
@@ -89,12 +89,13 @@ class PreActResNet(nn.Module):
         self.avgpool = nn.AdaptiveAvgPool2d(1)
         self.logit = nn.Linear(64, num_classes)
 
-    def forward(self, x):
+    def features(self, x):
+        """Everything up to (not including) the average pool: (feature map, trans_loss or None)."""
         if not self.with_admm:
             out = conv_bn_act(self.conv0, self.bn, self.act_q0, x, True)
             for layer in self.layers:
                 out = layer(out)
-            return self.logit(self.avgpool(out).view(out.size(0), -1))
+            return out, None
         trans_loss = 0.
         out, loss = self.act_q0(self.bn(self.conv0(x)))
         trans_loss += loss
@@ -102,7 +103,19 @@ class PreActResNet(nn.Module):
         for layer in self.layers:
             out, loss = layer(out)
             trans_loss += loss
-        return self.logit(self.avgpool(out).view(out.size(0), -1)), trans_loss
+        return out, trans_loss
+
+    def forward(self, x):
+        out, trans_loss = self.features(x)
+        logits = self.logit(self.avgpool(out).view(out.size(0), -1))
+        return logits if trans_loss is None else (logits, trans_loss)
+
+    def forward_ce(self, x, target):
+        """forward + ``F.cross_entropy(output, target)`` with the pool -> linear -> loss tail on the fused head kernels
+        (model/fused.py:avgpool_linear_ce): (loss, detached logits, trans_loss or None)."""
+        out, trans_loss = self.features(x)
+        loss, logits = avgpool_linear_ce(out, self.logit, target)
+        return loss, logits, trans_loss
 
 
 def resnet20_quant(bitW, abitW, stage, num_classes=10, variant=None):

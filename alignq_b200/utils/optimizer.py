@@ -38,8 +38,16 @@ class SGD(Optimizer):
         self._chunk_dev = None
         self._chunk_key = None
         self._pinned = []
-        self._table_side = False
-        self.upload_fork = None                      # optional (torch.cuda.Event, torch.cuda.Stream), see step()
+        self._table_in_graph_pool = False
+        self._table_bound_to_graph = False
+        self._deferred = []
+        self.defer_uploads_in_capture = False        # set by the owner of a capture that calls flush_deferred_uploads()
+
+    def flush_deferred_uploads(self):
+        """After a CUDA-graph capture of ``step``: upload the tables the captured kernels read (see ``step``)."""
+        for dst, host in self._deferred:
+            dst.copy_(host, non_blocking=True)
+        self._deferred = []
 
     def __setstate__(self, state):
         super().__setstate__(state)
@@ -129,25 +137,23 @@ class SGD(Optimizer):
             # re-reads this pinned buffer on replay, so the buffer is kept alive and never rewritten)
             host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).pin_memory()
             self._pinned.append(host)
-            if self.upload_fork is not None:
-                # (event recorded at the start of the iteration, side stream): the upload depends on nothing the
-                # iteration computes, so inside a captured graph the H2D node sits at the START of every replay, beside
-                # the forward, instead of ~15 us of PCIe latency between the last backward kernel and the update.
-                # The table is allocated ON the side stream: the caching allocator (graph-private pool included) hands a
-                # stream only blocks freed on that stream, so the hoisted copy can never land in memory that the main
-                # stream's activations occupy earlier in the iteration.
-                ev, side = self.upload_fork
-                side.wait_event(ev)
-                with torch.cuda.stream(side):
-                    if self._table_dev is None or self._table_dev.numel() != host.numel() or not self._table_side:
-                        self._table_dev = torch.empty(host.numel(), dtype=torch.uint8, device=dev)
-                        self._table_side = True
-                    self._table_dev.copy_(host, non_blocking=True)
-                torch.cuda.current_stream().wait_stream(side)
+            capturing = dev.type == "cuda" and torch.cuda.is_current_stream_capturing()
+            if capturing and self.defer_uploads_in_capture and self._table_dev is not None \
+                    and self._table_dev.numel() == host.numel() and not self._table_in_graph_pool:
+                # Captured iteration after eager warm-up: the pointers this table holds are fixed for the life of the
+                # graph, so the upload does not belong IN the graph (an H2D node costs ~15 us of PCIe latency between the
+                # last backward kernel and the update on every replay).  The warm-up's device buffer (ordinary pool,
+                # never recycled into the graph's activations) is kept, and the owner of the capture uploads the new
+                # contents once, right after the capture ends: flush_deferred_uploads().
+                self._deferred.append((self._table_dev, host))
+                self._table_bound_to_graph = True
             else:
-                self._table_dev = torch.empty(host.numel(), dtype=torch.uint8, device=dev)
-                self._table_side = False
-                self._table_dev.copy_(host, non_blocking=True)
+                if self._table_dev is None or self._table_dev.numel() != host.numel() or self._table_bound_to_graph \
+                        or self._table_in_graph_pool:
+                    self._table_dev = torch.empty(host.numel(), dtype=torch.uint8, device=dev)
+                    self._table_in_graph_pool = capturing
+                    self._table_bound_to_graph = False
+                self._table_dev.copy_(host, non_blocking=True)     # under capture: a memcpy node re-reading `host`
             if self._chunk_dev is None or self._chunk_key != tuple(e[0].numel() for e in ents):
                 _, chunk_t, t_chunk0, nchunks = L.plan_chunks([e[0].numel() for e in ents])
                 self._chunk_key = tuple(e[0].numel() for e in ents)

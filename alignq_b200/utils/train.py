@@ -127,7 +127,6 @@ class QATStep:
         self.graph = None
         self.static_x = self.static_t = None
         self.loss = torch.zeros((), device=dev)
-        self._aux = None
 
     # -- one eager iteration -------------------------------------------------------------------
     def _iteration(self, x, t):
@@ -138,11 +137,6 @@ class QATStep:
             args.async_wgrad = False
 
     def _iteration_body(self, x, t):
-        if self._aux is None and x.is_cuda:
-            self._aux = (torch.cuda.Event(), torch.cuda.Stream(device=x.device))
-        if self._aux is not None:                                  # host->device table uploads of the update step branch
-            self._aux[0].record()                                  # off HERE, not behind the backward (SGD.step)
-            self.opt.upload_fork = self._aux
         for p in self.all_params:                                  # optimizer.zero_grad(): autograd then hands
             p.grad = None                                          # over its gradient buffers without an add
         if self.bank is not None:
@@ -152,9 +146,12 @@ class QATStep:
         if self.forward_loss is not None:
             ce, trans_loss = self.forward_loss(self.model, x, t)
         else:
-            out = self.model(x)
-            logits, trans_loss = out if isinstance(out, tuple) else (out, None)
-            ce = F.cross_entropy(logits, t)
+            if args.fused_head and hasattr(self.model, "forward_ce"):
+                ce, logits, trans_loss = self.model.forward_ce(x, t)       # pool -> linear -> loss: two launches
+            else:
+                out = self.model(x)
+                logits, trans_loss = out if isinstance(out, tuple) else (out, None)
+                ce = F.cross_entropy(logits, t)
             if self.keep_logits:
                 if self.logits is None or self.logits.shape != logits.shape:
                     self.logits = torch.empty_like(logits)
@@ -235,8 +232,10 @@ class QATStep:
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
+        self.opt.defer_uploads_in_capture = True
         with torch.cuda.graph(g):
             self._iteration(self.static_x, self.static_t)
+        self.opt.flush_deferred_uploads()                          # pointer tables of the captured update: once, not per replay
         self.graph = g
         return self
 

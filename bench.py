@@ -331,7 +331,7 @@ def run_product(args):
     torch.backends.cudnn.benchmark = os.environ.get("ALIGNQ_CUDNN_BENCHMARK", "1") != "0"   # 0: cheap ncu runs
     fuse = not (args.no_fuse or args.nchw)
     aq.set_args(variant="A", bitW=8, abitW=8, act_range=2, lam=1.0, lam2=4.0, method="ours", train_batch_size=BATCH,
-                fuse_bn_act=fuse, own_conv=("off" if args.nchw else args.own_conv),
+                fuse_bn_act=fuse, own_conv=("off" if args.nchw else args.own_conv), fused_head=not (args.no_fused_head or args.nchw),
                 own_conv_channels=tuple(int(c) for c in args.own_conv_channels.split(",") if c))
     torch.manual_seed(0)                                   # identical replicas on every rank
     batch, img_hw, ncls, forward_loss = BATCH, 32, 10, None
@@ -659,7 +659,8 @@ def run_product(args):
                 "config": dict(CONFIG, global_batch=batch * world, parallelism=f"dp{world}", cuda_graph=graphed,
                                activation_layout="nchw" if args.nchw else "channels_last", fused_bn_act=fuse,
                                conv3x3=("cuDNN" if (args.nchw or args.own_conv == "off") else
-                                        f"own tcgen05 kernels ({args.own_conv}) for 3x3/s1/Cin==Cout in ({args.own_conv_channels}); cuDNN (tf32) for the rest"),
+                                        f"own tcgen05 kernels ({args.own_conv}) for 3x3/s1/Cin==Cout in ({args.own_conv_channels}) and own fp32 first-layer kernels; cuDNN (tf32) for the rest"),
+                               fused_head=not (args.no_fused_head or args.nchw),
                                sync_bn=bool(sync_bn),
                                sync_bn_impl=(None if not sync_bn else (
                                    ("fused bn-act kernels, fp64 (sum, sumsq) exchanged inside the kernels over NVLink peer memory"
@@ -693,6 +694,7 @@ def main():
                     help="default resnet20 = BASELINE.json configs[0] (the metric's workload); the others are configs[1..3], "
                     "for the record only (their JSON line says so in config.workload)")
     ap.add_argument("--gram-mode", type=str, default="tf32x3", choices=["fp32", "tf32x3", "bf16"])
+    ap.add_argument("--no-fused-head", action="store_true", help="library kernels for avg-pool -> classifier -> cross-entropy")
     ap.add_argument("--timeline", action="store_true", help="CUPTI timeline of one graph replay -> gpurun_out/timeline_<workload>.txt, exit")
     ap.add_argument("--kernel-shares", action="store_true", help="profile two eager steps, write gpurun_out/kernel_shares_<workload>.txt, exit")
     ap.add_argument("--strong", action="store_true", help="strong scaling: the GLOBAL batch stays 128 (per-GPU batch 128/N); "

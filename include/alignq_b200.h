@@ -213,6 +213,7 @@ int alignq_bn_act_bwd(const float* x, const float* y, const float* gy, int64_t r
                       float* g_residual, float* ggamma, float* gbeta, double* ws, uint32_t* counter,
                       alignq_stream_t stream);
 
+
 /* ---- 3x3 convolution of the quantized conv layers on the tensor cores (tcgen05) ------------------------------
  * `F.conv2d(input, weight_q, None, 1, 1)` of Conv2d_Q.forward (QA:116-120), its data gradient and its weight gradient,
  * for stride 1, padding 1, Cin == Cout == C in {16, 32, 64}, NHWC (channels_last) fp32:
@@ -257,6 +258,21 @@ int alignq_conv3x3_stem_fwd(const float* x, const float* w, float* y, int N, int
                             double* bn_ws, uint32_t* bn_counter, int64_t* num_batches_tracked, alignq_stream_t stream);
 int alignq_conv3x3_stem_bwd_weight(const float* x, const float* gy, float* gw, int N, int H, int W, int Cout, void* ws,
                                    size_t ws_bytes, alignq_stream_t stream);
+
+/* ---- classifier head + loss: avg_pool2d -> view -> linear -> CrossEntropyLoss(mean) ------------------------------------
+ * (cdf_alignment/resnet-20-cifar-10/model/resnet.py:108-110 and main.py:283-286) in one forward and one backward launch.
+ * feat [B, HW, C] (NHWC / channels_last) fp32, W [K, C], bias [K] or NULL, target [B] int64 in [0, K); C % 4 == 0,
+ * C <= 1024, K <= 1024 (else ALIGNQ_ERANGE).
+ * fwd: logits [B, K], loss [1]; saves pooled [B, C] and glogits [B, K] = (softmax - onehot) / B for the backward;
+ *      ws = alignq_head_ce_ws_bytes(B) bytes whose first 16 are ZERO before the first call (the kernel re-arms them).
+ * bwd: gloss = device pointer to the upstream gradient of the loss (NULL: 1); g_feat [B, HW, C], g_W [K, C], g_b [K]
+ *      (each may be NULL).  Deterministic (fixed summation orders). */
+size_t alignq_head_ce_ws_bytes(int B);
+int alignq_head_ce_fwd(const float* feat, const float* W, const float* bias, const int64_t* target, int B, int HW, int C, int K,
+                       float* logits, float* loss, float* pooled, float* glogits, void* ws, size_t ws_bytes,
+                       alignq_stream_t stream);
+int alignq_head_ce_bwd(const float* W, const float* pooled, const float* glogits, const float* gloss, int B, int HW, int C, int K,
+                       float* g_feat, float* g_W, float* g_b, alignq_stream_t stream);
 
 /* ---- LMMD loss of the DSAN head (cdf_alignment_admm/dsan_office/utils/mmd.py:9-41) ------------------------------
  * total = cat(source, target) [n, d] fp32; W [n, n] = [[w_ss, -w_st], [-w_st^T, w_tt]] (the label weights of
@@ -314,6 +330,7 @@ int alignq_bn_act_bwd_peer(const float* x, const float* y, const float* gy, int6
                            int a_bit, float act_range, int variant, int relu, float* gx, float* g_residual,
                            float* ggamma, float* gbeta, double* ws, uint32_t* counter, const void* const* peer_bufs,
                            uint32_t* peer_seq, int rank, int world, alignq_stream_t stream);
+
 
 #ifdef __cplusplus
 }

@@ -61,6 +61,7 @@ SIGNATURES = {
     "alignq_bn_act_ws_doubles": (_Z, [_I]),
     "alignq_bn_act_fwd": (_I, [_P, _L, _I, _P, _P, _P, _P, _F, _F, _I, _I, _F, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "alignq_bn_act_bwd": (_I, [_P, _P, _P, _L, _I, _P, _P, _P, _P, _I, _I, _F, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "alignq_bn_act_bwd_sum": (_I, [_P, _P, _P, _P, _L, _I, _P, _P, _P, _P, _I, _I, _F, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "alignq_bn_act_sync_stats": (_I, [_P, _L, _I, _P, _P, _P, _P]),
     "alignq_bn_act_sync_apply": (_I, [_P, _L, _L, _I, _P, _P, _P, _P, _P, _F, _F, _I, _F, _I, _I, _P, _P, _P, _P, _P, _P]),
     "alignq_bn_act_sync_bwd_reduce": (_I, [_P, _P, _P, _L, _I, _P, _P, _P, _P, _I, _F, _I, _I, _P, _P, _P, _P, _P, _P]),
@@ -68,6 +69,7 @@ SIGNATURES = {
     "alignq_bn_act_peer_bytes": (_Z, []),
     "alignq_bn_act_fwd_peer": (_I, [_P, _L, _L, _I, _P, _P, _P, _P, _F, _F, _I, _F, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "alignq_bn_act_bwd_peer": (_I, [_P, _P, _P, _L, _L, _I, _P, _P, _P, _P, _I, _F, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
+    "alignq_bn_act_bwd_peer_sum": (_I, [_P, _P, _P, _P, _L, _L, _I, _P, _P, _P, _P, _I, _F, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "alignq_conv3x3_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "alignq_conv3x3_fwd_bnstats": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P]),
     "alignq_bn_act_apply": (_I, [_P, _L, _I, _P, _P, _P, _P, _I, _F, _I, _I, _P, _P, _P]),

@@ -13,6 +13,7 @@
 // spinning) finalises the statistics and re-zeroes accumulators and ticket -- no extra launch, no memset.
 // The backward of tensors up to ~24 MB runs as ONE cooperative launch instead (bnq_bwd_fused_kernel below).
 #include <cooperative_groups.h>
+#include <cstdlib>
 #include "common.cuh"
 #include "../../include/alignq_b200.h"
 
@@ -47,6 +48,18 @@ struct Lane4 { float v[4]; };
 __device__ __forceinline__ Lane4 ld4(const float* p) {
   const float4 t = *reinterpret_cast<const float4*>(p);
   return Lane4{{t.x, t.y, t.z, t.w}};
+}
+
+// upstream gradient of a tensor with two consumers: gy (+ gy2 when the second consumer's gradient arrives separately,
+// so that autograd's accumulate kernel `ga + gb` never runs -- model/fused.py:_GradFork)
+__device__ __forceinline__ Lane4 ld4g(const float* gy, const float* gy2, int64_t o) {
+  Lane4 a = ld4(gy + o);
+  if (gy2) {
+    const Lane4 b = ld4(gy2 + o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a.v[j] += b.v[j];
+  }
+  return a;
 }
 
 // last-block ticket: returns true in every thread of the block that finishes last
@@ -245,6 +258,8 @@ __global__ void __launch_bounds__(BN_MAX_THREADS)
 bnq_apply_kernel(const float* __restrict__ x, int64_t R, int C, const float* __restrict__ gamma,
                  const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ invstd,
                  BnQ q, const float* __restrict__ residual, float* __restrict__ y) {
+  pdl_trigger();                                            // a convolution that follows may run its prologue beside us
+  pdl_wait();                                               // (and we beside the tail of the kernel before us)
   const int C4 = C >> 2, k = blockDim.x / C4;
   const int c4 = threadIdx.x % C4, rsub = threadIdx.x / C4;
   float m[4], is[4], g[4], b[4];
@@ -273,14 +288,16 @@ __device__ __forceinline__ float bnq_gz(float z, float gy, float yv, const BnQ& 
 
 // ---- backward pass 1: d beta = sum g_z, d gamma = sum g_z * xhat ------------------------------------------
 __global__ void __launch_bounds__(BN_MAX_THREADS)
-bnq_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ gy, int64_t R,
-                      int C, const float* __restrict__ gamma, const float* __restrict__ beta,
+bnq_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ gy,
+                      const float* __restrict__ gy2, int64_t R, int C, const float* __restrict__ gamma, const float* __restrict__ beta,
                       const float* __restrict__ mean, const float* __restrict__ invstd, BnQ q,
                       float* __restrict__ ggamma, float* __restrict__ gbeta, float* __restrict__ coef /* [C][2] */,
                       double* __restrict__ ws, unsigned* __restrict__ counter, double* __restrict__ sums_out, PeerCtx pc) {
   extern __shared__ float sh[];
   __shared__ unsigned flag;
 
+  pdl_trigger();
+  pdl_wait();
   const int C4 = C >> 2, k = blockDim.x / C4;
   const int c4 = threadIdx.x % C4, rsub = threadIdx.x / C4;
   float m[4], is[4], g[4], b[4];
@@ -310,7 +327,7 @@ bnq_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ y, 
       ok[u] = r + u * stride < R;
       const int64_t o = (r + u * stride) * C + 4 * c4;
       xs_[u] = ok[u] ? ld4(x + o) : ones;
-      gs_[u] = ok[u] ? ld4(gy + o) : ones;
+      gs_[u] = ok[u] ? ld4g(gy, gy2, o) : ones;
       ys_[u] = (ok[u] && q.relu) ? ld4(y + o) : ones;
     }
 #pragma unroll
@@ -352,10 +369,12 @@ bnq_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ y, 
 // ---- backward pass 2: gx = gamma * invstd * (g_z - mean(g_z) - xhat * mean(g_z xhat))  [training]
 //                        gx = gamma * invstd * g_z                                           [eval] --------
 __global__ void __launch_bounds__(BN_MAX_THREADS)
-bnq_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ gy, int64_t R,
-                     int C, const float* __restrict__ gamma, const float* __restrict__ beta,
+bnq_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ gy,
+                     const float* __restrict__ gy2, int64_t R, int C, const float* __restrict__ gamma, const float* __restrict__ beta,
                      const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ coef,
                      int training, BnQ q, float* __restrict__ gx, float* __restrict__ g_residual) {
+  pdl_trigger();
+  pdl_wait();
   const int C4 = C >> 2, k = blockDim.x / C4;
   const int c4 = threadIdx.x % C4, rsub = threadIdx.x / C4;
   float m[4], is[4], g[4], b[4], k1[4], k2[4];
@@ -367,7 +386,7 @@ bnq_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ y, c
   }
   for (int64_t r = (int64_t)blockIdx.x * k + rsub; r < R; r += (int64_t)gridDim.x * k) {
     const int64_t o = r * C + 4 * c4;
-    const Lane4 xv = ld4(x + o), gv = ld4(gy + o);
+    const Lane4 xv = ld4(x + o), gv = ld4g(gy, gy2, o);
     Lane4 yv = {{1.f, 1.f, 1.f, 1.f}};
     if (q.relu) yv = ld4(y + o);
     float out[4];
@@ -403,14 +422,15 @@ __device__ __forceinline__ void fused_zero_other(double* other, int n) {
 }
 
 __global__ void __launch_bounds__(BN_MAX_THREADS)
-bnq_bwd_fused_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ gy, int64_t R,
-                     int C, const float* __restrict__ gamma, const float* __restrict__ beta,
+bnq_bwd_fused_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ gy,
+                     const float* __restrict__ gy2, int64_t R, int C, const float* __restrict__ gamma, const float* __restrict__ beta,
                      const float* __restrict__ mean, const float* __restrict__ invstd, int training, BnQ q,
                      float* __restrict__ gx, float* __restrict__ g_residual, float* __restrict__ ggamma,
                      float* __restrict__ gbeta, double* __restrict__ ws, unsigned* __restrict__ epoch, PeerCtx pc,
                      float* __restrict__ coefg) {
   extern __shared__ float sh[];
   cg::grid_group grid = cg::this_grid();
+  pdl_trigger();
   const int C4 = C >> 2, k = blockDim.x / C4;
   const int c4 = threadIdx.x % C4, rsub = threadIdx.x / C4;
   const unsigned ep = *reinterpret_cast<volatile unsigned*>(epoch);
@@ -435,7 +455,7 @@ bnq_bwd_fused_kernel(const float* __restrict__ x, const float* __restrict__ y, c
       ok[u] = r + u * stride < R;
       const int64_t o = (r + u * stride) * C + 4 * c4;
       xs_[u] = ok[u] ? ld4(x + o) : ones;
-      gs_[u] = ok[u] ? ld4(gy + o) : ones;
+      gs_[u] = ok[u] ? ld4g(gy, gy2, o) : ones;
       ys_[u] = (ok[u] && q.relu) ? ld4(y + o) : ones;
     }
 #pragma unroll
@@ -506,7 +526,7 @@ bnq_bwd_fused_kernel(const float* __restrict__ x, const float* __restrict__ y, c
   // ---- phase 2: gx (and the shortcut's gradient) ----
   for (int64_t r = (int64_t)blockIdx.x * k + rsub; r < R; r += stride) {
     const int64_t o = r * C + 4 * c4;
-    const Lane4 xv = ld4(x + o), gv = ld4(gy + o);
+    const Lane4 xv = ld4(x + o), gv = ld4g(gy, gy2, o);
     Lane4 yv = {{1.f, 1.f, 1.f, 1.f}};
     if (q.relu) yv = ld4(y + o);
     float out[4];
@@ -542,10 +562,22 @@ static BnLaunch bn_launch(int64_t R, int C, int max_grid = BN_MAX_GRID) {
 
 // The single-launch path: small tensors, narrow layers, and a grid that is co-resident (cooperative launch).
 static bool bn_use_fused(int64_t R, int C, int64_t max_elems) { return C <= 256 && R * (int64_t)C <= max_elems; }
+// ALIGNQ_BN_COOP_PER_SM = n > 0 switches the single-launch (cooperative) backward on, with at most n co-resident blocks
+// per SM.  Default: off.  A cooperative grid starts only when ALL its blocks fit beside whatever else is running, so in
+// the training step it waited for the weight-gradient kernels of the side streams to drain (every bnq_bwd_fused launch
+// began 0.6 us before the preceding conv3x3_wgrad kernel ended: profiles/r02_timeline_resnet20_*.txt), the driver adds
+// a memcpy node after every cooperative launch of a CUDA graph, and a cooperative launch cannot be a programmatic
+// dependent.  Measured on the ResNet-20 step: 1.205 ms with it, 1.115 ms with the reduce + apply pair.
+static int bn_coop_cap() {
+  const char* e = getenv("ALIGNQ_BN_COOP_PER_SM");
+  return e ? atoi(e) : 0;
+}
 template <typename K>
 static int bn_coop_grid(K kernel, const BnLaunch& L) {
   int per_sm = 0;
+  if (bn_coop_cap() == 0) return 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, L.threads, L.smem) != cudaSuccess || per_sm < 1) return 0;
+  if (bn_coop_cap() > 0 && per_sm > bn_coop_cap()) per_sm = bn_coop_cap();
   const int cap = per_sm * ALIGNQ_NUM_SMS;
   return L.grid < cap ? L.grid : cap;
 }
@@ -595,8 +627,8 @@ extern "C" int alignq_bn_act_fwd(const float* x, int64_t rows, int C, const floa
     bnq_eval_stats_kernel<<<(C + 255) / 256, 256, 0, s>>>(running_mean, running_var, bn_eps, C, save_mean, save_invstd);
   }
   ALIGNQ_LAUNCH_CHECK();
-  bnq_apply_kernel<<<L.grid * 2, L.threads, 0, s>>>(x, rows, C, gamma, beta, save_mean, save_invstd,
-                                                    make_bnq(a_bit, act_range, variant, relu), residual, y);
+  { cudaError_t pe_ = launch_pdl(bnq_apply_kernel, dim3(L.grid * 2), dim3(L.threads), 0, s, x, rows, C, gamma, beta, save_mean, save_invstd,
+                                                    make_bnq(a_bit, act_range, variant, relu), residual, y); if (pe_ != cudaSuccess) return (int)pe_; }
   ALIGNQ_LAUNCH_CHECK();
   return ALIGNQ_OK;
 }
@@ -608,21 +640,21 @@ extern "C" int alignq_bn_act_apply(const float* x, int64_t rows, int C, const fl
   if (rc) return rc;
   if (!x || !y || !save_mean || !save_invstd) return ALIGNQ_EINVAL;
   const BnLaunch L = bn_launch(rows, C);
-  bnq_apply_kernel<<<L.grid * 2, L.threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      x, rows, C, gamma, beta, save_mean, save_invstd, make_bnq(a_bit, act_range, variant, relu), residual, y);
+  { cudaError_t pe_ = launch_pdl(bnq_apply_kernel, dim3(L.grid * 2), dim3(L.threads), 0, reinterpret_cast<cudaStream_t>(stream),
+      x, rows, C, gamma, beta, save_mean, save_invstd, make_bnq(a_bit, act_range, variant, relu), residual, y); if (pe_ != cudaSuccess) return (int)pe_; }
   ALIGNQ_LAUNCH_CHECK();
   return ALIGNQ_OK;
 }
 
-extern "C" int alignq_bn_act_bwd(const float* x, const float* y, const float* gy, int64_t rows, int C,
-                                 const float* gamma, const float* beta, const float* save_mean,
-                                 const float* save_invstd, int training, int a_bit, float act_range, int variant,
-                                 int relu, float* gx, float* g_residual, float* ggamma, float* gbeta, double* ws,
-                                 uint32_t* counter, alignq_stream_t stream) {
+extern "C" int alignq_bn_act_bwd_sum(const float* x, const float* y, const float* gy, const float* gy2, int64_t rows, int C,
+                                     const float* gamma, const float* beta, const float* save_mean,
+                                     const float* save_invstd, int training, int a_bit, float act_range, int variant,
+                                     int relu, float* gx, float* g_residual, float* ggamma, float* gbeta, double* ws,
+                                     uint32_t* counter, alignq_stream_t stream) {
   int rc = bn_check(rows, C, a_bit, variant, x, gy, gx);
   if (rc) return rc;
   if (!x || !gy || !gx || !save_mean || !save_invstd || !ws || !counter || (relu && !y)) return ALIGNQ_EINVAL;
-  if ((relu && !aligned16(y)) || (g_residual && !aligned16(g_residual))) return ALIGNQ_EALIGN;
+  if ((relu && !aligned16(y)) || (g_residual && !aligned16(g_residual)) || (gy2 && !aligned16(gy2))) return ALIGNQ_EALIGN;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const BnLaunch L = bn_launch(rows, C);
   BnQ q = make_bnq(a_bit, act_range, variant, relu);
@@ -632,7 +664,7 @@ extern "C" int alignq_bn_act_bwd(const float* x, const float* y, const float* gy
       uint32_t* epoch = counter + 1;
       PeerCtx nopeer{};
       float* nocoef = nullptr;
-      void* args[] = {(void*)&x, (void*)&y, (void*)&gy, (void*)&rows, (void*)&C, (void*)&gamma, (void*)&beta, (void*)&save_mean,
+      void* args[] = {(void*)&x, (void*)&y, (void*)&gy, (void*)&gy2, (void*)&rows, (void*)&C, (void*)&gamma, (void*)&beta, (void*)&save_mean,
                       (void*)&save_invstd, (void*)&training, (void*)&q, (void*)&gx, (void*)&g_residual, (void*)&ggamma,
                       (void*)&gbeta, (void*)&ws, (void*)&epoch, (void*)&nopeer, (void*)&nocoef};
       if (cudaLaunchCooperativeKernel((void*)bnq_bwd_fused_kernel, dim3(grid), dim3(L.threads), args, L.smem, s) == cudaSuccess) {
@@ -643,13 +675,22 @@ extern "C" int alignq_bn_act_bwd(const float* x, const float* y, const float* gy
     }
   }
   float* coef = reinterpret_cast<float*>(ws + (size_t)3 * BN_SLOTS * C * 2);       // [C][2] floats after the accumulators
-  bnq_bwd_reduce_kernel<<<L.grid, L.threads, L.smem, s>>>(x, y, gy, rows, C, gamma, beta, save_mean, save_invstd, q,
-                                                          ggamma, gbeta, coef, ws, counter, nullptr, PeerCtx{});
+  { cudaError_t pe_ = launch_pdl(bnq_bwd_reduce_kernel, dim3(L.grid), dim3(L.threads), L.smem, s, x, y, gy, gy2, rows, C, gamma, beta, save_mean, save_invstd, q,
+                                                          ggamma, gbeta, coef, ws, counter, nullptr, PeerCtx{}); if (pe_ != cudaSuccess) return (int)pe_; }
   ALIGNQ_LAUNCH_CHECK();
-  bnq_bwd_apply_kernel<<<L.grid * 2, L.threads, 0, s>>>(x, y, gy, rows, C, gamma, beta, save_mean, save_invstd, coef,
-                                                        training, q, gx, g_residual);
+  { cudaError_t pe_ = launch_pdl(bnq_bwd_apply_kernel, dim3(L.grid * 2), dim3(L.threads), 0, s, x, y, gy, gy2, rows, C, gamma, beta, save_mean, save_invstd, coef,
+                                                        training, q, gx, g_residual); if (pe_ != cudaSuccess) return (int)pe_; }
   ALIGNQ_LAUNCH_CHECK();
   return ALIGNQ_OK;
+}
+
+extern "C" int alignq_bn_act_bwd(const float* x, const float* y, const float* gy, int64_t rows, int C,
+                                 const float* gamma, const float* beta, const float* save_mean,
+                                 const float* save_invstd, int training, int a_bit, float act_range, int variant,
+                                 int relu, float* gx, float* g_residual, float* ggamma, float* gbeta, double* ws,
+                                 uint32_t* counter, alignq_stream_t stream) {
+  return alignq_bn_act_bwd_sum(x, y, gy, nullptr, rows, C, gamma, beta, save_mean, save_invstd, training, a_bit, act_range,
+                               variant, relu, gx, g_residual, ggamma, gbeta, ws, counter, stream);
 }
 
 // ---- data-parallel SyncBN: the same kernels cut at the point where the ranks' fp64 sums are all-reduced ----------
@@ -678,8 +719,8 @@ extern "C" int alignq_bn_act_sync_apply(const float* x, int64_t rows, int64_t ro
                                                             reinterpret_cast<long long*>(num_batches_tracked));
   ALIGNQ_LAUNCH_CHECK();
   const BnLaunch L = bn_launch(rows, C);
-  bnq_apply_kernel<<<L.grid * 2, L.threads, 0, s>>>(x, rows, C, gamma, beta, save_mean, save_invstd,
-                                                    make_bnq(a_bit, act_range, variant, relu), residual, y);
+  { cudaError_t pe_ = launch_pdl(bnq_apply_kernel, dim3(L.grid * 2), dim3(L.threads), 0, s, x, rows, C, gamma, beta, save_mean, save_invstd,
+                                                    make_bnq(a_bit, act_range, variant, relu), residual, y); if (pe_ != cudaSuccess) return (int)pe_; }
   ALIGNQ_LAUNCH_CHECK();
   return ALIGNQ_OK;
 }
@@ -695,9 +736,9 @@ extern "C" int alignq_bn_act_sync_bwd_reduce(const float* x, const float* y, con
   if (relu && !aligned16(y)) return ALIGNQ_EALIGN;
   const BnLaunch L = bn_launch(rows, C);
   float* coef = reinterpret_cast<float*>(ws + (size_t)3 * BN_SLOTS * C * 2);
-  bnq_bwd_reduce_kernel<<<L.grid, L.threads, L.smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-      x, y, gy, rows, C, gamma, beta, save_mean, save_invstd, make_bnq(a_bit, act_range, variant, relu), ggamma, gbeta, coef,
-      ws, counter, sums, PeerCtx{});
+  { cudaError_t pe_ = launch_pdl(bnq_bwd_reduce_kernel, dim3(L.grid), dim3(L.threads), L.smem, reinterpret_cast<cudaStream_t>(stream),
+      x, y, gy, nullptr, rows, C, gamma, beta, save_mean, save_invstd, make_bnq(a_bit, act_range, variant, relu), ggamma, gbeta,
+      coef, ws, counter, sums, PeerCtx{}); if (pe_ != cudaSuccess) return (int)pe_; }
   ALIGNQ_LAUNCH_CHECK();
   return ALIGNQ_OK;
 }
@@ -716,8 +757,8 @@ extern "C" int alignq_bn_act_sync_bwd_apply(const float* x, const float* y, cons
   bnq_sync_coef_kernel<<<(C + 255) / 256, 256, 0, s>>>(sums, (double)rows_global, C, coef);
   ALIGNQ_LAUNCH_CHECK();
   const BnLaunch L = bn_launch(rows, C);
-  bnq_bwd_apply_kernel<<<L.grid * 2, L.threads, 0, s>>>(x, y, gy, rows, C, gamma, beta, save_mean, save_invstd, coef, 1,
-                                                        make_bnq(a_bit, act_range, variant, relu), gx, g_residual);
+  { cudaError_t pe_ = launch_pdl(bnq_bwd_apply_kernel, dim3(L.grid * 2), dim3(L.threads), 0, s, x, y, gy, nullptr, rows, C, gamma, beta, save_mean, save_invstd, coef, 1,
+                                                        make_bnq(a_bit, act_range, variant, relu), gx, g_residual); if (pe_ != cudaSuccess) return (int)pe_; }
   ALIGNQ_LAUNCH_CHECK();
   return ALIGNQ_OK;
 }
@@ -749,21 +790,22 @@ extern "C" int alignq_bn_act_fwd_peer(const float* x, int64_t rows, int64_t rows
                                                      save_invstd, ws, counter,
                                                      reinterpret_cast<long long*>(num_batches_tracked), nullptr, pc);
   ALIGNQ_LAUNCH_CHECK();
-  bnq_apply_kernel<<<L.grid * 2, L.threads, 0, s>>>(x, rows, C, gamma, beta, save_mean, save_invstd,
-                                                    make_bnq(a_bit, act_range, variant, relu), residual, y);
+  { cudaError_t pe_ = launch_pdl(bnq_apply_kernel, dim3(L.grid * 2), dim3(L.threads), 0, s, x, rows, C, gamma, beta, save_mean, save_invstd,
+                                                    make_bnq(a_bit, act_range, variant, relu), residual, y); if (pe_ != cudaSuccess) return (int)pe_; }
   ALIGNQ_LAUNCH_CHECK();
   return ALIGNQ_OK;
 }
 
-extern "C" int alignq_bn_act_bwd_peer(const float* x, const float* y, const float* gy, int64_t rows, int64_t rows_global, int C,
-                                      const float* gamma, const float* beta, const float* save_mean, const float* save_invstd,
-                                      int a_bit, float act_range, int variant, int relu, float* gx, float* g_residual,
-                                      float* ggamma, float* gbeta, double* ws, uint32_t* counter, const void* const* peer_bufs,
-                                      uint32_t* peer_seq, int rank, int world, alignq_stream_t stream) {
+extern "C" int alignq_bn_act_bwd_peer_sum(const float* x, const float* y, const float* gy, const float* gy2, int64_t rows,
+                                          int64_t rows_global, int C, const float* gamma, const float* beta,
+                                          const float* save_mean, const float* save_invstd, int a_bit, float act_range,
+                                          int variant, int relu, float* gx, float* g_residual, float* ggamma, float* gbeta,
+                                          double* ws, uint32_t* counter, const void* const* peer_bufs, uint32_t* peer_seq,
+                                          int rank, int world, alignq_stream_t stream) {
   int rc = bn_check(rows, C, a_bit, variant, x, gy, gx);
   if (rc) return rc;
   if (!x || !gy || !gx || !save_mean || !save_invstd || !ws || !counter || (relu && !y)) return ALIGNQ_EINVAL;
-  if ((relu && !aligned16(y)) || (g_residual && !aligned16(g_residual))) return ALIGNQ_EALIGN;
+  if ((relu && !aligned16(y)) || (g_residual && !aligned16(g_residual)) || (gy2 && !aligned16(gy2))) return ALIGNQ_EALIGN;
   rc = peer_check(peer_bufs, peer_seq, rank, world, C, rows, rows_global);
   if (rc) return rc;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
@@ -777,7 +819,7 @@ extern "C" int alignq_bn_act_bwd_peer(const float* x, const float* y, const floa
       uint32_t* epoch = counter + 1;
       int training = 1;
       PeerCtx pcv = pc;
-      void* args[] = {(void*)&x, (void*)&y, (void*)&gy, (void*)&rows, (void*)&C, (void*)&gamma, (void*)&beta, (void*)&save_mean,
+      void* args[] = {(void*)&x, (void*)&y, (void*)&gy, (void*)&gy2, (void*)&rows, (void*)&C, (void*)&gamma, (void*)&beta, (void*)&save_mean,
                       (void*)&save_invstd, (void*)&training, (void*)&q, (void*)&gx, (void*)&g_residual, (void*)&ggamma,
                       (void*)&gbeta, (void*)&ws, (void*)&epoch, (void*)&pcv, (void*)&coef};
       if (cudaLaunchCooperativeKernel((void*)bnq_bwd_fused_kernel, dim3(grid), dim3(L.threads), args, L.smem, s) == cudaSuccess) {
@@ -787,11 +829,21 @@ extern "C" int alignq_bn_act_bwd_peer(const float* x, const float* y, const floa
       (void)cudaGetLastError();
     }
   }
-  bnq_bwd_reduce_kernel<<<L.grid, L.threads, L.smem, s>>>(x, y, gy, rows, C, gamma, beta, save_mean, save_invstd, q, ggamma,
-                                                          gbeta, coef, ws, counter, nullptr, pc);
+  { cudaError_t pe_ = launch_pdl(bnq_bwd_reduce_kernel, dim3(L.grid), dim3(L.threads), L.smem, s, x, y, gy, gy2, rows, C, gamma, beta, save_mean, save_invstd, q, ggamma,
+                                                          gbeta, coef, ws, counter, nullptr, pc); if (pe_ != cudaSuccess) return (int)pe_; }
   ALIGNQ_LAUNCH_CHECK();
-  bnq_bwd_apply_kernel<<<L.grid * 2, L.threads, 0, s>>>(x, y, gy, rows, C, gamma, beta, save_mean, save_invstd, coef, 1, q,
-                                                        gx, g_residual);
+  { cudaError_t pe_ = launch_pdl(bnq_bwd_apply_kernel, dim3(L.grid * 2), dim3(L.threads), 0, s, x, y, gy, gy2, rows, C, gamma, beta, save_mean, save_invstd, coef, 1, q,
+                                                        gx, g_residual); if (pe_ != cudaSuccess) return (int)pe_; }
   ALIGNQ_LAUNCH_CHECK();
   return ALIGNQ_OK;
+}
+
+extern "C" int alignq_bn_act_bwd_peer(const float* x, const float* y, const float* gy, int64_t rows, int64_t rows_global, int C,
+                                      const float* gamma, const float* beta, const float* save_mean, const float* save_invstd,
+                                      int a_bit, float act_range, int variant, int relu, float* gx, float* g_residual,
+                                      float* ggamma, float* gbeta, double* ws, uint32_t* counter, const void* const* peer_bufs,
+                                      uint32_t* peer_seq, int rank, int world, alignq_stream_t stream) {
+  return alignq_bn_act_bwd_peer_sum(x, y, gy, nullptr, rows, rows_global, C, gamma, beta, save_mean, save_invstd, a_bit, act_range,
+                                    variant, relu, gx, g_residual, ggamma, gbeta, ws, counter, peer_bufs, peer_seq, rank, world,
+                                    stream);
 }

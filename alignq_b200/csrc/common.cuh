@@ -7,6 +7,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cstdlib>
 
 #define ALIGNQ_NUM_SMS 148
 #define ALIGNQ_BN_SLOTS 16      // copies of the per-channel fp64 accumulators of the fused BatchNorm kernels (bn_act.cu, conv_tc.cu)
@@ -24,6 +25,44 @@ extern "C" void alignq_count_launch_(void);
   } while (0)
 
 namespace alignq {
+
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------------
+// The QAT step is a chain of 5-15 us kernels; each spends 1.5-4 us on launch ramp and a prologue that does not depend on
+// its predecessor (TMEM allocation, barrier set-up, staging the quantized weights, per-channel parameters).  A kernel
+// launched with cudaLaunchAttributeProgrammaticStreamSerialization may start as soon as every block of its predecessor
+// has executed pdl_trigger() (or exited): it runs that prologue beside the predecessor's tail and then blocks in
+// pdl_wait() until the predecessor has COMPLETED and its writes are visible (and, by induction along the chain, every
+// kernel before it: a dependent cannot complete its own wait earlier).  Rules kept here: (1) before pdl_wait() a kernel
+// touches no global memory at all -- except the convolutions, which stage the quantized weights; (2) those weights are
+// written by the weight bank at the start of the step, and at least one normally launched kernel (the stem convolution,
+// the statistics kernels, every library kernel: full barriers of the stream) lies between that write and the first
+// dependent launch, so "my predecessor has started" implies "the weights are complete".
+// Both instructions are no-ops in a kernel launched without the attribute / with nothing depending on it.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// host side: launch `kernel` as a programmatic dependent of whatever precedes it on the stream (ALIGNQ_PDL=0: plain launch)
+inline bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("ALIGNQ_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 constexpr float kInvSqrt2 = 0.70710677f;        // fp32(1/fp32(sqrt(2))): ATen multiplies by the reciprocal of a CPU scalar divisor
 constexpr float kTwoOverSqrtPi = 1.1283791f;    // erf'(v) = 2/sqrt(pi) exp(-v^2)

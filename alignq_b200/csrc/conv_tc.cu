@@ -35,6 +35,30 @@ using namespace tc;
 
 constexpr int NT = 256;                 // threads per CTA: 8 warps (warps w and w+4 share TMEM lane quarter w)
 
+// Dev aid (tools/conv_trace.py builds a second library with -DALIGNQ_CONV_TRACE): thread 0 of every CTA of the forward /
+// data-gradient kernel stamps %globaltimer at the phase boundaries; alignq_conv_trace_read copies the stamps out.
+#ifdef ALIGNQ_CONV_TRACE
+constexpr int TRACE_SLOTS = 16, TRACE_CTAS = 1024;
+__device__ unsigned long long g_conv_trace[TRACE_CTAS * TRACE_SLOTS];
+__device__ __forceinline__ void trace_stamp(int slot) {
+  if (threadIdx.x == 0 && blockIdx.x < TRACE_CTAS && slot < TRACE_SLOTS) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    g_conv_trace[blockIdx.x * TRACE_SLOTS + slot] = t;
+  }
+}
+__device__ __forceinline__ void trace_smid() {
+  if (threadIdx.x == 0 && blockIdx.x < TRACE_CTAS) {
+    unsigned id;
+    asm volatile("mov.u32 %0, %smid;" : "=r"(id));
+    g_conv_trace[blockIdx.x * TRACE_SLOTS + TRACE_SLOTS - 1] = id;
+  }
+}
+#define TRACE(slot) trace_stamp(slot)
+#else
+#define TRACE(slot) ((void)0)
+#endif
+
 struct Geo {
   int N, H, W, Hp, Wp;
   int per;                              // Hp * Wp positions per image
@@ -46,6 +70,14 @@ __device__ __forceinline__ uint32_t cvt_tf32(float v) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
   return r;
 }
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -127,9 +159,19 @@ __host__ __device__ constexpr int plane_stride(int C, int npt) {
 //   FLIP = true : Wt[tap][ci][co] = w[co][2 - kh][2 - kw][ci], roles swapped      (data gradient; in = gy, out = gx)
 // A = staged input planes (K-major, M = 128 positions per MMA), B = weights in shared memory (K-major, N = C rows),
 // accumulators in TMEM: per M tile C columns (+ C columns for the cross terms of the split mode).
+//
+// MMA count, not MMA size, bounds this kernel: a tcgen05.mma with N = 16 occupies the tensor core for ~80 clocks whatever
+// its 16 K MACs would need (measured with %globaltimer stamps, tools/conv_trace.py: 36 MMAs per 256 positions took 3.0 us
+// of a 4.1 us tile).  So the three kw taps are folded into N:
+//     D[q, (kw, co)] = sum_{kh} sum_{ci} in[q + kh Wp, ci] * Wt[kh][kw][co][ci]          (N = 3 C, 3 * C/8 MMAs per M tile)
+//     out[p, co]     = D[p, 0, co] + D[p + 1, 1, co] + D[p + 2, 2, co]
+// The kw shift has moved from the A descriptor to the epilogue, where accumulator row p + 1 is simply the NEXT LANE of the
+// warp: two __shfl_down per value; the last two lanes of a warp take the rows from a small shared-memory exchange the
+// next warp fills, and the last two rows of a tile belong to the next tile (tiles advance by MO = MT - 2 positions).
 template <int C>
 struct FwdCfg {
-  static constexpr int MT = 256;                                   // output positions per tile (two M = 128 MMAs)
+  static constexpr int MT = 256;                                   // accumulator rows per tile (two M = 128 MMAs)
+  static constexpr int MO = MT - 2;                                // output positions per tile
   static constexpr int W_TAP = C * C * 4;                          // one tap's weight tile, dense K-major
 };
 
@@ -146,9 +188,21 @@ conv3x3_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, fl
   uint64_t* bar = reinterpret_cast<uint64_t*>(planes + NS * tile_bytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int ACC = (NS == 2) ? 2 * C : C;                       // columns per M tile
-  constexpr int TCOLS = (2 * ACC < 32) ? 32 : 2 * ACC;             // two M tiles; power of two >= 32
+  constexpr int NF = 3 * C;                                        // MMA N: (kw, co)
+  constexpr int ACC = (NS == 2) ? 2 * NF : NF;                     // columns per M tile (main | cross)
+  constexpr int TCOLS = 2 * ACC <= 128 ? 128 : 2 * ACC <= 256 ? 256 : 512;      // two M tiles; power of two
+  static_assert(2 * ACC <= 512 && NF % 16 == 0 && NF <= 256, "forward MMA shape");
+  __shared__ __align__(16) float xch[NT / 32 + 1][3 * 16];                       // warp-edge rows of the kw fold, 16 channels at a time
 
+  TRACE(0);
+#ifdef ALIGNQ_CONV_TRACE
+  trace_smid();
+#endif
+  pdl_trigger();                  // the bn-act kernel that follows touches no memory before its own pdl_wait
+  // Prologue that does not depend on the preceding kernel (it may run beside that kernel's tail, see pdl_wait in
+  // common.cuh): barrier, TMEM columns, and the quantized weights, which the weight bank wrote at the start of the step.
+  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(tmem_slot, TCOLS);
   // ---- weights -> shared memory (K-major N x K tiles per tap), once per CTA ---------------------------------------
   // B-operand element (row r = N index, k): (r / 8) * SBO_W + (r % 8) * 16 + (k / 4) * 128 + (k % 4) * 4, SBO_W = (C/4) * 128
   constexpr int SBO_W = (C / 4) * 128;
@@ -175,47 +229,51 @@ conv3x3_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, fl
       *reinterpret_cast<float4*>(d + W_BYTES) = make_float4(l[0], l[1], l[2], l[3]);
     }
   }
-  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
-  if (warp == 0) tmem_alloc(tmem_slot, TCOLS);
+  // the input is the preceding kernel's output: wait for it, then request the first tile's positions
+  pdl_wait();
+  float4 fv[MAXI][1];
+  if ((int)blockIdx.x < ntiles) fetch_items<C, 1, false, MAXI>(in, G, blockIdx.x * F::MO, npt, fv);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  constexpr uint32_t IDESC = make_idesc(2u /*tf32*/, 128u, (uint32_t)C);
+  constexpr uint32_t IDESC = make_idesc(2u /*tf32*/, 128u, (uint32_t)NF);
+  TRACE(1);
 
-  float4 fv[MAXI][1];
-  if ((int)blockIdx.x < ntiles) fetch_items<C, 1, false, MAXI>(in, G, blockIdx.x * F::MT, npt, fv);
   float st_s[STATS ? C : 1], st_ss[STATS ? C : 1];                 // this thread's positions: per-channel sum, sum of squares
 #pragma unroll
   for (int c = 0; c < (STATS ? C : 1); ++c) { st_s[c] = 0.f; st_ss[c] = 0.f; }
   int it = 0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-    const int g0 = tile * F::MT;
-    // ---- 1. deposit the fetched input positions g0 .. g0 + MT + 2 Wp + 2 (the planes are free: last tile's MMAs retired)
+    const int g0 = tile * F::MO;
+    // ---- 1. deposit the fetched input positions g0 .. g0 + MT + 2 Wp (the planes are free: last tile's MMAs retired)
     deposit_tf32<C, NS, MAXI>(fv, npt, planes, PS, tile_bytes);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
+    TRACE(2 + 4 * it);
     // ---- 2. MMAs ---------------------------------------------------------------------------------------------------
     if (threadIdx.x == 0) {
       tc_fence_after();
       const uint32_t sa = smem_u32(planes), sw = smem_u32(wsm);
 #pragma unroll 1
       for (int mt = 0; mt < 2; ++mt) {
-        const uint32_t d_main = tmem_base + mt * ACC, d_cross = d_main + C;
+        const uint32_t d_main = tmem_base + mt * ACC, d_cross = d_main + NF;
 #pragma unroll 1
-        for (int tap = 0; tap < 9; ++tap) {
-          const uint32_t shift = (uint32_t)((tap / 3) * G.Wp + (tap % 3) + mt * 128) * 16u;
+        for (int kh = 0; kh < 3; ++kh) {
+          const uint32_t shift = (uint32_t)(kh * G.Wp + mt * 128) * 16u;
+          // the three kw taps of row kh are consecutive [C x C] tiles: one K-major [3 C x C] B operand (rows (kw, co))
+          const uint32_t wk = sw + kh * 3 * F::W_TAP;
 #pragma unroll
           for (int ks = 0; ks < C / 8; ++ks) {
-            const uint32_t acc = (tap > 0 || ks > 0) ? 1u : 0u;
+            const uint32_t acc = (kh > 0 || ks > 0) ? 1u : 0u;
             const uint64_t ah = make_desc(sa + shift + ks * 2 * PS, PS, 128);
-            const uint64_t bh = make_desc(sw + tap * F::W_TAP + ks * 2 * 128, 128, SBO_W);
+            const uint64_t bh = make_desc(wk + ks * 2 * 128, 128, SBO_W);
             umma<true>(d_main, ah, bh, IDESC, acc);
             if (NS == 2) {
               const uint64_t al = make_desc(sa + tile_bytes + shift + ks * 2 * PS, PS, 128);
-              const uint64_t bl = make_desc(sw + W_BYTES + tap * F::W_TAP + ks * 2 * 128, 128, SBO_W);
+              const uint64_t bl = make_desc(wk + W_BYTES + ks * 2 * 128, 128, SBO_W);
               umma<true>(d_cross, ah, bl, IDESC, acc);
               umma<true>(d_cross, al, bh, IDESC, 1u);
             }
@@ -223,11 +281,13 @@ conv3x3_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, fl
         }
       }
       umma_commit(bar);
+      TRACE(3 + 4 * it);
     }
     // ---- 3. next tile's positions -> registers while the tensor core works -----------------------------------------
-    if (tile + (int)gridDim.x < ntiles) fetch_items<C, 1, false, MAXI>(in, G, (tile + gridDim.x) * F::MT, npt, fv);
+    if (tile + (int)gridDim.x < ntiles) fetch_items<C, 1, false, MAXI>(in, G, (tile + gridDim.x) * F::MO, npt, fv);
     mbar_wait(bar, (uint32_t)(it & 1));
     tc_fence_after();
+    TRACE(4 + 4 * it);
     // ---- 4. epilogue: warp w -> M tile w / 4, TMEM lanes 32 (w % 4) .. +31; one output position per thread ---------
     {
       const int mt = warp >> 2;
@@ -236,21 +296,61 @@ conv3x3_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, fl
       const int n = g / G.per;
       const int q = g - n * G.per;
       const int yy = q / G.Wp, xx = q - yy * G.Wp;
-      const bool ok = g < G.npos && yy < G.H && xx < G.W;
+      const bool ok = j < F::MO && g < G.npos && yy < G.H && xx < G.W;
       float* o = out + ((int64_t)(n * G.H + yy) * G.W + xx) * C;
       const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + mt * ACC;
 #pragma unroll
       for (int c0 = 0; c0 < C; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(ta + c0, v);
-        float r[16];
+        // accumulator row of this thread: kw = 0 | 1 | 2 blocks of C columns (+ the cross-term set NF columns further)
+        float r[16], b1[16], c2[16];
+        {
+          uint32_t v[16], v1[16], v2[16];
+          tmem_ld16_nowait(ta + c0, v);                            // three loads in flight, one wait
+          tmem_ld16_nowait(ta + C + c0, v1);
+          tmem_ld16_nowait(ta + 2 * C + c0, v2);
+          tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 16; ++e) r[e] = __uint_as_float(v[e]);
-        if (NS == 2) {
-          uint32_t x2[16];
-          tmem_ld16(ta + C + c0, x2);
+          for (int e = 0; e < 16; ++e) { r[e] = __uint_as_float(v[e]); b1[e] = __uint_as_float(v1[e]); c2[e] = __uint_as_float(v2[e]); }
+          if (NS == 2) {
+            tmem_ld16(ta + NF + c0, v);
 #pragma unroll
-          for (int e = 0; e < 16; ++e) r[e] += __uint_as_float(x2[e]);
+            for (int e = 0; e < 16; ++e) r[e] += __uint_as_float(v[e]);
+            tmem_ld16(ta + NF + C + c0, v);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) b1[e] += __uint_as_float(v[e]);
+            tmem_ld16(ta + NF + 2 * C + c0, v);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) c2[e] += __uint_as_float(v[e]);
+          }
+        }
+        // rows p + 1 (kw = 1) and p + 2 (kw = 2): the next lanes; across the warp edge through shared memory
+        if (c0 > 0) __syncthreads();                               // the previous channel group's exchange has been read
+        if (lane < 2) {
+          float4* xw = reinterpret_cast<float4*>(xch[warp]);
+#pragma unroll
+          for (int e = 0; e < 16; e += 4) {
+            if (lane == 0) xw[e / 4] = make_float4(b1[e], b1[e + 1], b1[e + 2], b1[e + 3]);
+            xw[(lane == 0 ? 4 : 8) + e / 4] = make_float4(c2[e], c2[e + 1], c2[e + 2], c2[e + 3]);
+          }
+        }
+        __syncthreads();
+        {
+          // branch-free: every lane reads the (broadcast) exchange rows and selects; divergent `if (lane == 31)` loads
+          // compiled to 32 branch / reconverge pairs and cost 2.3 us per tile
+          const float4* xb = reinterpret_cast<const float4*>(xch[warp + 1]);
+          const float4* xc = xb + (lane == 31 ? 8 : 4);
+          const bool e31 = lane == 31, e30 = lane >= 30;
+#pragma unroll
+          for (int e = 0; e < 16; e += 4) {
+            const float4 yb4 = xb[e / 4], yc4 = xc[e / 4];
+            const float yb[4] = {yb4.x, yb4.y, yb4.z, yb4.w}, yc[4] = {yc4.x, yc4.y, yc4.z, yc4.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float nb = __shfl_down_sync(0xffffffffu, b1[e + k], 1);
+              const float nc = __shfl_down_sync(0xffffffffu, c2[e + k], 2);
+              r[e + k] = (r[e + k] + (e31 ? yb[k] : nb)) + (e30 ? yc[k] : nc);
+            }
+          }
         }
         if (ok) {
 #pragma unroll
@@ -264,7 +364,9 @@ conv3x3_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, fl
     }
     tc_fence_before();
     __syncthreads();                                               // accumulators and planes are free again
+    TRACE(5 + 4 * it);
   }
+  TRACE(13);
   if (STATS) {
     // CTA totals: warp shuffles, then the 8 warps through shared memory (the planes are idle) in fp64, one atomic per value
     double* red = reinterpret_cast<double*>(planes);               // [8 warps][2 C]
@@ -320,6 +422,7 @@ conv3x3_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, fl
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, TCOLS);
+  TRACE(14);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -521,6 +624,12 @@ conv3x3_wgrad_reduce_kernel(const float* __restrict__ partials, int nparts, int 
   }
 }
 
+// tuning knobs read from the environment on every launch set-up (host side, a getenv per call: nanoseconds)
+inline int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
 inline Geo make_geo(int N, int H, int W) {
   Geo G;
   G.N = N; G.H = H; G.W = W; G.Hp = H + 2; G.Wp = W + 2;
@@ -533,7 +642,7 @@ template <int C, int NS, bool FLIP, bool STATS = false>
 static int launch_fwd(const float* in, const float* w, float* out, int N, int H, int W, cudaStream_t s, BnStat bs = BnStat{}) {
   using F = FwdCfg<C>;
   const Geo G = make_geo(N, H, W);
-  const int ntiles = (G.npos + F::MT - 1) / F::MT;
+  const int ntiles = (G.npos + F::MO - 1) / F::MO;
   const int npt = F::MT + 2 * G.Wp + 2;
   const int PS = plane_stride(C, npt);
   const size_t smem = (size_t)NS * 9 * F::W_TAP + (size_t)NS * (C / 4) * PS + 64;
@@ -547,10 +656,12 @@ static int launch_fwd(const float* in, const float* w, float* out, int N, int H,
   // persistent CTAs (the weights are staged once per CTA): two per SM overlap each other's deposit / MMA / epilogue phases
   int per_sm = (int)((227 * 1024) / (smem + 1024));
   if (per_sm < 1) per_sm = 1;
-  if (per_sm > 2) per_sm = 2;
+  if (per_sm > env_int("ALIGNQ_CONV_PER_SM", 2)) per_sm = env_int("ALIGNQ_CONV_PER_SM", 2);
   int grid = ntiles < ALIGNQ_NUM_SMS * per_sm ? ntiles : ALIGNQ_NUM_SMS * per_sm;
   bs.count = (double)N * H * W;
-  conv3x3_fwd_kernel<C, NS, FLIP, MAXI, STATS><<<grid, NT, smem, s>>>(in, w, out, G, ntiles, npt, PS, bs);
+  // launched as a programmatic dependent of the preceding kernel (common.cuh: pdl_wait); ALIGNQ_PDL=0 switches it off
+  e = launch_pdl(conv3x3_fwd_kernel<C, NS, FLIP, MAXI, STATS>, dim3(grid), dim3(NT), smem, s, in, w, out, G, ntiles, npt, PS, bs);
+  if (e != cudaSuccess) return (int)e;
   ALIGNQ_LAUNCH_CHECK();
   return ALIGNQ_OK;
 }
@@ -569,7 +680,7 @@ static int launch_wgrad(const float* x, const float* gy, float* gw, int N, int H
   if (smem > 227 * 1024) return ALIGNQ_ERANGE;
   const int groups = 9 / TAPS;
   int per_sm = (int)((227 * 1024) / (smem + 1024));
-  if (per_sm > 2) per_sm = 2;
+  if (per_sm > env_int("ALIGNQ_WGRAD_PER_SM", 2)) per_sm = env_int("ALIGNQ_WGRAD_PER_SM", 2);
   if (per_sm < 1) per_sm = 1;
   int grid = ALIGNQ_NUM_SMS * per_sm / groups;
   if (grid > ntiles) grid = ntiles;
@@ -608,7 +719,7 @@ static int conv_args_ok(const void* a, const void* b, const void* c, int N, int 
   do {                                                              \
     if ((C_) == 16) { if ((NS_) == 1) { CALL(16, 1); } else { CALL(16, 2); } } \
     else if ((C_) == 32) { if ((NS_) == 1) { CALL(32, 1); } else { CALL(32, 2); } } \
-    else { if ((NS_) == 1) { CALL(64, 1); } else { CALL(64, 2); } } \
+    else { if ((NS_) == 1) { CALL(64, 1); } else { return ALIGNQ_ERANGE; } }   /* 64 x3: TMEM holds one set only */ \
   } while (0)
 
 extern "C" int alignq_conv3x3_fwd(const float* x, const float* w, float* y, int N, int H, int W, int C, int mode,
@@ -676,3 +787,10 @@ extern "C" int alignq_conv3x3_bwd_weight(const float* x, const float* gy, float*
   if (C == 32) return launch_wgrad<32, 3, 3, true>(x, gy, gw, N, H, W, accumulate, wsf, ws_bytes, s);
   return launch_wgrad<64, 3, 3, true>(x, gy, gw, N, H, W, accumulate, wsf, ws_bytes, s);
 }
+
+#ifdef ALIGNQ_CONV_TRACE
+extern "C" int alignq_conv_trace_read(void* host_dst, size_t bytes) {
+  if (bytes > sizeof(unsigned long long) * TRACE_CTAS * TRACE_SLOTS) return ALIGNQ_EINVAL;
+  return (int)cudaMemcpyFromSymbol(host_dst, g_conv_trace, bytes);
+}
+#endif

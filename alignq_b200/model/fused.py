@@ -29,9 +29,59 @@ def _bn_ws(bn, C: int, device):
     return ent
 
 
+# ---- two consumers of one bn-act output without autograd's accumulate kernel ---------------------------------------------
+# The input of a residual block feeds conv0 AND the shortcut (resnet.py:70-78), so autograd adds the two gradients with a
+# stand-alone element-wise kernel before the producing bn-act backward runs: 9 launches of 2-7 us on the critical path of a
+# ResNet-20 step.  `fork(x)` hands the block two aliases of x instead; in the backward pass the second alias' gradient
+# is parked in the `link` the producing `_BnActFn` / `_PeerBnActFn` shares with its output, and that backward reads
+# gy + gy2 straight from both buffers (alignq_bn_act_bwd_sum).
+def _take_extra(link, like):
+    """The parked second gradient of this layer's output (same layout as `like`), or None."""
+    if link is None:
+        return None
+    extra = link.pop("extra", None)
+    if extra is None:
+        return None
+    return L.like_layout(extra, like, "grad of the second consumer of a fused bn-act output")
+
+
+class _GradFork(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, link):
+        ctx.link = link
+        return x.view_as(x), x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, ga, gb):
+        if ga is None or gb is None:
+            return (gb if ga is None else ga), None
+        if (gb.shape != ga.shape or gb.stride() != ga.stride() or gb.dtype != torch.float32 or ga.dtype != torch.float32
+                or "extra" in ctx.link):
+            return ga + gb, None
+        ctx.link["extra"] = gb                   # consumed by the producer's backward, which autograd runs next for ga
+        return ga, None
+
+
+def fork(x):
+    """(x, x) for the two consumers of a block input; aliases whose gradients are summed inside the producing bn-act
+    backward when x came out of the fused bn-act path (see _GradFork), plain x twice otherwise."""
+    link = getattr(x, "_alignq_link", None)
+    if link is None or not (torch.is_grad_enabled() and x.requires_grad):
+        return x, x
+    return _GradFork.apply(x, link)
+
+
+def _linked(fn, *fn_args):
+    """Run a bn-act autograd function with a fresh link and hang the link on its output (see fork)."""
+    link = {}
+    y = fn.apply(*fn_args, link)
+    y._alignq_link = link
+    return y
+
+
 class _BnActFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, bn, a_bit, act_range, variant, relu, residual=None, mean=None, invstd=None):
+    def forward(ctx, x, weight, bias, bn, a_bit, act_range, variant, relu, residual=None, mean=None, invstd=None, link=None):
         B, C, H, W = x.shape
         rows = B * H * W
         training = bool(bn.training or bn.running_mean is None)
@@ -57,6 +107,7 @@ class _BnActFn(torch.autograd.Function):
         # (`out += shortcut`, resnet.py:77), so it must not be saved
         ctx.save_for_backward(x, y if relu else None, weight, bias, mean, invstd)
         ctx.cfg = (rows, C, training, a_bit, act_range, variant, relu, residual is not None)
+        ctx.link = link
         return y
 
     @staticmethod
@@ -64,17 +115,18 @@ class _BnActFn(torch.autograd.Function):
         x, y, weight, bias, mean, invstd = ctx.saved_tensors
         rows, C, training, a_bit, act_range, variant, relu, has_res = ctx.cfg
         gy = L.like_layout(gy, x, "grad of fused bn-act output")
+        gy2 = _take_extra(ctx.link, x)
         gx = torch.empty_like(x)
         gr = torch.empty_like(x) if (has_res and ctx.needs_input_grad[8]) else None
         gw = torch.empty(C, dtype=torch.float32, device=x.device) if weight is not None else None
         gb = torch.empty(C, dtype=torch.float32, device=x.device) if bias is not None else None
         ws, counter = _bn_ws(ctx.bn, C, x.device)
         with torch.cuda.device_of(x):
-            L.check(L.load().alignq_bn_act_bwd(
-                x.data_ptr(), L.ptr(y), gy.data_ptr(), rows, C, L.ptr(weight), L.ptr(bias), mean.data_ptr(),
+            L.check(L.load().alignq_bn_act_bwd_sum(
+                x.data_ptr(), L.ptr(y), gy.data_ptr(), L.ptr(gy2), rows, C, L.ptr(weight), L.ptr(bias), mean.data_ptr(),
                 invstd.data_ptr(), int(training), a_bit, act_range, variant, int(relu), gx.data_ptr(), L.ptr(gr),
-                L.ptr(gw), L.ptr(gb), ws.data_ptr(), counter.data_ptr(), L.stream_ptr()), "alignq_bn_act_bwd")
-        return gx, gw, gb, None, None, None, None, None, gr, None, None
+                L.ptr(gw), L.ptr(gb), ws.data_ptr(), counter.data_ptr(), L.stream_ptr()), "alignq_bn_act_bwd_sum")
+        return gx, gw, gb, None, None, None, None, None, gr, None, None, None
 
 
 class _SyncBnActFn(torch.autograd.Function):
@@ -168,7 +220,7 @@ class _PeerBnActFn(torch.autograd.Function):
     launches forward and two backward, no NCCL call on the path."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, bn, a_bit, act_range, variant, relu, residual, peer):
+    def forward(ctx, x, weight, bias, bn, a_bit, act_range, variant, relu, residual, peer, link=None):
         B, C, H, W = x.shape
         rows = B * H * W
         rows_global = rows * peer.world
@@ -182,7 +234,7 @@ class _PeerBnActFn(torch.autograd.Function):
                 float(bn.momentum), float(bn.eps), a_bit, act_range, variant, int(relu), L.ptr(residual), y.data_ptr(),
                 mean.data_ptr(), invstd.data_ptr(), ws.data_ptr(), counter.data_ptr(), L.ptr(bn.num_batches_tracked),
                 peer.ptrs_dev, peer.seq.data_ptr(), peer.rank, peer.world, L.stream_ptr()), "alignq_bn_act_fwd_peer")
-        ctx.bn, ctx.peer = bn, peer
+        ctx.bn, ctx.peer, ctx.link = bn, peer, link
         ctx.save_for_backward(x, y if relu else None, weight, bias, mean, invstd)
         ctx.cfg = (rows, rows_global, C, a_bit, act_range, variant, relu, residual is not None)
         return y
@@ -193,18 +245,19 @@ class _PeerBnActFn(torch.autograd.Function):
         rows, rows_global, C, a_bit, act_range, variant, relu, has_res = ctx.cfg
         peer = ctx.peer
         gy = L.like_layout(gy, x, "grad of fused bn-act output")
+        gy2 = _take_extra(ctx.link, x)
         gx = torch.empty_like(x)
         gr = torch.empty_like(x) if (has_res and ctx.needs_input_grad[8]) else None
         gw = torch.empty(C, dtype=torch.float32, device=x.device) if weight is not None else None
         gb = torch.empty(C, dtype=torch.float32, device=x.device) if bias is not None else None
         ws, counter = _bn_ws(ctx.bn, C, x.device)
         with torch.cuda.device_of(x):
-            L.check(L.load().alignq_bn_act_bwd_peer(
-                x.data_ptr(), L.ptr(y), gy.data_ptr(), rows, rows_global, C, L.ptr(weight), L.ptr(bias), mean.data_ptr(),
-                invstd.data_ptr(), a_bit, act_range, variant, int(relu), gx.data_ptr(), L.ptr(gr), L.ptr(gw), L.ptr(gb),
-                ws.data_ptr(), counter.data_ptr(), peer.ptrs_dev, peer.seq.data_ptr(), peer.rank, peer.world, L.stream_ptr()),
-                "alignq_bn_act_bwd_peer")
-        return gx, gw, gb, None, None, None, None, None, gr, None
+            L.check(L.load().alignq_bn_act_bwd_peer_sum(
+                x.data_ptr(), L.ptr(y), gy.data_ptr(), L.ptr(gy2), rows, rows_global, C, L.ptr(weight), L.ptr(bias),
+                mean.data_ptr(), invstd.data_ptr(), a_bit, act_range, variant, int(relu), gx.data_ptr(), L.ptr(gr), L.ptr(gw),
+                L.ptr(gb), ws.data_ptr(), counter.data_ptr(), peer.ptrs_dev, peer.seq.data_ptr(), peer.rank, peer.world,
+                L.stream_ptr()), "alignq_bn_act_bwd_peer_sum")
+        return gx, gw, gb, None, None, None, None, None, gr, None, None
 
 
 def _sync_world():
@@ -234,14 +287,14 @@ def conv_bn_act(conv, bn, actq, x, relu: bool, residual=None):
         weight_q = conv.quantize_fn(conv.weight)
         if residual is None and conv_tc.applies_stem(x, weight_q, conv.stride, conv.padding, conv.dilation, conv.groups, None):
             y_conv, mean, invstd = conv_tc.stem_conv(x, weight_q, bn, _bn_ws(bn, conv.out_channels, x.device))
-            return _BnActFn.apply(y_conv, bn.weight, bn.bias, bn, actq.a_bit, float(args.act_range),
-                                  L.VARIANT_ID[actq.variant], relu, None, mean, invstd)
+            return _linked(_BnActFn, y_conv, bn.weight, bn.bias, bn, actq.a_bit, float(args.act_range),
+                           L.VARIANT_ID[actq.variant], relu, None, mean, invstd)
         if (conv_tc.applies(x, weight_q, conv.stride, conv.padding, conv.dilation, conv.groups, None)
                 and (residual is None or (residual.shape == x.shape and residual.stride() == x.stride()
                                           and residual.dtype == torch.float32 and residual.data_ptr() % 16 == 0))):
             y_conv, mean, invstd = conv_tc.conv_with_bn_stats(x, weight_q, bn, _bn_ws(bn, conv.out_channels, x.device))
-            return _BnActFn.apply(y_conv, bn.weight, bn.bias, bn, actq.a_bit, float(args.act_range),
-                                  L.VARIANT_ID[actq.variant], relu, residual, mean, invstd)
+            return _linked(_BnActFn, y_conv, bn.weight, bn.bias, bn, actq.a_bit, float(args.act_range),
+                           L.VARIANT_ID[actq.variant], relu, residual, mean, invstd)
         # weight_q is already computed: finish the un-fused way without quantizing the weight twice
         if args.async_wgrad and x.is_cuda and conv.padding_mode == "zeros":
             y_conv = conv_tc.conv_async_wgrad(x, weight_q, conv.stride, conv.padding, conv.dilation, conv.groups)
@@ -260,13 +313,13 @@ def bn_act(bn, actq, x, relu: bool, residual=None):
         group, world = _sync_world()
         if world > 1 and bn.training and args.sync_bn == "peer" and world <= 8:
             # global-batch statistics exchanged inside the kernels over NVLink peer memory
-            return _PeerBnActFn.apply(x, bn.weight, bn.bias, bn, actq.a_bit, float(args.act_range),
-                                      L.VARIANT_ID[actq.variant], relu, residual, PeerExchange.get(group, x.device))
+            return _linked(_PeerBnActFn, x, bn.weight, bn.bias, bn, actq.a_bit, float(args.act_range),
+                           L.VARIANT_ID[actq.variant], relu, residual, PeerExchange.get(group, x.device))
         if world > 1 and bn.training:                      # global-batch statistics through an NCCL all-reduce
             return _SyncBnActFn.apply(x, bn.weight, bn.bias, bn, actq.a_bit, float(args.act_range),
                                       L.VARIANT_ID[actq.variant], relu, residual, group, world)
-        return _BnActFn.apply(x, bn.weight, bn.bias, bn, actq.a_bit, float(args.act_range),
-                              L.VARIANT_ID[actq.variant], relu, residual)
+        return _linked(_BnActFn, x, bn.weight, bn.bias, bn, actq.a_bit, float(args.act_range),
+                       L.VARIANT_ID[actq.variant], relu, residual, None, None)
     y = actq(bn(x))
     if residual is not None:
         y = y + residual

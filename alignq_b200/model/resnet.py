@@ -12,7 +12,7 @@ import torch.nn.functional as F
 
 from ..utils.admm import ADMM
 from ..utils.options import args
-from .fused import avgpool_linear_ce, bn_act, conv_bn_act
+from .fused import avgpool_linear_ce, bn_act, conv_bn_act, fork
 from .quantization import activation_quantize_fn, conv2d_Q_fn
 
 
@@ -50,7 +50,8 @@ class PreActBlock_conv_Q(nn.Module):
 
     def forward(self, x):
         if not self.with_admm:
-            shortcut = x if self.skip_conv is None else bn_act(self.skip_bn, self.act_skip_q, self.skip_conv(x), False)
+            x, xs = fork(x)           # two consumers: their gradients meet inside the producer's backward kernel
+            shortcut = xs if self.skip_conv is None else bn_act(self.skip_bn, self.act_skip_q, self.skip_conv(xs), False)
             out = conv_bn_act(self.conv0, self.bn0, self.act_q0, x, True)      # relu(act_q0(bn0(conv0(x))))
             return conv_bn_act(self.conv1, self.bn1, self.act_q1, out, True, residual=shortcut)   # relu(act_q1(.) + shortcut)
         trans_loss = 0.

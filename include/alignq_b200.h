@@ -212,6 +212,14 @@ int alignq_bn_act_bwd(const float* x, const float* y, const float* gy, int64_t r
                       int training, int a_bit, float act_range, int variant, int relu, float* gx,
                       float* g_residual, float* ggamma, float* gbeta, double* ws, uint32_t* counter,
                       alignq_stream_t stream);
+/* Same, for an output with TWO consumers (the block input of `out = conv0(x) ... ; out += shortcut`, resnet.py:70-78):
+ * the upstream gradient is gy + gy2 (gy2 nullable, same layout), added while it is read, so that autograd's separate
+ * accumulate kernel never runs (model/fused.py:_GradFork).                                             */
+int alignq_bn_act_bwd_sum(const float* x, const float* y, const float* gy, const float* gy2, int64_t rows, int C,
+                          const float* gamma, const float* beta, const float* save_mean, const float* save_invstd,
+                          int training, int a_bit, float act_range, int variant, int relu, float* gx,
+                          float* g_residual, float* ggamma, float* gbeta, double* ws, uint32_t* counter,
+                          alignq_stream_t stream);
 
 
 /* ---- 3x3 convolution of the quantized conv layers on the tensor cores (tcgen05) ------------------------------
@@ -330,6 +338,12 @@ int alignq_bn_act_bwd_peer(const float* x, const float* y, const float* gy, int6
                            int a_bit, float act_range, int variant, int relu, float* gx, float* g_residual,
                            float* ggamma, float* gbeta, double* ws, uint32_t* counter, const void* const* peer_bufs,
                            uint32_t* peer_seq, int rank, int world, alignq_stream_t stream);
+int alignq_bn_act_bwd_peer_sum(const float* x, const float* y, const float* gy, const float* gy2, int64_t rows,
+                               int64_t rows_global, int C, const float* gamma, const float* beta, const float* save_mean,
+                               const float* save_invstd, int a_bit, float act_range, int variant, int relu, float* gx,
+                               float* g_residual, float* ggamma, float* gbeta, double* ws, uint32_t* counter,
+                               const void* const* peer_bufs, uint32_t* peer_seq, int rank, int world,
+                               alignq_stream_t stream);
 
 
 #ifdef __cplusplus

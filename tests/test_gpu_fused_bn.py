@@ -240,3 +240,62 @@ def test_sync_bn_entries_compose_to_the_single_device_kernels(P, shape, relu, re
     assert rel(torch.stack(gws).sum(0), bn.weight.grad) <= 1e-5 and rel(torch.stack(gbs).sum(0), bn.bias.grad) <= 1e-5
     if res:
         close5(torch.cat(grs) * same, rr.grad * same, "sync g residual")
+
+
+@pytest.mark.parametrize("shape", [(128, 16, 32, 32), (16, 32, 9, 7), (4, 64, 8, 8)])
+def test_fork_sums_the_two_consumers_gradients_inside_the_backward_kernel(shape):
+    """The input of a residual block has two consumers (resnet.py:70-78).  `fork` parks the second gradient and the
+    producing bn-act backward reads gy + gy2 (alignq_bn_act_bwd_sum): same result as autograd's own accumulate kernel
+    up to the rounding of (ga + gb) -- the kernel adds the same two fp32 values, so bit-equal -- and no add launch."""
+    from alignq_b200.model.fused import fork
+    torch.manual_seed(1)
+    aq.set_args(variant="A", act_range=2, abitW=8, fuse_bn_act=True)
+    B, C, H, W = shape
+    x0 = (torch.randn(shape, device=DEV) * 1.2 - 0.1).contiguous(memory_format=torch.channels_last)
+    wa = torch.randn(shape, device=DEV).contiguous(memory_format=torch.channels_last)
+    wb = torch.randn(shape, device=DEV).contiguous(memory_format=torch.channels_last)
+    bn = nn.BatchNorm2d(C).to(DEV).train()
+    actq = aq.activation_quantize_fn(8, "second")
+    grads = []
+    for use_fork in (True, False):
+        bn_i = copy.deepcopy(bn)
+        x = x0.clone().requires_grad_(True)
+        y = bn_act(bn_i, actq, x, True)
+        assert hasattr(y, "_alignq_link")
+        ya, yb = fork(y) if use_fork else (y, y)
+        if use_fork:
+            assert ya.data_ptr() == y.data_ptr() and yb.data_ptr() == y.data_ptr()
+        ((ya * wa).sum() + (yb * yb * wb).sum()).backward()
+        assert not y._alignq_link, "the parked gradient must have been consumed"
+        grads.append((x.grad.clone(), bn_i.weight.grad.clone(), bn_i.bias.grad.clone()))
+    for a, b, what in zip(grads[0], grads[1], ("gx", "ggamma", "gbeta")):
+        assert torch.equal(a, b), f"{what}: max |d| {float((a - b).abs().max()):.3e}"
+    with torch.no_grad():                                          # no graph: plain aliases
+        y = bn_act(copy.deepcopy(bn), actq, x0, True)
+        ya, yb = fork(y)
+        assert ya is y and yb is y
+
+
+@pytest.mark.parametrize("shape", [(128, 16, 32, 32), (8, 24, 5, 7)])
+def test_single_launch_backward_equals_the_two_kernel_backward(shape, monkeypatch):
+    """The cooperative one-launch backward (opt-in: ALIGNQ_BN_COOP_PER_SM, off by default since the weight-gradient
+    side streams made it wait) must return what the default reduce + apply pair returns."""
+    torch.manual_seed(2)
+    aq.set_args(variant="A", act_range=2, abitW=8, fuse_bn_act=True)
+    B, C, H, W = shape
+    x0 = (torch.randn(shape, device=DEV) * 1.3 + 0.2).contiguous(memory_format=torch.channels_last)
+    gy = torch.randn(shape, device=DEV).contiguous(memory_format=torch.channels_last)
+    res = torch.randn(shape, device=DEV).contiguous(memory_format=torch.channels_last)
+    bn = nn.BatchNorm2d(C).to(DEV).train()
+    actq = aq.activation_quantize_fn(8, "second")
+    outs = []
+    for coop in ("0", "2"):
+        monkeypatch.setenv("ALIGNQ_BN_COOP_PER_SM", coop)
+        bn_i = copy.deepcopy(bn)
+        x = x0.clone().requires_grad_(True)
+        r = res.clone().requires_grad_(True)
+        y = bn_act(bn_i, actq, x, True, residual=r)
+        (y * gy).sum().backward()
+        outs.append((x.grad.clone(), r.grad.clone(), bn_i.weight.grad.clone(), bn_i.bias.grad.clone()))
+    for a, b, what in zip(outs[0], outs[1], ("gx", "g_residual", "ggamma", "gbeta")):
+        close5(a, b, what)

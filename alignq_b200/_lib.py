@@ -61,6 +61,8 @@ SIGNATURES = {
     "alignq_bn_act_ws_doubles": (_Z, [_I]),
     "alignq_bn_act_fwd": (_I, [_P, _L, _I, _P, _P, _P, _P, _F, _F, _I, _I, _F, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "alignq_bn_act_bwd": (_I, [_P, _P, _P, _L, _I, _P, _P, _P, _P, _I, _I, _F, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "alignq_bn_act_bwd_apply": (_I, [_P, _P, _P, _L, _I, _P, _P, _P, _P, _I, _F, _I, _I, _P, _P, _P, _P]),
+    "alignq_conv3x3_bwd_data_bnreduce": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _F, _I, _P, _P, _P, _P, _P]),
     "alignq_bn_act_bwd_sum": (_I, [_P, _P, _P, _P, _L, _I, _P, _P, _P, _P, _I, _I, _F, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "alignq_bn_act_sync_stats": (_I, [_P, _L, _I, _P, _P, _P, _P]),
     "alignq_bn_act_sync_apply": (_I, [_P, _L, _L, _I, _P, _P, _P, _P, _P, _F, _F, _I, _F, _I, _I, _P, _P, _P, _P, _P, _P]),

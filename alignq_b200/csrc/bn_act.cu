@@ -15,6 +15,7 @@
 #include <cooperative_groups.h>
 #include <cstdlib>
 #include "common.cuh"
+#include "bn_stat.cuh"
 #include "../../include/alignq_b200.h"
 
 namespace cg = cooperative_groups;
@@ -281,9 +282,7 @@ bnq_apply_kernel(const float* __restrict__ x, int64_t R, int C, const float* __r
 
 // g_z = gy * [y > 0 if relu] * gscale * exp(-(z/sqrt2)^2): the straight-through quantizer + ReLU backward
 __device__ __forceinline__ float bnq_gz(float z, float gy, float yv, const BnQ& q) {
-  const float v = __fmul_rn(z, kInvSqrt2);
-  const float g = __fmul_rn(gy, __fmul_rn(q.gscale, gauss_kernel_from_v(v)));
-  return (q.relu && !(yv > 0.f)) ? 0.f : g;
+  return bnq_gz_raw(z, gy, yv, q.gscale, q.relu);               // shared with the convolution epilogue (bn_stat.cuh)
 }
 
 // ---- backward pass 1: d beta = sum g_z, d gamma = sum g_z * xhat ------------------------------------------
@@ -691,6 +690,27 @@ extern "C" int alignq_bn_act_bwd(const float* x, const float* y, const float* gy
                                  uint32_t* counter, alignq_stream_t stream) {
   return alignq_bn_act_bwd_sum(x, y, gy, nullptr, rows, C, gamma, beta, save_mean, save_invstd, training, a_bit, act_range,
                                variant, relu, gx, g_residual, ggamma, gbeta, ws, counter, stream);
+}
+
+// The apply pass alone: the reduce pass already ran in the epilogue of the data-gradient convolution that produced gy
+// (alignq_conv3x3_bwd_data_bnreduce left mean(g_z), mean(g_z xhat) in the layer's workspace).
+extern "C" int alignq_bn_act_bwd_apply(const float* x, const float* y, const float* gy, int64_t rows, int C,
+                                       const float* gamma, const float* beta, const float* save_mean,
+                                       const float* save_invstd, int a_bit, float act_range, int variant, int relu,
+                                       float* gx, float* g_residual, double* ws, alignq_stream_t stream) {
+  int rc = bn_check(rows, C, a_bit, variant, x, gy, gx);
+  if (rc) return rc;
+  if (!x || !gy || !gx || !save_mean || !save_invstd || !ws || (relu && !y)) return ALIGNQ_EINVAL;
+  if ((relu && !aligned16(y)) || (g_residual && !aligned16(g_residual))) return ALIGNQ_EALIGN;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const BnLaunch L = bn_launch(rows, C);
+  const float* coef = reinterpret_cast<const float*>(ws + (size_t)3 * BN_SLOTS * C * 2);
+  const float* nogy2 = nullptr;
+  cudaError_t pe = launch_pdl(bnq_bwd_apply_kernel, dim3(L.grid * 2), dim3(L.threads), 0, s, x, y, gy, nogy2, rows, C, gamma, beta,
+                              save_mean, save_invstd, coef, 1, make_bnq(a_bit, act_range, variant, relu), gx, g_residual);
+  if (pe != cudaSuccess) return (int)pe;
+  ALIGNQ_LAUNCH_CHECK();
+  return ALIGNQ_OK;
 }
 
 // ---- data-parallel SyncBN: the same kernels cut at the point where the ranks' fp64 sums are all-reduced ----------

@@ -175,10 +175,11 @@ struct FwdCfg {
   static constexpr int W_TAP = C * C * 4;                          // one tap's weight tile, dense K-major
 };
 
-template <int C, int NS, bool FLIP, int MAXI, bool STATS>
+template <int C, int NS, bool FLIP, int MAXI, bool STATS, bool BNRED>
 __global__ void __launch_bounds__(NT)
 conv3x3_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, float* __restrict__ out, Geo G, int ntiles,
-                   int npt, int PS, BnStat bs) {
+                   int npt, int PS, BnStat bs, BnRed br) {
+  static_assert(!(STATS && BNRED) && (!BNRED || (FLIP && C == 16)), "epilogue reductions");
   using F = FwdCfg<C>;
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int W_BYTES = 9 * F::W_TAP;
@@ -187,6 +188,7 @@ conv3x3_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, fl
   const int tile_bytes = (C / 4) * PS;
   uint64_t* bar = reinterpret_cast<uint64_t*>(planes + NS * tile_bytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int stage_off = NS * W_BYTES + NS * tile_bytes + 64;      // BNRED staging behind barrier + TMEM slot (16-byte aligned)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int NF = 3 * C;                                        // MMA N: (kw, co)
   constexpr int ACC = (NS == 2) ? 2 * NF : NF;                     // columns per M tile (main | cross)
@@ -241,9 +243,22 @@ conv3x3_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, fl
   constexpr uint32_t IDESC = make_idesc(2u /*tf32*/, 128u, (uint32_t)NF);
   TRACE(1);
 
-  float st_s[STATS ? C : 1], st_ss[STATS ? C : 1];                 // this thread's positions: per-channel sum, sum of squares
+  // this thread's positions: per-channel (sum, sum of squares) [STATS] or (sum g_z, sum g_z xhat) [BNRED]
+  // (BNRED reduces every tile over the warp at once and keeps the warp totals in shared memory: no registers held)
+  float st_s[STATS ? C : 1], st_ss[STATS ? C : 1];
 #pragma unroll
   for (int c = 0; c < (STATS ? C : 1); ++c) { st_s[c] = 0.f; st_ss[c] = 0.f; }
+  __shared__ float wred[BNRED ? NT / 32 : 1][32];                  // [warp][lane]: channel lane & 15, sum (lane >> 4)
+  if constexpr (BNRED) wred[warp][lane] = 0.f;
+  // BNRED staging: x, y, gy2 of this thread's output position arrive by cp.async while the MMAs run ([12][NT] float4)
+  float4* stage = reinterpret_cast<float4*>(smem + stage_off);
+  __shared__ float bnp[BNRED ? 4 : 1][BNRED ? C : 1];              // mean | invstd | gamma | beta of the bn-act layer
+  if constexpr (BNRED) if (threadIdx.x < C) {                                  // (forward-pass data: long complete; visible after the sync below)
+    bnp[0][threadIdx.x] = br.mean[threadIdx.x];
+    bnp[1][threadIdx.x] = br.invstd[threadIdx.x];
+    bnp[2][threadIdx.x] = br.gamma ? br.gamma[threadIdx.x] : 1.f;
+    bnp[3][threadIdx.x] = br.beta ? br.beta[threadIdx.x] : 0.f;
+  }
   int it = 0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
     const int g0 = tile * F::MO;
@@ -285,19 +300,36 @@ conv3x3_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, fl
     }
     // ---- 3. next tile's positions -> registers while the tensor core works -----------------------------------------
     if (tile + (int)gridDim.x < ntiles) fetch_items<C, 1, false, MAXI>(in, G, (tile + gridDim.x) * F::MO, npt, fv);
+    // this thread's output position (warp w -> M tile w / 4, TMEM lanes 32 (w % 4) .. +31)
+    const int mt = warp >> 2;
+    const int j = mt * 128 + (warp & 3) * 32 + lane;               // position inside the tile
+    const int g = g0 + j;
+    const int n = g / G.per;
+    const int q = g - n * G.per;
+    const int yy = q / G.Wp, xx = q - yy * G.Wp;
+    const bool ok = j < F::MO && g < G.npos && yy < G.H && xx < G.W;
+    const int64_t ooff = ((int64_t)(n * G.H + yy) * G.W + xx) * C;
+    // BNRED: the bn-act layer's x, y (and the second consumer's gradient) at this position, requested before the wait
+    if constexpr (BNRED) {
+      if (ok) {
+#pragma unroll
+        for (int k = 0; k < C / 4; ++k) {
+          tcsmall::cp_async16(smem_u32(stage + (0 * (C / 4) + k) * NT + threadIdx.x), reinterpret_cast<const float4*>(br.x + ooff) + k);
+          if (br.relu)
+            tcsmall::cp_async16(smem_u32(stage + (1 * (C / 4) + k) * NT + threadIdx.x), reinterpret_cast<const float4*>(br.y + ooff) + k);
+          if (br.gy2)
+            tcsmall::cp_async16(smem_u32(stage + (2 * (C / 4) + k) * NT + threadIdx.x), reinterpret_cast<const float4*>(br.gy2 + ooff) + k);
+        }
+      }
+      tcsmall::cp_async_commit();
+    }
     mbar_wait(bar, (uint32_t)(it & 1));
     tc_fence_after();
     TRACE(4 + 4 * it);
-    // ---- 4. epilogue: warp w -> M tile w / 4, TMEM lanes 32 (w % 4) .. +31; one output position per thread ---------
+    // ---- 4. epilogue: one output position per thread -----------------------------------------------------------------
+    if constexpr (BNRED) tcsmall::cp_async_wait_all();             // this thread's own staged x / y / gy2
     {
-      const int mt = warp >> 2;
-      const int j = mt * 128 + (warp & 3) * 32 + lane;             // position inside the tile
-      const int g = g0 + j;
-      const int n = g / G.per;
-      const int q = g - n * G.per;
-      const int yy = q / G.Wp, xx = q - yy * G.Wp;
-      const bool ok = j < F::MO && g < G.npos && yy < G.H && xx < G.W;
-      float* o = out + ((int64_t)(n * G.H + yy) * G.W + xx) * C;
+      float* o = out + ooff;
       const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + mt * ACC;
 #pragma unroll
       for (int c0 = 0; c0 < C; c0 += 16) {
@@ -353,12 +385,46 @@ conv3x3_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, fl
           }
         }
         if (ok) {
+          if constexpr (BNRED) {
+            if (br.gy2) {                          // r becomes the bn-act output's total upstream gradient
+#pragma unroll
+              for (int e = 0; e < 16; e += 4) {
+                const float4 g4 = stage[(2 * (C / 4) + (c0 + e) / 4) * NT + threadIdx.x];
+                r[e] += g4.x; r[e + 1] += g4.y; r[e + 2] += g4.z; r[e + 3] += g4.w;
+              }
+            }
+          }
 #pragma unroll
           for (int e = 0; e < 16; e += 4) *reinterpret_cast<float4*>(o + c0 + e) = make_float4(r[e], r[e + 1], r[e + 2], r[e + 3]);
-          if (STATS) {
+          if constexpr (STATS) {
 #pragma unroll
             for (int e = 0; e < 16; ++e) { st_s[c0 + e] += r[e]; st_ss[c0 + e] = fmaf(r[e], r[e], st_ss[c0 + e]); }
           }
+        }
+        if constexpr (BNRED) {
+          // g_z and the two BatchNorm-backward sums of this tile: v[0..15] = g_z, v[16..31] = g_z xhat per channel, summed
+          // over the warp at once (lane l keeps the total of value l), accumulated in the warp's shared-memory row
+          float v[32];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = 0.f;
+          if (ok) {
+#pragma unroll
+            for (int e = 0; e < 16; e += 4) {
+              const float4 x4 = stage[(0 * (C / 4) + (c0 + e) / 4) * NT + threadIdx.x];
+              float4 y4 = make_float4(1.f, 1.f, 1.f, 1.f);
+              if (br.relu) y4 = stage[(1 * (C / 4) + (c0 + e) / 4) * NT + threadIdx.x];
+              const float xx4[4] = {x4.x, x4.y, x4.z, x4.w}, yy4[4] = {y4.x, y4.y, y4.z, y4.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int c = c0 + e + k;
+                const float xh = (xx4[k] - bnp[0][c]) * bnp[1][c];
+                const float gz = bnq_gz_raw(fmaf(xh, bnp[2][c], bnp[3][c]), r[e + k], yy4[k], br.gscale, br.relu);
+                v[e + k] = gz;
+                v[16 + e + k] = gz * xh;
+              }
+            }
+          }
+          wred[warp][lane] += warp_reduce_transpose32(v, lane);
         }
       }
     }
@@ -367,57 +433,20 @@ conv3x3_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, fl
     TRACE(5 + 4 * it);
   }
   TRACE(13);
-  if (STATS) {
-    // CTA totals: warp shuffles, then the 8 warps through shared memory (the planes are idle) in fp64, one atomic per value
-    double* red = reinterpret_cast<double*>(planes);               // [8 warps][2 C]
-    __shared__ unsigned last_flag;
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-      float a = st_s[c], b = st_ss[c];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
-      if (lane == 0) { red[warp * 2 * C + 2 * c] = (double)a; red[warp * 2 * C + 2 * c + 1] = (double)b; }
-    }
-    __syncthreads();
-    if (threadIdx.x < 2 * C) {
-      double v = 0.0;
-#pragma unroll
-      for (int wv = 0; wv < NT / 32; ++wv) v += red[wv * 2 * C + threadIdx.x];
-      atomicAdd(bs.ws + (size_t)(blockIdx.x % ALIGNQ_BN_SLOTS) * C * 2 + threadIdx.x, v);
-    }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const unsigned t = atomicAdd(bs.counter, 1u);
-      last_flag = (t == gridDim.x - 1) ? 1u : 0u;
-    }
-    __syncthreads();
-    if (last_flag) {
-      __threadfence();
-      for (int c = threadIdx.x; c < C; c += NT) {
-        double S = 0.0, SS = 0.0;
-#pragma unroll
-        for (int sl = 0; sl < ALIGNQ_BN_SLOTS; ++sl) {               // fixed order over the accumulator copies
-          double* a = bs.ws + ((size_t)sl * C + c) * 2;
-          S += __ldcg(a); SS += __ldcg(a + 1);
-          a[0] = 0.0; a[1] = 0.0;                                    // re-arm the accumulators
-        }
-        const double mean = S / bs.count;
-        double var = SS / bs.count - mean * mean;                  // biased: what BN normalises with
-        var = var < 0.0 ? 0.0 : var;
-        bs.save_mean[c] = (float)mean;
-        bs.save_invstd[c] = (float)(1.0 / sqrt(var + (double)bs.eps));
-        if (bs.running_mean) {
-          const double unbiased = bs.count > 1.0 ? var * bs.count / (bs.count - 1.0) : var;
-          bs.running_mean[c] = (float)((1.0 - bs.momentum) * bs.running_mean[c] + bs.momentum * mean);
-          bs.running_var[c] = (float)((1.0 - bs.momentum) * bs.running_var[c] + bs.momentum * unbiased);
-        }
-      }
-      if (threadIdx.x == 0) {
-        *bs.counter = 0u;                                          // re-arm for the next launch
-        if (bs.num_batches_tracked) *bs.num_batches_tracked += 1;
-      }
-    }
+  if constexpr (STATS) {
+    // CTA totals -> fp64 atomics -> the last CTA finishes mean / invstd / running statistics (bn_stat.cuh); the planes are idle
+    bn_stat_cta_finish<C, NT>(st_s, st_ss, reinterpret_cast<double*>(planes), bs);
+  }
+  if constexpr (BNRED) {
+    // the preceding bn-act layer's backward sums; the last CTA leaves mean(g_z), mean(g_z xhat) and the affine gradients
+    double* red = reinterpret_cast<double*>(planes);               // [warp][2 C] (the planes are idle)
+    red[warp * 2 * C + 2 * (lane & 15) + (lane >> 4)] = (double)wred[warp][lane];
+    bn_cta_finish_from_red<C, NT>(red, br.ws, br.counter, [&](int c, double S, double SS) {
+      if (br.gbeta) br.gbeta[c] = (float)S;
+      if (br.ggamma) br.ggamma[c] = (float)SS;
+      br.coef[2 * c] = (float)(S / br.count);
+      br.coef[2 * c + 1] = (float)(SS / br.count);
+    });
   }
   tc_fence_before();
   __syncthreads();
@@ -638,20 +667,21 @@ inline Geo make_geo(int N, int H, int W) {
   return G;
 }
 
-template <int C, int NS, bool FLIP, bool STATS = false>
-static int launch_fwd(const float* in, const float* w, float* out, int N, int H, int W, cudaStream_t s, BnStat bs = BnStat{}) {
+template <int C, int NS, bool FLIP, bool STATS = false, bool BNRED = false>
+static int launch_fwd(const float* in, const float* w, float* out, int N, int H, int W, cudaStream_t s, BnStat bs = BnStat{},
+                      BnRed br = BnRed{}) {
   using F = FwdCfg<C>;
   const Geo G = make_geo(N, H, W);
   const int ntiles = (G.npos + F::MO - 1) / F::MO;
   const int npt = F::MT + 2 * G.Wp + 2;
   const int PS = plane_stride(C, npt);
-  const size_t smem = (size_t)NS * 9 * F::W_TAP + (size_t)NS * (C / 4) * PS + 64;
+  const size_t smem = (size_t)NS * 9 * F::W_TAP + (size_t)NS * (C / 4) * PS + 64 + (BNRED ? (size_t)3 * (C / 4) * NT * 16 : 0);
   if (smem > 227 * 1024) return ALIGNQ_ERANGE;
   // staging registers: items per thread = ceil(npt / (NT / (C/4))); the instantiation covers rows up to W = 32 + 2
   constexpr int STEP = NT / (C / 4);
   constexpr int MAXI = (F::MT + 2 * 34 + 2 + STEP - 1) / STEP;
   if (npt > MAXI * STEP) return ALIGNQ_ERANGE;                 // wider images: the caller's library convolution
-  cudaError_t e = cudaFuncSetAttribute(conv3x3_fwd_kernel<C, NS, FLIP, MAXI, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(conv3x3_fwd_kernel<C, NS, FLIP, MAXI, STATS, BNRED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   // persistent CTAs (the weights are staged once per CTA): two per SM overlap each other's deposit / MMA / epilogue phases
   int per_sm = (int)((227 * 1024) / (smem + 1024));
@@ -659,8 +689,9 @@ static int launch_fwd(const float* in, const float* w, float* out, int N, int H,
   if (per_sm > env_int("ALIGNQ_CONV_PER_SM", 2)) per_sm = env_int("ALIGNQ_CONV_PER_SM", 2);
   int grid = ntiles < ALIGNQ_NUM_SMS * per_sm ? ntiles : ALIGNQ_NUM_SMS * per_sm;
   bs.count = (double)N * H * W;
+  br.count = (double)N * H * W;
   // launched as a programmatic dependent of the preceding kernel (common.cuh: pdl_wait); ALIGNQ_PDL=0 switches it off
-  e = launch_pdl(conv3x3_fwd_kernel<C, NS, FLIP, MAXI, STATS>, dim3(grid), dim3(NT), smem, s, in, w, out, G, ntiles, npt, PS, bs);
+  e = launch_pdl(conv3x3_fwd_kernel<C, NS, FLIP, MAXI, STATS, BNRED>, dim3(grid), dim3(NT), smem, s, in, w, out, G, ntiles, npt, PS, bs, br);
   if (e != cudaSuccess) return (int)e;
   ALIGNQ_LAUNCH_CHECK();
   return ALIGNQ_OK;
@@ -765,6 +796,25 @@ extern "C" int alignq_conv3x3_bwd_data(const float* gy, const float* w, float* g
   return ALIGNQ_EINVAL;
 }
 
+extern "C" int alignq_conv3x3_bwd_data_bnreduce(const float* gy, const float* w, float* gx, int N, int H, int W, int C, int mode,
+                                                const float* bn_x, const float* bn_y, const float* gy2,
+                                                const float* save_mean, const float* save_invstd, const float* gamma,
+                                                const float* beta, float act_range, int relu, float* ggamma, float* gbeta,
+                                                double* bn_ws, uint32_t* bn_counter, alignq_stream_t stream) {
+  int rc = conv_args_ok(gy, w, gx, N, H, W, C, mode);
+  if (rc) return rc;
+  if (C != 16) return ALIGNQ_ERANGE;                         // per-thread channel accumulators + prefetch registers
+  if (!bn_x || !save_mean || !save_invstd || !bn_ws || !bn_counter || (relu && !bn_y)) return ALIGNQ_EINVAL;
+  if (!aligned16(bn_x) || (relu && !aligned16(bn_y)) || (gy2 && !aligned16(gy2))) return ALIGNQ_EALIGN;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  // coefficients where the bn-act backward's apply pass looks for them: behind the three accumulator sets of the layer
+  float* coef = reinterpret_cast<float*>(bn_ws + (size_t)3 * ALIGNQ_BN_SLOTS * C * 2);
+  BnRed br{bn_x, bn_y, gy2, save_mean, save_invstd, gamma, beta, 2.0f * act_range * kInvSqrt2Pi, relu, bn_ws, bn_counter,
+           coef, ggamma, gbeta, 0.0};
+  if (mode == ALIGNQ_CONV_TF32X3) return launch_fwd<16, 2, true, false, true>(gy, w, gx, N, H, W, s, BnStat{}, br);
+  return launch_fwd<16, 1, true, false, true>(gy, w, gx, N, H, W, s, BnStat{}, br);
+}
+
 extern "C" size_t alignq_conv3x3_ws_bytes(int C) {
   // partials of at most 2 CTAs per SM: [groups * ctas][C][taps * C] floats = ctas_total * C * 9 * C / groups... <= 2 * 148 * 9 C^2
   return (size_t)2 * ALIGNQ_NUM_SMS * 9 * C * C * sizeof(float);
@@ -789,6 +839,12 @@ extern "C" int alignq_conv3x3_bwd_weight(const float* x, const float* gy, float*
 }
 
 #ifdef ALIGNQ_CONV_TRACE
+extern "C" int alignq_conv_trace_reset(void) {
+  void* p = nullptr;
+  cudaError_t e = cudaGetSymbolAddress(&p, g_conv_trace);
+  if (e != cudaSuccess) return (int)e;
+  return (int)cudaMemset(p, 0, sizeof(unsigned long long) * TRACE_CTAS * TRACE_SLOTS);
+}
 extern "C" int alignq_conv_trace_read(void* host_dst, size_t bytes) {
   if (bytes > sizeof(unsigned long long) * TRACE_CTAS * TRACE_SLOTS) return ALIGNQ_EINVAL;
   return (int)cudaMemcpyFromSymbol(host_dst, g_conv_trace, bytes);

@@ -141,8 +141,9 @@ class _ConvQFn(torch.autograd.Function):
     """Any bias-free Conv2d_Q convolution with the weight gradient on the side stream."""
 
     @staticmethod
-    def forward(ctx, x, w, stride, padding, dilation, groups, own, mode, bn=None, bn_ws=None, sync=True):
+    def forward(ctx, x, w, stride, padding, dilation, groups, own, mode, bn=None, bn_ws=None, sync=True, up=None):
         mean = invstd = None
+        ctx.up = up if own else None                  # link of the fused bn-act layer that produced x (fused.py), or None
         if own:
             N, C, H, W = x.shape
             wc = w if w.is_contiguous(memory_format=torch.channels_last) else w.contiguous(memory_format=torch.channels_last)
@@ -176,7 +177,7 @@ class _ConvQFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy, *_unused):
         if gy is None:
-            return (None,) * 11
+            return (None,) * 12
         x, wc = ctx.saved_tensors
         stride, padding, dilation, groups, own, mode, on_side = ctx.cfg
         lib = L.load()
@@ -219,13 +220,32 @@ class _ConvQFn(torch.autograd.Function):
             if own:
                 N, C, H, W = x.shape
                 gx = torch.empty_like(x)
+                fwd = ctx.up.get("fwd") if ctx.up is not None else None
+                if (fwd is not None and C == 16 and fwd[0].shape == x.shape and fwd[0].stride() == x.stride()
+                        and fwd[0].dtype == torch.float32 and fwd[0].data_ptr() % 16 == 0 and "reduced" not in ctx.up):
+                    # x is the output of a fused bn-act layer and gx its upstream gradient: that layer's backward reduce
+                    # pass (and the sum with a parked second gradient) runs in this kernel's epilogue
+                    from .fused import _bn_ws, _take_extra
+                    bx, mean, invstd, bw, bb, bn, (rows, Cb, a_bit, act_range, variant, relu) = fwd
+                    gy2 = _take_extra(ctx.up, x)
+                    gw_bn = torch.empty(C, dtype=torch.float32, device=x.device) if bw is not None else None
+                    gb_bn = torch.empty(C, dtype=torch.float32, device=x.device) if bb is not None else None
+                    ws, counter = _bn_ws(bn, C, x.device)
+                    with torch.cuda.device_of(x):
+                        L.check(lib.alignq_conv3x3_bwd_data_bnreduce(
+                            gy.data_ptr(), wc.data_ptr(), gx.data_ptr(), N, H, W, C, mode, bx.data_ptr(), x.data_ptr(),
+                            L.ptr(gy2), mean.data_ptr(), invstd.data_ptr(), L.ptr(bw), L.ptr(bb), float(act_range),
+                            int(relu), L.ptr(gw_bn), L.ptr(gb_bn), ws.data_ptr(), counter.data_ptr(), L.stream_ptr()),
+                            "alignq_conv3x3_bwd_data_bnreduce")
+                    ctx.up["reduced"] = (gx.data_ptr(), gw_bn, gb_bn)
+                    return gx, gw, None, None, None, None, None, None, None, None, None, None
                 with torch.cuda.device_of(x):
                     L.check(lib.alignq_conv3x3_bwd_data(gy.data_ptr(), wc.data_ptr(), gx.data_ptr(), N, H, W, C, mode,
                                                         L.stream_ptr()), "alignq_conv3x3_bwd_data")
             else:
                 gx, _, _ = torch.ops.aten.convolution_backward(gy, x, wc, None, stride, padding, dilation, False, (0, 0),
                                                                groups, (True, False, False))
-        return gx, gw, None, None, None, None, None, None, None, None, None
+        return gx, gw, None, None, None, None, None, None, None, None, None, None
 
 
 _stem_ws = {}
@@ -322,16 +342,22 @@ def stem_conv(x, weight, bn=None, bn_ws=None):
     return _StemConvFn.apply(x, weight, bn, bn_ws, bool(args.async_wgrad))
 
 
+def _up_link(x):
+    """The link of the fused bn-act layer whose output x is (model/fused.py), when its backward reduce pass may move into
+    this convolution's data-gradient epilogue."""
+    return getattr(x, "_alignq_link", None) if (args.fuse_dgrad_bn and not args.sync_bn) else None
+
+
 def conv_async_wgrad(x, weight, stride, padding, dilation, groups):
     if applies_stem(x, weight, stride, padding, dilation, groups, None):
         return stem_conv(x, weight)
     own = applies(x, weight, stride, padding, dilation, groups, None)
     return _ConvQFn.apply(x, weight, tuple(stride), tuple(padding), tuple(dilation), groups, own,
-                          L.CONV_MODE_ID[args.own_conv] if own else 0)
+                          L.CONV_MODE_ID[args.own_conv] if own else 0, None, None, True, _up_link(x))
 
 
 def conv_with_bn_stats(x, weight, bn, bn_ws):
     """Own 3x3 convolution whose epilogue also produces the batch statistics of ``bn`` (training mode): returns
     (conv output, save_mean, save_invstd).  The weight gradient goes to the side stream when ``args.async_wgrad``."""
     return _ConvQFn.apply(x, weight, (1, 1), (1, 1), (1, 1), 1, True, L.CONV_MODE_ID[args.own_conv], bn, bn_ws,
-                          bool(args.async_wgrad))
+                          bool(args.async_wgrad), _up_link(x))

@@ -49,7 +49,8 @@ class _GradFork(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, link):
         ctx.link = link
-        return x.view_as(x), x.view_as(x)
+        ctx.set_materialize_grads(False)           # a parked shortcut gradient arrives as None, not as a zero tensor
+        return x.detach(), x.detach()          # two aliases (not autograd views: a view output makes the engine re-materialise the gradient)
 
     @staticmethod
     def backward(ctx, ga, gb):
@@ -63,25 +64,39 @@ class _GradFork(torch.autograd.Function):
 
 
 def fork(x):
-    """(x, x) for the two consumers of a block input; aliases whose gradients are summed inside the producing bn-act
-    backward when x came out of the fused bn-act path (see _GradFork), plain x twice otherwise."""
+    """(x, x) for the two consumers of a block input -- first the convolution path, second the shortcut; aliases whose
+    gradients are summed inside the producing bn-act backward when x came out of the fused bn-act path (see _GradFork),
+    plain x twice otherwise."""
     link = getattr(x, "_alignq_link", None)
     if link is None or not (torch.is_grad_enabled() and x.requires_grad):
         return x, x
-    return _GradFork.apply(x, link)
+    xa, xb = _GradFork.apply(x, link)
+    xa._alignq_link = link        # a convolution consuming xa may run the producer's backward reduce pass (conv_tc.py)
+    xb._alignq_fork = link        # a bn-act layer taking xb as its residual parks that gradient in the link right away
+    return xa, xb
 
 
-def _linked(fn, *fn_args):
+def _linked(fn, *fn_args, residual=None):
     """Run a bn-act autograd function with a fresh link and hang the link on its output (see fork)."""
     link = {}
-    y = fn.apply(*fn_args, link)
+    y = fn.apply(*fn_args, link, getattr(residual, "_alignq_fork", None))
     y._alignq_link = link
     return y
 
 
+def _park_residual_grad(ctx, gr):
+    """An identity shortcut taken from a fork: hand its gradient to the producer's link now (the convolution path's
+    backward, which runs before the fork's, may want to add it in its epilogue) and return nothing to autograd."""
+    if gr is not None and ctx.res_link is not None and "extra" not in ctx.res_link:
+        ctx.res_link["extra"] = gr
+        return None
+    return gr
+
+
 class _BnActFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, bn, a_bit, act_range, variant, relu, residual=None, mean=None, invstd=None, link=None):
+    def forward(ctx, x, weight, bias, bn, a_bit, act_range, variant, relu, residual=None, mean=None, invstd=None, link=None,
+                res_link=None):
         B, C, H, W = x.shape
         rows = B * H * W
         training = bool(bn.training or bn.running_mean is None)
@@ -107,7 +122,10 @@ class _BnActFn(torch.autograd.Function):
         # (`out += shortcut`, resnet.py:77), so it must not be saved
         ctx.save_for_backward(x, y if relu else None, weight, bias, mean, invstd)
         ctx.cfg = (rows, C, training, a_bit, act_range, variant, relu, residual is not None)
-        ctx.link = link
+        ctx.link, ctx.res_link = link, res_link
+        if link is not None and training:
+            # what a data-gradient convolution needs to run this layer's backward reduce pass in its epilogue
+            link["fwd"] = (x, mean, invstd, weight, bias, bn, (rows, C, a_bit, act_range, variant, relu))
         return y
 
     @staticmethod
@@ -116,17 +134,28 @@ class _BnActFn(torch.autograd.Function):
         rows, C, training, a_bit, act_range, variant, relu, has_res = ctx.cfg
         gy = L.like_layout(gy, x, "grad of fused bn-act output")
         gy2 = _take_extra(ctx.link, x)
+        red = ctx.link.pop("reduced", None) if ctx.link is not None else None
+        if ctx.link is not None:
+            ctx.link.pop("fwd", None)
         gx = torch.empty_like(x)
         gr = torch.empty_like(x) if (has_res and ctx.needs_input_grad[8]) else None
+        ws, counter = _bn_ws(ctx.bn, C, x.device)
+        if red is not None and gy2 is None and red[0] == gy.data_ptr():
+            # the convolution that produced gy has run the reduce pass (and written the affine gradients): apply only
+            with torch.cuda.device_of(x):
+                L.check(L.load().alignq_bn_act_bwd_apply(
+                    x.data_ptr(), L.ptr(y), gy.data_ptr(), rows, C, L.ptr(weight), L.ptr(bias), mean.data_ptr(),
+                    invstd.data_ptr(), a_bit, act_range, variant, int(relu), gx.data_ptr(), L.ptr(gr), ws.data_ptr(),
+                    L.stream_ptr()), "alignq_bn_act_bwd_apply")
+            return gx, red[1], red[2], None, None, None, None, None, _park_residual_grad(ctx, gr), None, None, None, None
         gw = torch.empty(C, dtype=torch.float32, device=x.device) if weight is not None else None
         gb = torch.empty(C, dtype=torch.float32, device=x.device) if bias is not None else None
-        ws, counter = _bn_ws(ctx.bn, C, x.device)
         with torch.cuda.device_of(x):
             L.check(L.load().alignq_bn_act_bwd_sum(
                 x.data_ptr(), L.ptr(y), gy.data_ptr(), L.ptr(gy2), rows, C, L.ptr(weight), L.ptr(bias), mean.data_ptr(),
                 invstd.data_ptr(), int(training), a_bit, act_range, variant, int(relu), gx.data_ptr(), L.ptr(gr),
                 L.ptr(gw), L.ptr(gb), ws.data_ptr(), counter.data_ptr(), L.stream_ptr()), "alignq_bn_act_bwd_sum")
-        return gx, gw, gb, None, None, None, None, None, gr, None, None, None
+        return gx, gw, gb, None, None, None, None, None, _park_residual_grad(ctx, gr), None, None, None, None
 
 
 class _SyncBnActFn(torch.autograd.Function):
@@ -220,7 +249,7 @@ class _PeerBnActFn(torch.autograd.Function):
     launches forward and two backward, no NCCL call on the path."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, bn, a_bit, act_range, variant, relu, residual, peer, link=None):
+    def forward(ctx, x, weight, bias, bn, a_bit, act_range, variant, relu, residual, peer, link=None, res_link=None):
         B, C, H, W = x.shape
         rows = B * H * W
         rows_global = rows * peer.world
@@ -234,7 +263,7 @@ class _PeerBnActFn(torch.autograd.Function):
                 float(bn.momentum), float(bn.eps), a_bit, act_range, variant, int(relu), L.ptr(residual), y.data_ptr(),
                 mean.data_ptr(), invstd.data_ptr(), ws.data_ptr(), counter.data_ptr(), L.ptr(bn.num_batches_tracked),
                 peer.ptrs_dev, peer.seq.data_ptr(), peer.rank, peer.world, L.stream_ptr()), "alignq_bn_act_fwd_peer")
-        ctx.bn, ctx.peer, ctx.link = bn, peer, link
+        ctx.bn, ctx.peer, ctx.link, ctx.res_link = bn, peer, link, res_link
         ctx.save_for_backward(x, y if relu else None, weight, bias, mean, invstd)
         ctx.cfg = (rows, rows_global, C, a_bit, act_range, variant, relu, residual is not None)
         return y
@@ -257,7 +286,7 @@ class _PeerBnActFn(torch.autograd.Function):
                 mean.data_ptr(), invstd.data_ptr(), a_bit, act_range, variant, int(relu), gx.data_ptr(), L.ptr(gr), L.ptr(gw),
                 L.ptr(gb), ws.data_ptr(), counter.data_ptr(), peer.ptrs_dev, peer.seq.data_ptr(), peer.rank, peer.world,
                 L.stream_ptr()), "alignq_bn_act_bwd_peer_sum")
-        return gx, gw, gb, None, None, None, None, None, gr, None, None
+        return gx, gw, gb, None, None, None, None, None, _park_residual_grad(ctx, gr), None, None, None
 
 
 def _sync_world():
@@ -294,7 +323,7 @@ def conv_bn_act(conv, bn, actq, x, relu: bool, residual=None):
                                           and residual.dtype == torch.float32 and residual.data_ptr() % 16 == 0))):
             y_conv, mean, invstd = conv_tc.conv_with_bn_stats(x, weight_q, bn, _bn_ws(bn, conv.out_channels, x.device))
             return _linked(_BnActFn, y_conv, bn.weight, bn.bias, bn, actq.a_bit, float(args.act_range),
-                           L.VARIANT_ID[actq.variant], relu, residual, mean, invstd)
+                           L.VARIANT_ID[actq.variant], relu, residual, mean, invstd, residual=residual)
         # weight_q is already computed: finish the un-fused way without quantizing the weight twice
         if args.async_wgrad and x.is_cuda and conv.padding_mode == "zeros":
             y_conv = conv_tc.conv_async_wgrad(x, weight_q, conv.stride, conv.padding, conv.dilation, conv.groups)
@@ -314,12 +343,12 @@ def bn_act(bn, actq, x, relu: bool, residual=None):
         if world > 1 and bn.training and args.sync_bn == "peer" and world <= 8:
             # global-batch statistics exchanged inside the kernels over NVLink peer memory
             return _linked(_PeerBnActFn, x, bn.weight, bn.bias, bn, actq.a_bit, float(args.act_range),
-                           L.VARIANT_ID[actq.variant], relu, residual, PeerExchange.get(group, x.device))
+                           L.VARIANT_ID[actq.variant], relu, residual, PeerExchange.get(group, x.device), residual=residual)
         if world > 1 and bn.training:                      # global-batch statistics through an NCCL all-reduce
             return _SyncBnActFn.apply(x, bn.weight, bn.bias, bn, actq.a_bit, float(args.act_range),
                                       L.VARIANT_ID[actq.variant], relu, residual, group, world)
         return _linked(_BnActFn, x, bn.weight, bn.bias, bn, actq.a_bit, float(args.act_range),
-                       L.VARIANT_ID[actq.variant], relu, residual, None, None)
+                       L.VARIANT_ID[actq.variant], relu, residual, None, None, residual=residual)
     y = actq(bn(x))
     if residual is not None:
         y = y + residual

@@ -220,6 +220,12 @@ int alignq_bn_act_bwd_sum(const float* x, const float* y, const float* gy, const
                           int training, int a_bit, float act_range, int variant, int relu, float* gx,
                           float* g_residual, float* ggamma, float* gbeta, double* ws, uint32_t* counter,
                           alignq_stream_t stream);
+/* The apply pass of the backward alone, for a gy that came out of alignq_conv3x3_bwd_data_bnreduce (below): that
+ * convolution's epilogue has already formed the two BatchNorm-backward sums and left their means in `ws`.   */
+int alignq_bn_act_bwd_apply(const float* x, const float* y, const float* gy, int64_t rows, int C, const float* gamma,
+                            const float* beta, const float* save_mean, const float* save_invstd, int a_bit,
+                            float act_range, int variant, int relu, float* gx, float* g_residual, double* ws,
+                            alignq_stream_t stream);
 
 
 /* ---- 3x3 convolution of the quantized conv layers on the tensor cores (tcgen05) ------------------------------
@@ -238,6 +244,17 @@ int alignq_conv3x3_fwd(const float* x, const float* w, float* y, int N, int H, i
                        alignq_stream_t stream);
 int alignq_conv3x3_bwd_data(const float* gy, const float* w, float* gx, int N, int H, int W, int C, int mode,
                             alignq_stream_t stream);
+/* The data gradient with the reduce pass of the PRECEDING bn-act layer's backward in its epilogue (C = 16).  gx, the
+ * gradient with respect to the convolution's input, is that layer's upstream gradient: the epilogue adds gy2 (nullable:
+ * the gradient of a second consumer of the same tensor, e.g. the block shortcut, resnet.py:70-78) and WRITES THE SUM to
+ * gx, forms g_z = gx [bn_y > 0 if relu] 2 ar phi(z) from bn_x (the bn-act layer's input; bn_y its output, i.e. this
+ * convolution's forward input) and accumulates sum g_z, sum g_z xhat into the layer's workspace; the last CTA writes
+ * ggamma / gbeta ([C], nullable) and the two means.  Follow it with alignq_bn_act_bwd_apply on the same workspace. */
+int alignq_conv3x3_bwd_data_bnreduce(const float* gy, const float* w, float* gx, int N, int H, int W, int C, int mode,
+                                     const float* bn_x, const float* bn_y, const float* gy2, const float* save_mean,
+                                     const float* save_invstd, const float* gamma, const float* beta, float act_range,
+                                     int relu, float* ggamma, float* gbeta, double* bn_ws, uint32_t* bn_counter,
+                                     alignq_stream_t stream);
 /* The forward convolution with the batch statistics of the FOLLOWING BatchNorm2d taken from its epilogue (C in {16, 32}):
  * save_mean / save_invstd [C] out, running statistics updated (nullable), *num_batches_tracked += 1 (nullable); bn_ws /
  * bn_counter are that BatchNorm layer's alignq_bn_act_* workspace (same accumulator layout, same last-block finalisation).

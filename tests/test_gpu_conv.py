@@ -195,3 +195,54 @@ def test_stem_conv_epilogue_bn_statistics(Cout, H):
     assert bad <= max(2, int(1e-4 * y.numel())), f"{bad} codes differ"      # BN-output rounding ties only (fp32 library arm)
     assert relmax(conv.weight.grad, conv2.weight.grad) <= 1e-3
     assert relmax(bn.weight.grad, bn2.weight.grad) <= 1e-3
+
+
+@pytest.mark.parametrize("mode", ["tf32x3", "tf32"])
+def test_bn_act_backward_reduce_in_the_data_gradient_epilogue(mode):
+    """Two residual blocks of the C = 16 stage (resnet.py:51-55): with ``fuse_dgrad_bn`` the data-gradient kernel of each
+    own convolution also runs the reduce pass of the preceding bn-act layer's backward (sum g_z, sum g_z xhat, the
+    affine gradients) and adds the parked shortcut gradient, so that layer's backward is its apply pass alone
+    (alignq_conv3x3_bwd_data_bnreduce + alignq_bn_act_bwd_apply).  Same forward, so the gradients must agree with the
+    un-fused backward to fp32 summation-order noise."""
+    import copy
+    from alignq_b200.model.fused import bn_act
+    from alignq_b200.model.resnet import PreActBlock_conv_Q
+    torch.manual_seed(70)
+    base = dict(variant="A", bitW=8, abitW=8, act_range=2, fuse_bn_act=True, own_conv=mode, own_conv_channels=(16,), method="none")
+    aq.set_args(**base)
+    C, N, H = 16, 32, 32
+    blocks = torch.nn.ModuleList([PreActBlock_conv_Q("second", 8, 8, C, C, 1, variant="A") for _ in range(2)]).to(DEV).train()
+    bn0 = torch.nn.BatchNorm2d(C).to(DEV).train()
+    q0 = aq.activation_quantize_fn(8, "second")
+    for m in blocks.modules():
+        if isinstance(m, torch.nn.Conv2d):
+            m.weight.data = m.weight.data.contiguous(memory_format=torch.channels_last)
+        if isinstance(m, torch.nn.BatchNorm2d):
+            with torch.no_grad():
+                m.weight.copy_(1 + 0.2 * torch.randn(C, device=DEV))
+                m.bias.copy_(0.1 * torch.randn(C, device=DEV))
+    x0 = torch.randn(N, C, H, H, device=DEV).contiguous(memory_format=torch.channels_last)
+    gy = torch.randn_like(x0)
+    lib = L.load()
+    res = []
+    for fuse in (True, False):
+        aq.set_args(fuse_dgrad_bn=fuse)
+        net, bn = copy.deepcopy(blocks), copy.deepcopy(bn0)
+        x = x0.clone().requires_grad_(True)
+        n0 = lib.alignq_launch_count()
+        out = bn_act(bn, q0, x, True)               # the stem's bn-act: its output feeds block 1 (conv path + shortcut)
+        for blk in net:
+            out = blk(out)
+        (out * gy).sum().backward()
+        torch.cuda.synchronize()
+        grads = [x.grad.clone()] + [p.grad.clone() for p in list(bn.parameters()) + list(net.parameters())]
+        res.append((out.detach().clone(), grads, lib.alignq_launch_count() - n0))
+    aq.set_args(fuse_dgrad_bn=True)
+    assert torch.equal(res[0][0], res[1][0])                          # identical forward
+    assert res[0][2] == res[1][2] - 4, (res[0][2], res[1][2])         # four reduce launches fewer (one per own convolution)
+    worst = 0.0
+    for a, b in zip(res[0][1], res[1][1]):
+        assert a.shape == b.shape
+        worst = max(worst, relmax(a, b))
+    print(f"fuse_dgrad_bn {mode}: worst max|d|/max|ref| over x.grad and {len(res[0][1]) - 1} parameter gradients {worst:.2e}")
+    assert worst <= 2e-5, worst

@@ -35,6 +35,8 @@ def run(fn, shape, flush):
     for _ in range(3):
         if flush:
             junk.zero_()
+        torch.cuda.synchronize()
+        assert lib.alignq_conv_trace_reset() == 0
         rc = getattr(lib, fn)(x.data_ptr(), w.data_ptr(), y.data_ptr(), N, H, W, Cc, 0, s)
         assert rc == 0, rc
     torch.cuda.synchronize()
@@ -58,7 +60,7 @@ def run(fn, shape, flush):
 
 
 if __name__ == "__main__":
-    shapes = [(128, 16, 32, 32)]
+    shapes = [(128, 16, 32, 32), (128, 32, 16, 16), (128, 64, 8, 8)]
     for shape in shapes:
         for fn in ("alignq_conv3x3_fwd", "alignq_conv3x3_bwd_data"):
             run(fn, shape, True)

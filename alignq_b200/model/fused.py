@@ -76,6 +76,44 @@ def fork(x):
     return xa, xb
 
 
+class side_branch:
+    """``with side_branch(x) as br: y = f(x)`` ... ``br.join(y)``: run an independent branch of the forward pass on a side
+    stream beside what the caller launches until ``join`` (CUDA events both ways, so the pattern is captured into the
+    step's CUDA graph as parallel branches; autograd replays each node's backward on its forward stream).  Active only
+    inside a training step that opted in (``args.async_wgrad``) and never with cross-GPU BatchNorm statistics, whose
+    kernels must all sit in one stream order; otherwise the branch simply runs in line."""
+
+    _streams = {}
+
+    def __init__(self, x):
+        self.on = bool(args.async_wgrad and not args.sync_bn and x.is_cuda)
+        self.ctx = None
+        if self.on:
+            dev = x.device.index
+            if dev not in side_branch._streams:
+                side_branch._streams[dev] = torch.cuda.Stream(device=x.device)
+            self.side = side_branch._streams[dev]
+            self.main = torch.cuda.current_stream(x.device)
+
+    def __enter__(self):
+        if self.on:
+            self.side.wait_stream(self.main)
+            self.ctx = torch.cuda.stream(self.side)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
+
+    def join(self, *tensors):
+        if self.on:
+            self.main.wait_stream(self.side)
+            for t in tensors:
+                t.record_stream(self.main)          # allocated on the side stream, consumed on the caller's
+
+
 def _linked(fn, *fn_args, residual=None):
     """Run a bn-act autograd function with a fresh link and hang the link on its output (see fork)."""
     link = {}

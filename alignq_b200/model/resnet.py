@@ -12,7 +12,7 @@ import torch.nn.functional as F
 
 from ..utils.admm import ADMM
 from ..utils.options import args
-from .fused import avgpool_linear_ce, bn_act, conv_bn_act, fork
+from .fused import avgpool_linear_ce, bn_act, conv_bn_act, fork, side_branch
 from .quantization import activation_quantize_fn, conv2d_Q_fn
 
 
@@ -51,8 +51,16 @@ class PreActBlock_conv_Q(nn.Module):
     def forward(self, x):
         if not self.with_admm:
             x, xs = fork(x)           # two consumers: their gradients meet inside the producer's backward kernel
-            shortcut = xs if self.skip_conv is None else bn_act(self.skip_bn, self.act_skip_q, self.skip_conv(xs), False)
-            out = conv_bn_act(self.conv0, self.bn0, self.act_q0, x, True)      # relu(act_q0(bn0(conv0(x))))
+            if self.skip_conv is None:
+                shortcut = xs
+                out = conv_bn_act(self.conv0, self.bn0, self.act_q0, x, True)  # relu(act_q0(bn0(conv0(x))))
+            else:
+                # the projection shortcut (1x1 conv -> bn -> act-quant) does not depend on conv0 / bn0: inside a training
+                # step it runs on a side stream beside them (autograd runs its backward on that stream as well)
+                with side_branch(xs) as br:
+                    shortcut = bn_act(self.skip_bn, self.act_skip_q, self.skip_conv(xs), False)
+                out = conv_bn_act(self.conv0, self.bn0, self.act_q0, x, True)
+                br.join(shortcut)
             return conv_bn_act(self.conv1, self.bn1, self.act_q1, out, True, residual=shortcut)   # relu(act_q1(.) + shortcut)
         trans_loss = 0.
         shortcut = x

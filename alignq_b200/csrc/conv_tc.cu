@@ -22,6 +22,7 @@
 // default under torch.backends.cudnn.allow_tf32 = True, the reference's own GPU path; ~5e-4 relative); ALIGNQ_CONV_TF32X3 =
 // operands split v = H + L (H = top 19 bits), three MMAs (H H into the main accumulator, H L + L H into a second one:
 // the tensor core truncates when it adds into the fp32 accumulator), fp32-level parity with F.conv2d (tested to 1e-5).
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "tc_small_common.cuh"
@@ -208,27 +209,54 @@ conv3x3_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, fl
   // ---- weights -> shared memory (K-major N x K tiles per tap), once per CTA ---------------------------------------
   // B-operand element (row r = N index, k): (r / 8) * SBO_W + (r % 8) * 16 + (k / 4) * 128 + (k % 4) * 4, SBO_W = (C/4) * 128
   constexpr int SBO_W = (C / 4) * 128;
-  for (int idx = threadIdx.x; idx < 9 * C * (C / 4); idx += NT) {
-    const int k4 = idx % (C / 4), r = (idx / (C / 4)) % C, tap = idx / (C * (C / 4));
-    const int kh = tap / 3, kw = tap % 3;
-    float v[4];
-    if (!FLIP) {                                                   // row = co, k = ci: 4 consecutive ci of w[co][kh][kw][:]
-      const float4 t = __ldg(reinterpret_cast<const float4*>(w + ((size_t)(r * 3 + kh) * 3 + kw) * C + 4 * k4));
-      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-    } else {                                                       // row = ci, k = co: w[co][2-kh][2-kw][ci] for 4 consecutive co
+  {
+    // item = (tap, row co, 4 consecutive ci): one 16-byte load of w[co][kh][kw][4 ci4 ..].  Loads are issued in batches
+    // (one dependent round trip to L2 per batch: a loop that loaded and stored item by item spent 6 us here at C = 32)
+    // and then deposited: forward -> one 16-byte row chunk (row co, k = ci); data gradient -> four scalars, transposed
+    // (rows ci, k = co) into the flipped tap 8 - tap.
+    constexpr int NITEM = 9 * C * (C / 4), PER = (NITEM + NT - 1) / NT, BATCH = PER < 12 ? PER : 12;
+#pragma unroll 1
+    for (int b0 = 0; b0 < PER; b0 += BATCH) {
+      float4 t[BATCH];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) v[e] = __ldg(w + ((size_t)((4 * k4 + e) * 3 + (2 - kh)) * 3 + (2 - kw)) * C + r);
-    }
-    uint8_t* d = wsm + tap * F::W_TAP + (r >> 3) * SBO_W + (r & 7) * 16 + k4 * 128;
-    if (NS == 1) {
-      *reinterpret_cast<uint4*>(d) = make_uint4(cvt_tf32(v[0]), cvt_tf32(v[1]), cvt_tf32(v[2]), cvt_tf32(v[3]));
-    } else {
-      uint32_t h[4];
-      float l[4];
+      for (int i = 0; i < BATCH; ++i) {
+        const int idx = threadIdx.x + (b0 + i) * NT;
+        t[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (idx < NITEM) t[i] = __ldg(reinterpret_cast<const float4*>(w) + idx);      // physical [co][tap][ci]: idx = (co * 9 + tap) * C/4 + ci4
+      }
 #pragma unroll
-      for (int e = 0; e < 4; ++e) { h[e] = __float_as_uint(v[e]) & 0xFFFFE000u; l[e] = v[e] - __uint_as_float(h[e]); }
-      *reinterpret_cast<uint4*>(d) = make_uint4(h[0], h[1], h[2], h[3]);
-      *reinterpret_cast<float4*>(d + W_BYTES) = make_float4(l[0], l[1], l[2], l[3]);
+      for (int i = 0; i < BATCH; ++i) {
+        const int idx = threadIdx.x + (b0 + i) * NT;
+        if (idx >= NITEM) continue;
+        const int ci4 = idx % (C / 4), tap = (idx / (C / 4)) % 9, co = idx / (9 * (C / 4));
+        const float v[4] = {t[i].x, t[i].y, t[i].z, t[i].w};
+        if (!FLIP) {
+          uint8_t* d = wsm + tap * F::W_TAP + (co >> 3) * SBO_W + (co & 7) * 16 + ci4 * 128;
+          if (NS == 1) {
+            *reinterpret_cast<uint4*>(d) = make_uint4(cvt_tf32(v[0]), cvt_tf32(v[1]), cvt_tf32(v[2]), cvt_tf32(v[3]));
+          } else {
+            uint32_t h[4];
+            float l[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { h[e] = __float_as_uint(v[e]) & 0xFFFFE000u; l[e] = v[e] - __uint_as_float(h[e]); }
+            *reinterpret_cast<uint4*>(d) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<float4*>(d + W_BYTES) = make_float4(l[0], l[1], l[2], l[3]);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int r = 4 * ci4 + e;                             // row = ci, k = co
+            uint8_t* d = wsm + (8 - tap) * F::W_TAP + (r >> 3) * SBO_W + (r & 7) * 16 + (co >> 2) * 128 + (co & 3) * 4;
+            if (NS == 1) {
+              *reinterpret_cast<uint32_t*>(d) = cvt_tf32(v[e]);
+            } else {
+              const uint32_t h = __float_as_uint(v[e]) & 0xFFFFE000u;
+              *reinterpret_cast<uint32_t*>(d) = h;
+              *reinterpret_cast<float*>(d + W_BYTES) = v[e] - __uint_as_float(h);
+            }
+          }
+        }
+      }
     }
   }
   // the input is the preceding kernel's output: wait for it, then request the first tile's positions
@@ -485,9 +513,29 @@ __host__ __device__ constexpr int plane_stride_bf16(int C, int npt) {
 // bf16-term planes (tiles `term_off` bytes apart) from fetched 8-channel items.
 // IM2COL = false: unit c8, position j.   IM2COL = true (the x operand; npt = KT + 2 Wp + 2 halo positions were fetched):
 // source position j is written to unit (tap, c8) at position j - shift(tap) for every tap of the CTA that needs it.
+// NSB = 1: ONE fp16 term per value (11 significand bits = tf32's), the value multiplied by a power of two first (exact)
+// so that the tile's largest magnitude sits near 2^14 -- fp16's narrow exponent range then costs nothing: elements
+// more than 2^28 below the largest one lose bits, and their products are that far below the sum's own rounding error.
+// Saturating: |v| scale > 65504 (only possible for the unscaled x operand) becomes +-65504, never inf.
+__device__ __forceinline__ uint4 pack_fp16x8(const float (&c)[8], float scale) {
+  uint32_t h[4];
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const float a = fminf(fmaxf(c[2 * p] * scale, -65504.f), 65504.f), b = fminf(fmaxf(c[2 * p + 1] * scale, -65504.f), 65504.f);
+    const __half2 hh = __floats2half2_rn(a, b);
+    h[p] = *reinterpret_cast<const uint32_t*>(&hh);
+  }
+  return make_uint4(h[0], h[1], h[2], h[3]);
+}
+template <int NSB>
+__device__ __forceinline__ void make_terms(const float (&c)[8], float scale, uint4 (&t)[NSB]) {
+  if constexpr (NSB == 1) t[0] = pack_fp16x8(c, scale);
+  else tcsmall::split_chunk_n<NSB>(c, t);
+}
+
 template <int C, int NSB, bool IM2COL, int TAPS, int MAXI>
 __device__ __forceinline__ void deposit_bf16(const float4 (&v)[MAXI][2], const Geo& G, int npt, int kt, int tap0,
-                                             uint8_t* planes, int PS, int term_off) {
+                                             uint8_t* planes, int PS, int term_off, float scale = 1.f) {
   constexpr int C8 = C / 8, STEP = NT / C8;
   const int c8 = threadIdx.x % C8;
   const int j0 = threadIdx.x / C8;
@@ -496,11 +544,12 @@ __device__ __forceinline__ void deposit_bf16(const float4 (&v)[MAXI][2], const G
     const int j = j0 + i * STEP;
     if (j >= npt) continue;
     const float c[8] = {v[i][0].x, v[i][0].y, v[i][0].z, v[i][0].w, v[i][1].x, v[i][1].y, v[i][1].z, v[i][1].w};
+    uint4 t[NSB];
+    make_terms<NSB>(c, scale, t);
     if (!IM2COL) {
-      tcsmall::store_chunk_n<NSB>(planes + c8 * PS + j * 16, term_off, c);
+#pragma unroll
+      for (int k = 0; k < NSB; ++k) *reinterpret_cast<uint4*>(planes + c8 * PS + j * 16 + k * term_off) = t[k];
     } else {
-      uint4 t[NSB];
-      tcsmall::split_chunk_n<NSB>(c, t);
 #pragma unroll
       for (int tt = 0; tt < TAPS; ++tt) {
         const int tap = tap0 + tt;
@@ -518,7 +567,7 @@ __device__ __forceinline__ void deposit_bf16(const float4 (&v)[MAXI][2], const G
 template <int C, int NSB, int TAPS, bool CROSS, int MAXG, int MAXX>
 __global__ void __launch_bounds__(NT)
 conv3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ partials, Geo G,
-                     int ntiles, int npx, int PS) {
+                     int ntiles, int npx, int PS, float* __restrict__ inv_scales) {
   using K = WgCfg<C>;
   constexpr int C8 = C / 8;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -533,8 +582,15 @@ conv3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ gy, 
   // halves the TMEM columns so that two CTAs fit on an SM (a second 512-column allocation would wait for the first)
   constexpr int NEED = CROSS ? 2 * ACC : ACC;
   constexpr int TCOLS = NEED <= 32 ? 32 : NEED <= 64 ? 64 : NEED <= 128 ? 128 : NEED <= 256 ? 256 : 512;
-  static_assert(NEED <= 512 && ACC <= 256 && ACC % 8 == 0, "weight-gradient MMA shape");
+  constexpr int NSPLIT = ACC > 256 ? 2 : 1;                        // an MMA's N is at most 256: wider sets take two
+  constexpr int NMMA = ACC / NSPLIT;
+  static_assert(NEED <= 512 && NMMA <= 256 && NMMA % 16 == 0 && (TAPS * C8) % NSPLIT == 0, "weight-gradient MMA shape");
+  static_assert(NSB != 1 || !CROSS, "the single-term mode has one accumulator set");
   const int tap0 = blockIdx.y * TAPS;
+  TRACE(0);
+#ifdef ALIGNQ_CONV_TRACE
+  trace_smid();
+#endif
 
   if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
   if (warp == 0) tmem_alloc(tmem_slot, TCOLS);
@@ -542,21 +598,49 @@ conv3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ gy, 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // bf16 operands, both MN-major (bits 15, 16)
-  constexpr uint32_t IDESC = make_idesc(1u /*bf16*/, 64u, (uint32_t)ACC) | (1u << 15) | (1u << 16);
+  // bf16 terms (fp16 in the single-term mode), both operands MN-major (bits 15, 16)
+  constexpr uint32_t IDESC = make_idesc(NSB == 1 ? 0u /*fp16*/ : 1u /*bf16*/, 64u, (uint32_t)NMMA) | (1u << 15) | (1u << 16);
 
   float4 fg[MAXG][2], fx[MAXX][2];
+  // Single-term mode: this CTA's power-of-two scale for gy, from the largest |gy| over ITS tiles (a first pass over gy,
+  // which the main pass then finds in L2); the partial sums are scaled back by the reduce kernel, exactly.
+  float gscale = 1.f, ginv = 1.f;
+  if constexpr (NSB == 1) {
+    __shared__ float wmax[NT / 32];
+    float amax = 0.f;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      fetch_items<C, 2, true, MAXG>(gy, G, tile * K::KT, K::KT, fg);
+#pragma unroll
+      for (int i = 0; i < MAXG; ++i)
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+          amax = fmaxf(amax, fmaxf(fmaxf(fabsf(fg[i][k].x), fabsf(fg[i][k].y)), fmaxf(fabsf(fg[i][k].z), fabsf(fg[i][k].w))));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if (lane == 0) wmax[warp] = amax;
+    __syncthreads();
+#pragma unroll
+    for (int wv = 0; wv < NT / 32; ++wv) amax = fmaxf(amax, wmax[wv]);
+    const int e = (int)((__float_as_uint(amax) >> 23) & 0xffu);      // amax in [2^(e-127), 2^(e-126))
+    if (e >= 16 && e < 255) {                                        // (zero / denormal-tiny / inf / nan: unscaled)
+      gscale = __uint_as_float((uint32_t)(268 - e) << 23);           // 2^(14 - (e - 127)): scaled amax in [2^14, 2^15)
+      ginv = __uint_as_float((uint32_t)(e - 14) << 23);
+    }
+  }
+  TRACE(1);
   if ((int)blockIdx.x < ntiles) {
     fetch_items<C, 2, true, MAXG>(gy, G, blockIdx.x * K::KT, K::KT, fg);
     fetch_items<C, 2, false, MAXX>(x, G, blockIdx.x * K::KT, npx, fx);
   }
   int it = 0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-    deposit_bf16<C, NSB, false, 1, MAXG>(fg, G, K::KT, K::KT, 0, gplanes, PS, gtile);       // gy is zero at pad positions
+    deposit_bf16<C, NSB, false, 1, MAXG>(fg, G, K::KT, K::KT, 0, gplanes, PS, gtile, gscale);   // gy is zero at pad positions
     deposit_bf16<C, NSB, true, TAPS, MAXX>(fx, G, npx, K::KT, tap0, xplanes, PS, xtile);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
+    if (it < 2) TRACE(2 + 4 * it);
     if (threadIdx.x == 0) {
       tc_fence_after();
       const uint32_t sg = smem_u32(gplanes), sx = smem_u32(xplanes);
@@ -567,6 +651,12 @@ conv3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ gy, 
         // MN-major: LBO = stride of the 8-position K groups (128 B: K is linear in the position), SBO = unit stride
         const uint32_t ga = sg + ks * 256, xa = sx + ks * 256;
         const uint64_t ah = make_desc(ga, 128, PS), bh = make_desc(xa, 128, PS);
+        if constexpr (NSB == 1) {                                            // one product; N in NSPLIT pieces
+#pragma unroll
+          for (int h = 0; h < NSPLIT; ++h)
+            umma<false>(d_main + h * NMMA, ah, make_desc(xa + h * (TAPS * C8 / NSPLIT) * PS, 128, PS), IDESC, acc);
+          continue;
+        }
         const uint64_t am = make_desc(ga + gtile, 128, PS), bm = make_desc(xa + xtile, 128, PS);
         umma<false>(d_main, ah, bh, IDESC, acc);                             // H H
         umma<false>(d_cross, ah, bm, IDESC, CROSS ? acc : 1u);               // the small products
@@ -579,6 +669,7 @@ conv3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ gy, 
         }
       }
       umma_commit(bar);
+      if (it < 2) TRACE(3 + 4 * it);
     }
     if (tile + (int)gridDim.x < ntiles) {                          // next tile -> registers while the tensor core works
       fetch_items<C, 2, true, MAXG>(gy, G, (tile + gridDim.x) * K::KT, K::KT, fg);
@@ -586,9 +677,13 @@ conv3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ gy, 
     }
     mbar_wait(bar, (uint32_t)(it & 1));                            // the planes are rewritten by the next deposit
     tc_fence_after();
+    if (it < 2) TRACE(4 + 4 * it);
     tc_fence_before();
     __syncthreads();
+    if (it < 2) TRACE(5 + 4 * it);
   }
+  TRACE(13);
+  if (threadIdx.x == 0 && inv_scales) inv_scales[blockIdx.y * gridDim.x + blockIdx.x] = ginv;
   // ---- epilogue: accumulator row co = 16 w + l sits in lane l of warp w's quarter (w < C / 16, l < 16) ------------
   // (all 32 lanes of a warp must take part in tcgen05.ld: the store is predicated instead)
   if (warp < 4) {
@@ -623,6 +718,7 @@ conv3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ gy, 
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, TCOLS);
+  TRACE(14);
 }
 
 // gw[co][kh][kw][ci] (+)= sum over the CTAs' partials [grp][cta][co][TAPS * C], fixed order.  Block = 32 elements x
@@ -630,7 +726,7 @@ conv3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ gy, 
 // version with one thread per element walking all ~300 partials took 26 us -- longer than the MMA kernel itself.)
 __global__ void __launch_bounds__(1024)
 conv3x3_wgrad_reduce_kernel(const float* __restrict__ partials, int nparts, int C, int taps, float* __restrict__ gw,
-                            int accumulate) {
+                            int accumulate, const float* __restrict__ inv_scales) {
   __shared__ float sm[32][33];
   const int e = blockIdx.x * 32 + threadIdx.x;                    // index into [co][9][ci]
   const int pl = threadIdx.y;
@@ -641,7 +737,11 @@ conv3x3_wgrad_reduce_kernel(const float* __restrict__ partials, int nparts, int 
     const int grp = tap / taps, t = tap - grp * taps;
     const int acc = taps * C;
     const float* p = partials + ((size_t)grp * nparts * C + co) * acc + t * C + ci;
-    for (int k = pl; k < nparts; k += 32) s += p[(size_t)k * C * acc];
+    if (inv_scales) {                                              // per-CTA powers of two of the single-term mode: exact
+      for (int k = pl; k < nparts; k += 32) s += p[(size_t)k * C * acc] * inv_scales[grp * nparts + k];
+    } else {
+      for (int k = pl; k < nparts; k += 32) s += p[(size_t)k * C * acc];
+    }
   }
   sm[pl][threadIdx.x] = s;
   __syncthreads();
@@ -712,21 +812,23 @@ static int launch_wgrad(const float* x, const float* gy, float* gw, int N, int H
   const int groups = 9 / TAPS;
   int per_sm = (int)((227 * 1024) / (smem + 1024));
   if (per_sm > env_int("ALIGNQ_WGRAD_PER_SM", 2)) per_sm = env_int("ALIGNQ_WGRAD_PER_SM", 2);
+  if ((CROSS ? 2 : 1) * TAPS * C > 256) per_sm = 1;              // a 512-column TMEM allocation: a second CTA would wait
   if (per_sm < 1) per_sm = 1;
   int grid = ALIGNQ_NUM_SMS * per_sm / groups;
   if (grid > ntiles) grid = ntiles;
   if (grid < 1) grid = 1;
   const size_t need = (size_t)groups * grid * C * TAPS * C * sizeof(float);
-  if (ws_bytes < need) return ALIGNQ_ENOSPACE;
+  if (ws_bytes < need + (size_t)groups * grid * sizeof(float)) return ALIGNQ_ENOSPACE;
+  float* inv_scales = NSB == 1 ? ws + need / sizeof(float) : nullptr;
   constexpr int STEP = NT / (C / 8);
   constexpr int MAXG = (K::KT + STEP - 1) / STEP, MAXX = (K::KT + 2 * 34 + 2 + STEP - 1) / STEP;
   if (npx > MAXX * STEP) return ALIGNQ_ERANGE;                  // wider images: the caller's library convolution
   cudaError_t e = cudaFuncSetAttribute(conv3x3_wgrad_kernel<C, NSB, TAPS, CROSS, MAXG, MAXX>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  conv3x3_wgrad_kernel<C, NSB, TAPS, CROSS, MAXG, MAXX><<<dim3(grid, groups), NT, smem, s>>>(x, gy, ws, G, ntiles, npx, PS);
+  conv3x3_wgrad_kernel<C, NSB, TAPS, CROSS, MAXG, MAXX><<<dim3(grid, groups), NT, smem, s>>>(x, gy, ws, G, ntiles, npx, PS, inv_scales);
   ALIGNQ_LAUNCH_CHECK();
-  conv3x3_wgrad_reduce_kernel<<<(C * 9 * C + 31) / 32, dim3(32, 32), 0, s>>>(ws, grid, C, TAPS, gw, accumulate);
+  conv3x3_wgrad_reduce_kernel<<<(C * 9 * C + 31) / 32, dim3(32, 32), 0, s>>>(ws, grid, C, TAPS, gw, accumulate, inv_scales);
   ALIGNQ_LAUNCH_CHECK();
   return ALIGNQ_OK;
 }
@@ -817,7 +919,7 @@ extern "C" int alignq_conv3x3_bwd_data_bnreduce(const float* gy, const float* w,
 
 extern "C" size_t alignq_conv3x3_ws_bytes(int C) {
   // partials of at most 2 CTAs per SM: [groups * ctas][C][taps * C] floats = ctas_total * C * 9 * C / groups... <= 2 * 148 * 9 C^2
-  return (size_t)2 * ALIGNQ_NUM_SMS * 9 * C * C * sizeof(float);
+  return (size_t)2 * ALIGNQ_NUM_SMS * 9 * C * C * sizeof(float) + (size_t)8 * ALIGNQ_NUM_SMS * sizeof(float);
 }
 
 extern "C" int alignq_conv3x3_bwd_weight(const float* x, const float* gy, float* gw, int N, int H, int W, int C, int mode,
@@ -828,6 +930,14 @@ extern "C" int alignq_conv3x3_bwd_weight(const float* x, const float* gy, float*
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   float* wsf = reinterpret_cast<float*>(ws);
   // bf16 terms per value: 2 (16 bits, >= tf32) or 3 (24 bits); taps per CTA so that main + cross accumulators fit TMEM
+  // TF32 mode: ONE fp16 term per value (11 significand bits = tf32's; gy scaled per CTA by a power of two), one MMA per
+  // k-step -- a third of the tensor work and half the staging of the two-term bf16 split this mode used before
+  // (ALIGNQ_WGRAD_TERMS=2 brings that back); TF32X3 mode: three bf16 terms (24 bits), six MMAs.
+  if (mode == ALIGNQ_CONV_TF32 && env_int("ALIGNQ_WGRAD_TERMS", 1) == 1) {
+    if (C == 16) return launch_wgrad<16, 1, 9, false>(x, gy, gw, N, H, W, accumulate, wsf, ws_bytes, s);
+    if (C == 32) return launch_wgrad<32, 1, 9, false>(x, gy, gw, N, H, W, accumulate, wsf, ws_bytes, s);
+    return launch_wgrad<64, 1, 3, false>(x, gy, gw, N, H, W, accumulate, wsf, ws_bytes, s);
+  }
   if (mode == ALIGNQ_CONV_TF32) {
     if (C == 16) return launch_wgrad<16, 2, 9, false>(x, gy, gw, N, H, W, accumulate, wsf, ws_bytes, s);
     if (C == 32) return launch_wgrad<32, 2, 3, false>(x, gy, gw, N, H, W, accumulate, wsf, ws_bytes, s);

@@ -25,7 +25,7 @@ def _workspace(C, device):
     return ws
 
 
-def applies(x, weight, stride, padding, dilation, groups, bias) -> bool:
+def _covered(x, weight, stride, padding, dilation, groups, bias, channels) -> bool:
     if args.own_conv == "off" or bias is not None or groups != 1:
         return False
     if tuple(stride) != (1, 1) or tuple(padding) != (1, 1) or tuple(dilation) != (1, 1):
@@ -33,11 +33,23 @@ def applies(x, weight, stride, padding, dilation, groups, bias) -> bool:
     if weight.dim() != 4 or tuple(weight.shape[2:]) != (3, 3) or weight.shape[0] != weight.shape[1]:
         return False
     C = weight.shape[0]
-    if C not in (16, 32, 64) or C not in tuple(args.own_conv_channels) or (C == 64 and args.own_conv == "tf32x3"):
+    if C not in (16, 32, 64) or C not in tuple(channels) or (C == 64 and args.own_conv == "tf32x3"):
         return False
     return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] == C
             and x.is_contiguous(memory_format=torch.channels_last) and x.data_ptr() % 16 == 0
             and weight.dtype == torch.float32 and weight.data_ptr() % 16 == 0)
+
+
+def applies(x, weight, stride, padding, dilation, groups, bias) -> bool:
+    """Forward + data gradient (+ weight gradient) on the own kernels."""
+    return _covered(x, weight, stride, padding, dilation, groups, bias, args.own_conv_channels)
+
+
+def applies_wgrad(x, weight, stride, padding, dilation, groups, bias) -> bool:
+    """The WEIGHT gradient alone on the own kernel (``own_wgrad_channels``): at C = 32 / 64 the library's forward and data
+    gradient are still the faster ones, its split-K weight gradient (14-21 us per layer, a memset in front) is not."""
+    return (_covered(x, weight, stride, padding, dilation, groups, bias, tuple(args.own_conv_channels) + tuple(args.own_wgrad_channels))
+            and weight.is_contiguous(memory_format=torch.channels_last))
 
 
 class _Conv3x3Fn(torch.autograd.Function):
@@ -141,8 +153,9 @@ class _ConvQFn(torch.autograd.Function):
     """Any bias-free Conv2d_Q convolution with the weight gradient on the side stream."""
 
     @staticmethod
-    def forward(ctx, x, w, stride, padding, dilation, groups, own, mode, bn=None, bn_ws=None, sync=True, up=None):
+    def forward(ctx, x, w, stride, padding, dilation, groups, own, mode, bn=None, bn_ws=None, sync=True, up=None, own_w=None):
         mean = invstd = None
+        own_w = own if own_w is None else bool(own_w)      # the weight gradient may take the own kernel on its own
         ctx.up = up if own else None                  # link of the fused bn-act layer that produced x (fused.py), or None
         if own:
             N, C, H, W = x.shape
@@ -165,7 +178,7 @@ class _ConvQFn(torch.autograd.Function):
             wc = w
             y = torch.ops.aten.convolution(x, w, None, stride, padding, dilation, False, (0, 0), groups)
         ctx.save_for_backward(x, wc)
-        ctx.cfg = (tuple(stride), tuple(padding), tuple(dilation), groups, own, mode, bool(sync))
+        ctx.cfg = (tuple(stride), tuple(padding), tuple(dilation), groups, own, mode, bool(sync), own_w)
         ctx.w_like = w
         ctx.gup = getattr(w, "_alignq_gup", None) if sync else None    # (WeightBank, layer index) or None
         ctx.set_materialize_grads(False)              # no zero-fill launches for the (non-differentiable) statistics outputs
@@ -177,12 +190,12 @@ class _ConvQFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy, *_unused):
         if gy is None:
-            return (None,) * 12
+            return (None,) * 13
         x, wc = ctx.saved_tensors
-        stride, padding, dilation, groups, own, mode, on_side = ctx.cfg
+        stride, padding, dilation, groups, own, mode, on_side, own_w = ctx.cfg
         lib = L.load()
         gx = gw = None
-        if own:
+        if own or own_w:
             gy = L.like_layout(gy, x, "grad of conv output")
         else:
             gy = gy if gy.is_contiguous(memory_format=torch.channels_last) or gy.is_contiguous() else gy.contiguous()
@@ -197,7 +210,7 @@ class _ConvQFn(torch.autograd.Function):
                 if slot.shape != wc.shape or slot.stride() != wc.stride() or slot.data_ptr() % 16:
                     slot = None
             with torch.cuda.stream(side):
-                if own:
+                if own_w:
                     N, C, H, W = x.shape
                     gw = slot if slot is not None else torch.empty_like(wc)
                     wsp = _workspace(C, x.device)     # keyed by the side stream: successive launches there are ordered
@@ -238,14 +251,14 @@ class _ConvQFn(torch.autograd.Function):
                             int(relu), L.ptr(gw_bn), L.ptr(gb_bn), ws.data_ptr(), counter.data_ptr(), L.stream_ptr()),
                             "alignq_conv3x3_bwd_data_bnreduce")
                     ctx.up["reduced"] = (gx.data_ptr(), gw_bn, gb_bn)
-                    return gx, gw, None, None, None, None, None, None, None, None, None, None
+                    return gx, gw, None, None, None, None, None, None, None, None, None, None, None
                 with torch.cuda.device_of(x):
                     L.check(lib.alignq_conv3x3_bwd_data(gy.data_ptr(), wc.data_ptr(), gx.data_ptr(), N, H, W, C, mode,
                                                         L.stream_ptr()), "alignq_conv3x3_bwd_data")
             else:
                 gx, _, _ = torch.ops.aten.convolution_backward(gy, x, wc, None, stride, padding, dilation, False, (0, 0),
                                                                groups, (True, False, False))
-        return gx, gw, None, None, None, None, None, None, None, None, None, None
+        return gx, gw, None, None, None, None, None, None, None, None, None, None, None
 
 
 _stem_ws = {}
@@ -352,8 +365,9 @@ def conv_async_wgrad(x, weight, stride, padding, dilation, groups):
     if applies_stem(x, weight, stride, padding, dilation, groups, None):
         return stem_conv(x, weight)
     own = applies(x, weight, stride, padding, dilation, groups, None)
+    own_w = own or applies_wgrad(x, weight, stride, padding, dilation, groups, None)
     return _ConvQFn.apply(x, weight, tuple(stride), tuple(padding), tuple(dilation), groups, own,
-                          L.CONV_MODE_ID[args.own_conv] if own else 0, None, None, True, _up_link(x))
+                          L.CONV_MODE_ID[args.own_conv] if own_w else 0, None, None, True, _up_link(x), own_w)
 
 
 def conv_with_bn_stats(x, weight, bn, bn_ws):

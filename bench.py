@@ -332,7 +332,8 @@ def run_product(args):
     fuse = not (args.no_fuse or args.nchw)
     aq.set_args(variant="A", bitW=8, abitW=8, act_range=2, lam=1.0, lam2=4.0, method="ours", train_batch_size=BATCH,
                 fuse_bn_act=fuse, own_conv=("off" if args.nchw else args.own_conv), fused_head=not (args.no_fused_head or args.nchw),
-                own_conv_channels=tuple(int(c) for c in args.own_conv_channels.split(",") if c))
+                own_conv_channels=tuple(int(c) for c in args.own_conv_channels.split(",") if c),
+                own_wgrad_channels=tuple(int(c) for c in args.own_wgrad_channels.split(",") if c))
     torch.manual_seed(0)                                   # identical replicas on every rank
     batch, img_hw, ncls, forward_loss = BATCH, 32, 10, None
     # ADMM(dim): the GLOBAL batch in dp_gram='feature' mode (weak scaling: per-GPU batch x ranks), else the per-GPU batch
@@ -712,6 +713,7 @@ def main():
                     help="3x3 / stride-1 quantized convolutions on the hand-written tcgen05 kernels: tf32 (one pass, the numerics "
                     "of cuDNN under torch's default allow_tf32), tf32x3 (fp32 parity) or off (cuDNN everywhere)")
     ap.add_argument("--own-conv-channels", type=str, default="16", help="channel counts (Cin == Cout) routed to the own kernels")
+    ap.add_argument("--own-wgrad-channels", type=str, default="", help="further channel counts whose WEIGHT gradient alone runs on the own kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-local-bn-line", action="store_true", help="N>1: skip the extra timing with per-rank BatchNorm statistics")
     ap.add_argument("--no-dp-parity", action="store_true", help="N>1: skip the N-rank vs single-device parity block")

@@ -19,8 +19,12 @@ for name in ("alignq_conv3x3_fwd", "alignq_conv3x3_bwd_data"):
     getattr(lib, name).argtypes = [P, P, P, I, I, I, I, I, P]
     getattr(lib, name).restype = I
 lib.alignq_conv_trace_read.argtypes = [P, C.c_size_t]
+lib.alignq_conv3x3_bwd_weight.argtypes = [P, P, P, I, I, I, I, I, I, P, C.c_size_t, P]
+lib.alignq_conv3x3_bwd_weight.restype = I
+lib.alignq_conv3x3_ws_bytes.argtypes = [I]
+lib.alignq_conv3x3_ws_bytes.restype = C.c_size_t
 SLOTS, CTAS = 16, 1024
-NAMES = {0: "entry", 1: "weights staged, TMEM ready", 2: "tile0 deposited", 3: "tile0 MMAs issued", 4: "tile0 MMAs done",
+NAMES = {0: "entry", 1: "prologue done (weights / gy scale)", 2: "tile0 deposited", 3: "tile0 MMAs issued", 4: "tile0 MMAs done",
          5: "tile0 epilogue done", 6: "tile1 deposited", 7: "tile1 MMAs issued", 8: "tile1 MMAs done", 9: "tile1 epilogue done",
          13: "loop done", 14: "exit"}
 
@@ -32,12 +36,16 @@ def run(fn, shape, flush):
     y = torch.empty_like(x)
     junk = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     s = torch.cuda.current_stream().cuda_stream
+    ws = torch.empty(int(lib.alignq_conv3x3_ws_bytes(Cc)), dtype=torch.uint8, device="cuda")
     for _ in range(3):
         if flush:
             junk.zero_()
         torch.cuda.synchronize()
         assert lib.alignq_conv_trace_reset() == 0
-        rc = getattr(lib, fn)(x.data_ptr(), w.data_ptr(), y.data_ptr(), N, H, W, Cc, 0, s)
+        if fn == "alignq_conv3x3_bwd_weight":       # x, gy -> gw (w is the output here)
+            rc = lib.alignq_conv3x3_bwd_weight(x.data_ptr(), y.normal_().data_ptr(), w.data_ptr(), N, H, W, Cc, 0, 0, ws.data_ptr(), ws.numel(), s)
+        else:
+            rc = getattr(lib, fn)(x.data_ptr(), w.data_ptr(), y.data_ptr(), N, H, W, Cc, 0, s)
         assert rc == 0, rc
     torch.cuda.synchronize()
     buf = np.zeros(CTAS * SLOTS, dtype=np.uint64)

@@ -91,22 +91,23 @@ __device__ __forceinline__ void bn_cta_sums_finish(const float (&a)[C], const fl
   bn_cta_finish_from_red<C, NTHREADS>(red, ws, counter, fin);
 }
 
-// (sum, sum of squares) -> mean / invstd / running statistics, exactly as bnq_stats_kernel's last block does
+// (sum, sum of squares) of channel c -> mean / invstd / running statistics, exactly as bnq_stats_kernel's last block does
+__device__ __forceinline__ void bn_stat_finalize(const BnStat& bs, int c, double S, double SS) {
+  const double mean = S / bs.count;
+  double var = SS / bs.count - mean * mean;                        // biased: what BN normalises with
+  var = var < 0.0 ? 0.0 : var;
+  bs.save_mean[c] = (float)mean;
+  bs.save_invstd[c] = (float)(1.0 / sqrt(var + (double)bs.eps));
+  if (bs.running_mean) {
+    const double unbiased = bs.count > 1.0 ? var * bs.count / (bs.count - 1.0) : var;
+    bs.running_mean[c] = (float)((1.0 - bs.momentum) * bs.running_mean[c] + bs.momentum * mean);
+    bs.running_var[c] = (float)((1.0 - bs.momentum) * bs.running_var[c] + bs.momentum * unbiased);
+  }
+  if (c == 0 && bs.num_batches_tracked) *bs.num_batches_tracked += 1;
+}
 template <int C, int NTHREADS>
 __device__ __forceinline__ void bn_stat_cta_finish(const float (&st_s)[C], const float (&st_ss)[C], double* red, const BnStat& bs) {
-  bn_cta_sums_finish<C, NTHREADS>(st_s, st_ss, red, bs.ws, bs.counter, [&](int c, double S, double SS) {
-    const double mean = S / bs.count;
-    double var = SS / bs.count - mean * mean;                      // biased: what BN normalises with
-    var = var < 0.0 ? 0.0 : var;
-    bs.save_mean[c] = (float)mean;
-    bs.save_invstd[c] = (float)(1.0 / sqrt(var + (double)bs.eps));
-    if (bs.running_mean) {
-      const double unbiased = bs.count > 1.0 ? var * bs.count / (bs.count - 1.0) : var;
-      bs.running_mean[c] = (float)((1.0 - bs.momentum) * bs.running_mean[c] + bs.momentum * mean);
-      bs.running_var[c] = (float)((1.0 - bs.momentum) * bs.running_var[c] + bs.momentum * unbiased);
-    }
-    if (c == 0 && bs.num_batches_tracked) *bs.num_batches_tracked += 1;
-  });
+  bn_cta_sums_finish<C, NTHREADS>(st_s, st_ss, red, bs.ws, bs.counter, [&](int c, double S, double SS) { bn_stat_finalize(bs, c, S, SS); });
 }
 
 // ---- the fused bn-act BACKWARD's reduce pass from a data-gradient convolution's epilogue ---------------------------

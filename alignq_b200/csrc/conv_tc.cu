@@ -272,12 +272,14 @@ conv3x3_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, fl
   TRACE(1);
 
   // this thread's positions: per-channel (sum, sum of squares) [STATS] or (sum g_z, sum g_z xhat) [BNRED]
-  // (BNRED reduces every tile over the warp at once and keeps the warp totals in shared memory: no registers held)
-  float st_s[STATS ? C : 1], st_ss[STATS ? C : 1];
+  // Every tile is reduced over the warp at once (butterfly, bn_stat.cuh) and the warp totals are kept in shared memory:
+  // no per-thread accumulators (2 C registers: the C = 32 kernel had 170 and one CTA per SM)
+  constexpr bool RED = STATS || BNRED;
+  __shared__ float wred[RED ? NT / 32 : 1][RED ? C / 16 : 1][32];  // [warp][channel group][lane]: channel lane & 15, sum (lane >> 4)
+  if constexpr (RED) {
 #pragma unroll
-  for (int c = 0; c < (STATS ? C : 1); ++c) { st_s[c] = 0.f; st_ss[c] = 0.f; }
-  __shared__ float wred[BNRED ? NT / 32 : 1][32];                  // [warp][lane]: channel lane & 15, sum (lane >> 4)
-  if constexpr (BNRED) wred[warp][lane] = 0.f;
+    for (int gq = 0; gq < C / 16; ++gq) wred[warp][gq][lane] = 0.f;
+  }
   // BNRED staging: x, y, gy2 of this thread's output position arrive by cp.async while the MMAs run ([12][NT] float4)
   float4* stage = reinterpret_cast<float4*>(smem + stage_off);
   __shared__ float bnp[BNRED ? 4 : 1][BNRED ? C : 1];              // mean | invstd | gamma | beta of the bn-act layer
@@ -424,10 +426,12 @@ conv3x3_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, fl
           }
 #pragma unroll
           for (int e = 0; e < 16; e += 4) *reinterpret_cast<float4*>(o + c0 + e) = make_float4(r[e], r[e + 1], r[e + 2], r[e + 3]);
-          if constexpr (STATS) {
+        }
+        if constexpr (STATS) {                                     // per-channel sum and sum of squares of this tile's rows
+          float v[32];
 #pragma unroll
-            for (int e = 0; e < 16; ++e) { st_s[c0 + e] += r[e]; st_ss[c0 + e] = fmaf(r[e], r[e], st_ss[c0 + e]); }
-          }
+          for (int e = 0; e < 16; ++e) { v[e] = ok ? r[e] : 0.f; v[16 + e] = ok ? r[e] * r[e] : 0.f; }
+          wred[warp][c0 / 16][lane] += warp_reduce_transpose32(v, lane);
         }
         if constexpr (BNRED) {
           // g_z and the two BatchNorm-backward sums of this tile: v[0..15] = g_z, v[16..31] = g_z xhat per channel, summed
@@ -452,7 +456,7 @@ conv3x3_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, fl
               }
             }
           }
-          wred[warp][lane] += warp_reduce_transpose32(v, lane);
+          wred[warp][c0 / 16][lane] += warp_reduce_transpose32(v, lane);
         }
       }
     }
@@ -463,12 +467,15 @@ conv3x3_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, fl
   TRACE(13);
   if constexpr (STATS) {
     // CTA totals -> fp64 atomics -> the last CTA finishes mean / invstd / running statistics (bn_stat.cuh); the planes are idle
-    bn_stat_cta_finish<C, NT>(st_s, st_ss, reinterpret_cast<double*>(planes), bs);
+    double* red = reinterpret_cast<double*>(planes);               // [warp][2 C]
+#pragma unroll
+    for (int gq = 0; gq < C / 16; ++gq) red[warp * 2 * C + 2 * (16 * gq + (lane & 15)) + (lane >> 4)] = (double)wred[warp][gq][lane];
+    bn_cta_finish_from_red<C, NT>(red, bs.ws, bs.counter, [&](int c, double S, double SS) { bn_stat_finalize(bs, c, S, SS); });
   }
   if constexpr (BNRED) {
     // the preceding bn-act layer's backward sums; the last CTA leaves mean(g_z), mean(g_z xhat) and the affine gradients
     double* red = reinterpret_cast<double*>(planes);               // [warp][2 C] (the planes are idle)
-    red[warp * 2 * C + 2 * (lane & 15) + (lane >> 4)] = (double)wred[warp][lane];
+    red[warp * 2 * C + 2 * (lane & 15) + (lane >> 4)] = (double)wred[warp][0][lane];
     bn_cta_finish_from_red<C, NT>(red, br.ws, br.counter, [&](int c, double S, double SS) {
       if (br.gbeta) br.gbeta[c] = (float)S;
       if (br.ggamma) br.ggamma[c] = (float)SS;
@@ -564,18 +571,21 @@ __device__ __forceinline__ void deposit_bf16(const float4 (&v)[MAXI][2], const G
   }
 }
 
-template <int C, int NSB, int TAPS, bool CROSS, int MAXG, int MAXX>
+template <int C, int NSB, int TAPS, bool CROSS, int MAXG, int MAXX, int NBUF>
 __global__ void __launch_bounds__(NT)
 conv3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ partials, Geo G,
                      int ntiles, int npx, int PS, float* __restrict__ inv_scales) {
   using K = WgCfg<C>;
   constexpr int C8 = C / 8;
   extern __shared__ __align__(128) uint8_t smem[];
-  uint8_t* gplanes = smem;                                         // [NSB][C8 units][KT]
+  // NBUF operand buffers: with two, the staging of tile t + 1 runs beside the MMAs of tile t (measured per tile with one
+  // buffer: deposit 0.8 us, then MMAs 0.9 us, strictly one after the other -- tools/conv_trace.py)
   const int gtile = C8 * PS, xtile = TAPS * C8 * PS;
-  uint8_t* xplanes = smem + NSB * gtile;                           // [NSB][TAPS * C8 units][KT]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(xplanes + NSB * xtile);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int bufbytes = NSB * (gtile + xtile);
+  uint8_t* gplanes0 = smem;                                        // [NSB][C8 units][KT]
+  uint8_t* xplanes0 = smem + NSB * gtile;                          // [NSB][TAPS * C8 units][KT]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + NBUF * bufbytes);        // one barrier per buffer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int ACC = TAPS * C;                                    // columns of one accumulator set = MMA N
   // CROSS: the small products get their own accumulator (fp32-parity mode); without it everything shares one, which
@@ -592,7 +602,8 @@ conv3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ gy, 
   trace_smid();
 #endif
 
-  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  pdl_trigger();                                                   // the reduce kernel launches early and waits for us
+  if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); fence_barrier_init(); }
   if (warp == 0) tmem_alloc(tmem_slot, TCOLS);
   tc_fence_before();
   __syncthreads();
@@ -635,6 +646,13 @@ conv3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ gy, 
   }
   int it = 0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int b = NBUF == 2 ? (it & 1) : 0;
+    uint8_t* gplanes = gplanes0 + b * bufbytes;
+    uint8_t* xplanes = xplanes0 + b * bufbytes;
+    if (NBUF == 2 && it >= 2) {                                    // this buffer's previous MMAs (tile it - 2) have retired
+      mbar_wait(bar + b, (uint32_t)(((it >> 1) - 1) & 1));
+      tc_fence_after();
+    }
     deposit_bf16<C, NSB, false, 1, MAXG>(fg, G, K::KT, K::KT, 0, gplanes, PS, gtile, gscale);   // gy is zero at pad positions
     deposit_bf16<C, NSB, true, TAPS, MAXX>(fx, G, npx, K::KT, tap0, xplanes, PS, xtile);
     fence_proxy_async();
@@ -668,19 +686,25 @@ conv3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ gy, 
           umma<false>(d_cross, am, bm, IDESC, 1u);
         }
       }
-      umma_commit(bar);
+      umma_commit(bar + b);
       if (it < 2) TRACE(3 + 4 * it);
     }
     if (tile + (int)gridDim.x < ntiles) {                          // next tile -> registers while the tensor core works
       fetch_items<C, 2, true, MAXG>(gy, G, (tile + gridDim.x) * K::KT, K::KT, fg);
       fetch_items<C, 2, false, MAXX>(x, G, (tile + gridDim.x) * K::KT, npx, fx);
     }
-    mbar_wait(bar, (uint32_t)(it & 1));                            // the planes are rewritten by the next deposit
+    if (NBUF == 1) {
+      mbar_wait(bar, (uint32_t)(it & 1));                          // the planes are rewritten by the next deposit
+      tc_fence_after();
+      if (it < 2) TRACE(4 + 4 * it);
+      tc_fence_before();
+      __syncthreads();
+      if (it < 2) TRACE(5 + 4 * it);
+    }
+  }
+  if (NBUF == 2 && it > 0) {                                       // MMAs complete in order: the last commit covers them all
+    mbar_wait(bar + ((it - 1) & 1), (uint32_t)(((it - 1) >> 1) & 1));
     tc_fence_after();
-    if (it < 2) TRACE(4 + 4 * it);
-    tc_fence_before();
-    __syncthreads();
-    if (it < 2) TRACE(5 + 4 * it);
   }
   TRACE(13);
   if (threadIdx.x == 0 && inv_scales) inv_scales[blockIdx.y * gridDim.x + blockIdx.x] = ginv;
@@ -728,6 +752,7 @@ __global__ void __launch_bounds__(1024)
 conv3x3_wgrad_reduce_kernel(const float* __restrict__ partials, int nparts, int C, int taps, float* __restrict__ gw,
                             int accumulate, const float* __restrict__ inv_scales) {
   __shared__ float sm[32][33];
+  pdl_wait();                                                     // launched as a programmatic dependent of the kernel above
   const int e = blockIdx.x * 32 + threadIdx.x;                    // index into [co][9][ci]
   const int pl = threadIdx.y;
   const int total = C * 9 * C;
@@ -797,7 +822,7 @@ static int launch_fwd(const float* in, const float* w, float* out, int N, int H,
   return ALIGNQ_OK;
 }
 
-template <int C, int NSB, int TAPS, bool CROSS>
+template <int C, int NSB, int TAPS, bool CROSS, int NBUF = 1>
 static int launch_wgrad(const float* x, const float* gy, float* gw, int N, int H, int W, int accumulate, float* ws,
                         size_t ws_bytes, cudaStream_t s) {
   using K = WgCfg<C>;
@@ -805,7 +830,7 @@ static int launch_wgrad(const float* x, const float* gy, float* gw, int N, int H
   const int ntiles = (G.npos + K::KT - 1) / K::KT;
   const int npx = K::KT + 2 * G.Wp + 2;
   const int PS = plane_stride_bf16(C, K::KT);
-  size_t smem = (size_t)NSB * (C / 8) * PS * (1 + TAPS) + 64;
+  size_t smem = (size_t)NBUF * NSB * (C / 8) * PS * (1 + TAPS) + 64;
   const size_t reach = (size_t)(NSB - 1) * (C / 8) * PS + 8 * (size_t)PS + K::KT * 16;   // what the M = 64 descriptors may touch
   if (smem < reach + 64) smem = reach + 64;
   if (smem > 227 * 1024) return ALIGNQ_ERANGE;
@@ -823,12 +848,14 @@ static int launch_wgrad(const float* x, const float* gy, float* gw, int N, int H
   constexpr int STEP = NT / (C / 8);
   constexpr int MAXG = (K::KT + STEP - 1) / STEP, MAXX = (K::KT + 2 * 34 + 2 + STEP - 1) / STEP;
   if (npx > MAXX * STEP) return ALIGNQ_ERANGE;                  // wider images: the caller's library convolution
-  cudaError_t e = cudaFuncSetAttribute(conv3x3_wgrad_kernel<C, NSB, TAPS, CROSS, MAXG, MAXX>,
+  cudaError_t e = cudaFuncSetAttribute(conv3x3_wgrad_kernel<C, NSB, TAPS, CROSS, MAXG, MAXX, NBUF>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  conv3x3_wgrad_kernel<C, NSB, TAPS, CROSS, MAXG, MAXX><<<dim3(grid, groups), NT, smem, s>>>(x, gy, ws, G, ntiles, npx, PS, inv_scales);
+  conv3x3_wgrad_kernel<C, NSB, TAPS, CROSS, MAXG, MAXX, NBUF><<<dim3(grid, groups), NT, smem, s>>>(x, gy, ws, G, ntiles, npx, PS, inv_scales);
   ALIGNQ_LAUNCH_CHECK();
-  conv3x3_wgrad_reduce_kernel<<<(C * 9 * C + 31) / 32, dim3(32, 32), 0, s>>>(ws, grid, C, TAPS, gw, accumulate, inv_scales);
+  e = launch_pdl(conv3x3_wgrad_reduce_kernel, dim3((C * 9 * C + 31) / 32), dim3(32, 32), 0, s, (const float*)ws, grid, C, TAPS, gw,
+                 accumulate, (const float*)inv_scales);
+  if (e != cudaSuccess) return (int)e;
   ALIGNQ_LAUNCH_CHECK();
   return ALIGNQ_OK;
 }
@@ -934,8 +961,8 @@ extern "C" int alignq_conv3x3_bwd_weight(const float* x, const float* gy, float*
   // k-step -- a third of the tensor work and half the staging of the two-term bf16 split this mode used before
   // (ALIGNQ_WGRAD_TERMS=2 brings that back); TF32X3 mode: three bf16 terms (24 bits), six MMAs.
   if (mode == ALIGNQ_CONV_TF32 && env_int("ALIGNQ_WGRAD_TERMS", 1) == 1) {
-    if (C == 16) return launch_wgrad<16, 1, 9, false>(x, gy, gw, N, H, W, accumulate, wsf, ws_bytes, s);
-    if (C == 32) return launch_wgrad<32, 1, 9, false>(x, gy, gw, N, H, W, accumulate, wsf, ws_bytes, s);
+    if (C == 16) return launch_wgrad<16, 1, 9, false, 2>(x, gy, gw, N, H, W, accumulate, wsf, ws_bytes, s);
+    if (C == 32) return launch_wgrad<32, 1, 9, false, 2>(x, gy, gw, N, H, W, accumulate, wsf, ws_bytes, s);
     return launch_wgrad<64, 1, 3, false>(x, gy, gw, N, H, W, accumulate, wsf, ws_bytes, s);
   }
   if (mode == ALIGNQ_CONV_TF32) {

@@ -713,7 +713,7 @@ def main():
                     help="3x3 / stride-1 quantized convolutions on the hand-written tcgen05 kernels: tf32 (one pass, the numerics "
                     "of cuDNN under torch's default allow_tf32), tf32x3 (fp32 parity) or off (cuDNN everywhere)")
     ap.add_argument("--own-conv-channels", type=str, default="16", help="channel counts (Cin == Cout) routed to the own kernels")
-    ap.add_argument("--own-wgrad-channels", type=str, default="", help="further channel counts whose WEIGHT gradient alone runs on the own kernel")
+    ap.add_argument("--own-wgrad-channels", type=str, default="32", help="further channel counts whose WEIGHT gradient alone runs on the own kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-local-bn-line", action="store_true", help="N>1: skip the extra timing with per-rank BatchNorm statistics")
     ap.add_argument("--no-dp-parity", action="store_true", help="N>1: skip the N-rank vs single-device parity block")

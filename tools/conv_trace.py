@@ -70,6 +70,6 @@ def run(fn, shape, flush):
 if __name__ == "__main__":
     shapes = [(128, 16, 32, 32), (128, 32, 16, 16), (128, 64, 8, 8)]
     for shape in shapes:
-        for fn in ("alignq_conv3x3_fwd", "alignq_conv3x3_bwd_data"):
+        for fn in ("alignq_conv3x3_bwd_weight",):
             run(fn, shape, True)
     run("alignq_conv3x3_fwd", shapes[0], False)

@@ -113,6 +113,7 @@ class WgradStream:
         self.side = self.sides[0]                     # the stream data-parallel bucket reductions are issued on
         self.next = 0
         self.keep = []                                # tensors the side streams still read
+        self.used = set()                             # indices of the side streams forked since the last join
         self.dirty = False
 
     @classmethod
@@ -126,7 +127,9 @@ class WgradStream:
         main = torch.cuda.current_stream()
         ev = torch.cuda.Event()
         ev.record(main)
-        side = self.sides[0] if single else self.sides[self.next % self.NSTREAMS]
+        k = 0 if single else self.next % self.NSTREAMS
+        side = self.sides[k]
+        self.used.add(k)
         self.next += 1
         side.wait_event(ev)
         self.keep.extend(tensors)
@@ -137,8 +140,11 @@ class WgradStream:
         """Make the current stream wait for every weight gradient issued so far (call before they are consumed)."""
         if self.dirty:
             main = torch.cuda.current_stream()
-            for sd in self.sides:
-                main.wait_stream(sd)
+            # only the streams that were forked: inside a CUDA-graph capture, waiting for a stream that never joined the
+            # capture (data-parallel overlap mode uses side stream 0 alone) is cudaErrorStreamCaptureIsolation
+            for k in sorted(self.used):
+                main.wait_stream(self.sides[k])
+            self.used.clear()
             self.keep.clear()
             self.dirty = False
             self.next = 0

@@ -180,7 +180,10 @@ template <int C, int NS, bool FLIP, int MAXI, bool STATS, bool BNRED>
 __global__ void __launch_bounds__(NT)
 conv3x3_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, float* __restrict__ out, Geo G, int ntiles,
                    int npt, int PS, BnStat bs, BnRed br) {
-  static_assert(!(STATS && BNRED) && (!BNRED || (FLIP && C == 16)), "epilogue reductions");
+  static_assert(!(STATS && BNRED) && (!BNRED || (FLIP && (C == 16 || C == 32))), "epilogue reductions");
+  // BNRED staging by cp.async: x, y and gy2 at C = 16 (48 KB); x alone at C = 32 (32 KB: two CTAs still share an SM), y and
+  // gy2 -- just written / just read by the weight gradient, i.e. L2 hits -- are loaded in the epilogue itself
+  constexpr bool STAGE_ALL = C == 16;
   using F = FwdCfg<C>;
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int W_BYTES = 9 * F::W_TAP;
@@ -345,9 +348,9 @@ conv3x3_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, fl
 #pragma unroll
         for (int k = 0; k < C / 4; ++k) {
           tcsmall::cp_async16(smem_u32(stage + (0 * (C / 4) + k) * NT + threadIdx.x), reinterpret_cast<const float4*>(br.x + ooff) + k);
-          if (br.relu)
+          if (STAGE_ALL && br.relu)
             tcsmall::cp_async16(smem_u32(stage + (1 * (C / 4) + k) * NT + threadIdx.x), reinterpret_cast<const float4*>(br.y + ooff) + k);
-          if (br.gy2)
+          if (STAGE_ALL && br.gy2)
             tcsmall::cp_async16(smem_u32(stage + (2 * (C / 4) + k) * NT + threadIdx.x), reinterpret_cast<const float4*>(br.gy2 + ooff) + k);
         }
       }
@@ -419,7 +422,8 @@ conv3x3_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, fl
             if (br.gy2) {                          // r becomes the bn-act output's total upstream gradient
 #pragma unroll
               for (int e = 0; e < 16; e += 4) {
-                const float4 g4 = stage[(2 * (C / 4) + (c0 + e) / 4) * NT + threadIdx.x];
+                const float4 g4 = STAGE_ALL ? stage[(2 * (C / 4) + (c0 + e) / 4) * NT + threadIdx.x]
+                                            : __ldg(reinterpret_cast<const float4*>(br.gy2 + ooff + c0 + e));
                 r[e] += g4.x; r[e + 1] += g4.y; r[e + 2] += g4.z; r[e + 3] += g4.w;
               }
             }
@@ -444,7 +448,8 @@ conv3x3_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, fl
             for (int e = 0; e < 16; e += 4) {
               const float4 x4 = stage[(0 * (C / 4) + (c0 + e) / 4) * NT + threadIdx.x];
               float4 y4 = make_float4(1.f, 1.f, 1.f, 1.f);
-              if (br.relu) y4 = stage[(1 * (C / 4) + (c0 + e) / 4) * NT + threadIdx.x];
+              if (br.relu) y4 = STAGE_ALL ? stage[(1 * (C / 4) + (c0 + e) / 4) * NT + threadIdx.x]
+                                          : __ldg(reinterpret_cast<const float4*>(br.y + ooff + c0 + e));
               const float xx4[4] = {x4.x, x4.y, x4.z, x4.w}, yy4[4] = {y4.x, y4.y, y4.z, y4.w};
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
@@ -475,7 +480,8 @@ conv3x3_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, fl
   if constexpr (BNRED) {
     // the preceding bn-act layer's backward sums; the last CTA leaves mean(g_z), mean(g_z xhat) and the affine gradients
     double* red = reinterpret_cast<double*>(planes);               // [warp][2 C] (the planes are idle)
-    red[warp * 2 * C + 2 * (lane & 15) + (lane >> 4)] = (double)wred[warp][0][lane];
+#pragma unroll
+    for (int gq = 0; gq < C / 16; ++gq) red[warp * 2 * C + 2 * (16 * gq + (lane & 15)) + (lane >> 4)] = (double)wred[warp][gq][lane];
     bn_cta_finish_from_red<C, NT>(red, br.ws, br.counter, [&](int c, double S, double SS) {
       if (br.gbeta) br.gbeta[c] = (float)S;
       if (br.ggamma) br.ggamma[c] = (float)SS;
@@ -800,7 +806,7 @@ static int launch_fwd(const float* in, const float* w, float* out, int N, int H,
   const int ntiles = (G.npos + F::MO - 1) / F::MO;
   const int npt = F::MT + 2 * G.Wp + 2;
   const int PS = plane_stride(C, npt);
-  const size_t smem = (size_t)NS * 9 * F::W_TAP + (size_t)NS * (C / 4) * PS + 64 + (BNRED ? (size_t)3 * (C / 4) * NT * 16 : 0);
+  const size_t smem = (size_t)NS * 9 * F::W_TAP + (size_t)NS * (C / 4) * PS + 64 + (BNRED ? (size_t)(C == 16 ? 3 : 1) * (C / 4) * NT * 16 : 0);
   if (smem > 227 * 1024) return ALIGNQ_ERANGE;
   // staging registers: items per thread = ceil(npt / (NT / (C/4))); the instantiation covers rows up to W = 32 + 2
   constexpr int STEP = NT / (C / 4);
@@ -932,7 +938,9 @@ extern "C" int alignq_conv3x3_bwd_data_bnreduce(const float* gy, const float* w,
                                                 double* bn_ws, uint32_t* bn_counter, alignq_stream_t stream) {
   int rc = conv_args_ok(gy, w, gx, N, H, W, C, mode);
   if (rc) return rc;
-  if (C != 16) return ALIGNQ_ERANGE;                         // per-thread channel accumulators + prefetch registers
+  // C = 16 only.  (The kernel template also covers C = 32 -- x staged by cp.async, y / gy2 loaded in the epilogue -- but
+  // the two-channel-group epilogue made the ResNet-20 step slower, 1.10-1.13 ms against 1.08, so it is not instantiated.)
+  if (C != 16) return ALIGNQ_ERANGE;
   if (!bn_x || !save_mean || !save_invstd || !bn_ws || !bn_counter || (relu && !bn_y)) return ALIGNQ_EINVAL;
   if (!aligned16(bn_x) || (relu && !aligned16(bn_y)) || (gy2 && !aligned16(gy2))) return ALIGNQ_EALIGN;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);

@@ -47,6 +47,13 @@ def applies(x, weight, stride, padding, dilation, groups, bias) -> bool:
     return _covered(x, weight, stride, padding, dilation, groups, bias, args.own_conv_channels)
 
 
+def applies_dgrad(x, weight, stride, padding, dilation, groups, bias) -> bool:
+    """The DATA gradient alone on the own kernel (``own_dgrad_channels``): the library's data-gradient kernels for these
+    shapes are cluster launches that come with a parameter-copy node in front (2.5 us on the main chain, each)."""
+    return (_covered(x, weight, stride, padding, dilation, groups, bias, tuple(args.own_conv_channels) + tuple(args.own_dgrad_channels))
+            and weight.is_contiguous(memory_format=torch.channels_last))
+
+
 def applies_wgrad(x, weight, stride, padding, dilation, groups, bias) -> bool:
     """The WEIGHT gradient alone on the own kernel (``own_wgrad_channels``): at C = 32 / 64 the library's forward and data
     gradient are still the faster ones, its split-K weight gradient (14-21 us per layer, a memset in front) is not."""
@@ -161,10 +168,12 @@ class _ConvQFn(torch.autograd.Function):
     """Any bias-free Conv2d_Q convolution with the weight gradient on the side stream."""
 
     @staticmethod
-    def forward(ctx, x, w, stride, padding, dilation, groups, own, mode, bn=None, bn_ws=None, sync=True, up=None, own_w=None):
+    def forward(ctx, x, w, stride, padding, dilation, groups, own, mode, bn=None, bn_ws=None, sync=True, up=None, own_w=None,
+                own_d=None):
         mean = invstd = None
-        own_w = own if own_w is None else bool(own_w)      # the weight gradient may take the own kernel on its own
-        ctx.up = up if own else None                  # link of the fused bn-act layer that produced x (fused.py), or None
+        own_w = own if own_w is None else bool(own_w)      # the weight / data gradient may take the own kernels on their own
+        own_d = own if own_d is None else bool(own_d)
+        ctx.up = up                                   # link of the fused bn-act layer that produced x (fused.py), or None
         if own:
             N, C, H, W = x.shape
             wc = w if w.is_contiguous(memory_format=torch.channels_last) else w.contiguous(memory_format=torch.channels_last)
@@ -186,7 +195,7 @@ class _ConvQFn(torch.autograd.Function):
             wc = w
             y = torch.ops.aten.convolution(x, w, None, stride, padding, dilation, False, (0, 0), groups)
         ctx.save_for_backward(x, wc)
-        ctx.cfg = (tuple(stride), tuple(padding), tuple(dilation), groups, own, mode, bool(sync), own_w)
+        ctx.cfg = (tuple(stride), tuple(padding), tuple(dilation), groups, own, mode, bool(sync), own_w, own_d)
         ctx.w_like = w
         ctx.gup = getattr(w, "_alignq_gup", None) if sync else None    # (WeightBank, layer index) or None
         ctx.set_materialize_grads(False)              # no zero-fill launches for the (non-differentiable) statistics outputs
@@ -198,12 +207,12 @@ class _ConvQFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy, *_unused):
         if gy is None:
-            return (None,) * 13
+            return (None,) * 14
         x, wc = ctx.saved_tensors
-        stride, padding, dilation, groups, own, mode, on_side, own_w = ctx.cfg
+        stride, padding, dilation, groups, own, mode, on_side, own_w, own_d = ctx.cfg
         lib = L.load()
         gx = gw = None
-        if own or own_w:
+        if own_d or own_w:
             gy = L.like_layout(gy, x, "grad of conv output")
         else:
             gy = gy if gy.is_contiguous(memory_format=torch.channels_last) or gy.is_contiguous() else gy.contiguous()
@@ -248,7 +257,7 @@ class _ConvQFn(torch.autograd.Function):
         def data_gradient():
             nonlocal gx
             if ctx.needs_input_grad[0]:
-                if own:
+                if own_d:
                     N, C, H, W = x.shape
                     gx = torch.empty_like(x)
                     fwd = ctx.up.get("fwd") if ctx.up is not None else None
@@ -279,7 +288,7 @@ class _ConvQFn(torch.autograd.Function):
 
         for step in ((weight_gradient, data_gradient) if wgrad_first else (data_gradient, weight_gradient)):
             step()
-        return gx, gw, None, None, None, None, None, None, None, None, None, None, None
+        return gx, gw, None, None, None, None, None, None, None, None, None, None, None, None
 
 
 _stem_ws = {}
@@ -387,8 +396,9 @@ def conv_async_wgrad(x, weight, stride, padding, dilation, groups):
         return stem_conv(x, weight)
     own = applies(x, weight, stride, padding, dilation, groups, None)
     own_w = own or applies_wgrad(x, weight, stride, padding, dilation, groups, None)
+    own_d = own or applies_dgrad(x, weight, stride, padding, dilation, groups, None)
     return _ConvQFn.apply(x, weight, tuple(stride), tuple(padding), tuple(dilation), groups, own,
-                          L.CONV_MODE_ID[args.own_conv] if own_w else 0, None, None, True, _up_link(x), own_w)
+                          L.CONV_MODE_ID[args.own_conv] if (own_w or own_d) else 0, None, None, True, _up_link(x), own_w, own_d)
 
 
 def conv_with_bn_stats(x, weight, bn, bn_ws):

@@ -24,8 +24,8 @@ hand-written tcgen05 kernels (model/conv_tc.py) instead of the library convoluti
 kernels are correct but cuDNN's tiles are still faster -- profiles/r02_conv_bench.json); ``own_conv_stem`` (default
 True, effective unless ``own_conv`` is "off") runs the first-layer convolution (3 -> 16 / 32 channels, 3x3, stride 1) on the
 direct fp32 kernels of csrc/conv_stem.cu.
-``own_wgrad_channels`` adds channel counts whose WEIGHT gradient alone runs on the own kernel (forward / data gradient stay
-with the library).
+``own_wgrad_channels`` / ``own_dgrad_channels`` add channel counts whose WEIGHT / DATA gradient alone runs on the own kernel
+(the rest stays with the library).
 ``fuse_dgrad_bn`` (default True; effective where an own C = 16 convolution follows a fused bn-act layer) moves the reduce
 pass of that bn-act layer's backward into the epilogue of the convolution's data-gradient kernel (model/conv_tc.py).
 ``fused_head`` lets ``QATStep`` run the average pool -> classifier -> cross-entropy tail of models that offer ``forward_ce``
@@ -40,7 +40,7 @@ _DEFAULTS = dict(
     gpus=[0], bitW=2, abitW=2, act_range=2, lam=1.0, lam2=4.0, method="ours", stage="second",
     train_batch_size=128, eval_batch_size=100, lr=0.04, momentum=0.9, weight_decay=1e-4,
     variant="A", gram_mode="fp32", store_weight_attrs=True, fuse_bn_act=False, admm_param_grads=True,
-    dp_gram="replica", sync_bn=False, own_conv="off", own_conv_channels=(16,), own_wgrad_channels=(), own_conv_stem=True, fused_head=False, async_wgrad=False, fuse_dgrad_bn=True,
+    dp_gram="replica", sync_bn=False, own_conv="off", own_conv_channels=(16,), own_wgrad_channels=(), own_dgrad_channels=(), own_conv_stem=True, fused_head=False, async_wgrad=False, fuse_dgrad_bn=True,
 )
 
 args = SimpleNamespace(**_DEFAULTS)

@@ -333,7 +333,8 @@ def run_product(args):
     aq.set_args(variant="A", bitW=8, abitW=8, act_range=2, lam=1.0, lam2=4.0, method="ours", train_batch_size=BATCH,
                 fuse_bn_act=fuse, own_conv=("off" if args.nchw else args.own_conv), fused_head=not (args.no_fused_head or args.nchw),
                 own_conv_channels=tuple(int(c) for c in args.own_conv_channels.split(",") if c),
-                own_wgrad_channels=tuple(int(c) for c in args.own_wgrad_channels.split(",") if c))
+                own_wgrad_channels=tuple(int(c) for c in args.own_wgrad_channels.split(",") if c),
+                own_dgrad_channels=tuple(int(c) for c in args.own_dgrad_channels.split(",") if c))
     torch.manual_seed(0)                                   # identical replicas on every rank
     batch, img_hw, ncls, forward_loss = BATCH, 32, 10, None
     # ADMM(dim): the GLOBAL batch in dp_gram='feature' mode (weak scaling: per-GPU batch x ranks), else the per-GPU batch
@@ -660,7 +661,8 @@ def run_product(args):
                 "config": dict(CONFIG, global_batch=batch * world, parallelism=f"dp{world}", cuda_graph=graphed,
                                activation_layout="nchw" if args.nchw else "channels_last", fused_bn_act=fuse,
                                conv3x3=("cuDNN" if (args.nchw or args.own_conv == "off") else
-                                        f"own tcgen05 kernels ({args.own_conv}) for 3x3/s1/Cin==Cout in ({args.own_conv_channels}) and own fp32 first-layer kernels; cuDNN (tf32) for the rest"),
+                                        f"own tcgen05 kernels ({args.own_conv}) for 3x3/s1/Cin==Cout in ({args.own_conv_channels}) [+ data gradient in ({args.own_dgrad_channels}), "
+                                        f"weight gradient in ({args.own_wgrad_channels})] and own fp32 first-layer kernels; cuDNN (tf32) for the rest"),
                                fused_head=not (args.no_fused_head or args.nchw),
                                sync_bn=bool(sync_bn),
                                sync_bn_impl=(None if not sync_bn else (
@@ -713,6 +715,7 @@ def main():
                     help="3x3 / stride-1 quantized convolutions on the hand-written tcgen05 kernels: tf32 (one pass, the numerics "
                     "of cuDNN under torch's default allow_tf32), tf32x3 (fp32 parity) or off (cuDNN everywhere)")
     ap.add_argument("--own-conv-channels", type=str, default="16", help="channel counts (Cin == Cout) routed to the own kernels")
+    ap.add_argument("--own-dgrad-channels", type=str, default="32", help="further channel counts whose DATA gradient alone runs on the own kernel")
     ap.add_argument("--own-wgrad-channels", type=str, default="32", help="further channel counts whose WEIGHT gradient alone runs on the own kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-local-bn-line", action="store_true", help="N>1: skip the extra timing with per-rank BatchNorm statistics")

@@ -197,8 +197,9 @@ def test_stem_conv_epilogue_bn_statistics(Cout, H):
     assert relmax(bn.weight.grad, bn2.weight.grad) <= 1e-3
 
 
+@pytest.mark.parametrize("C,H", [(16, 32)])
 @pytest.mark.parametrize("mode", ["tf32x3", "tf32"])
-def test_bn_act_backward_reduce_in_the_data_gradient_epilogue(mode):
+def test_bn_act_backward_reduce_in_the_data_gradient_epilogue(mode, C, H):
     """Two residual blocks of the C = 16 stage (resnet.py:51-55): with ``fuse_dgrad_bn`` the data-gradient kernel of each
     own convolution also runs the reduce pass of the preceding bn-act layer's backward (sum g_z, sum g_z xhat, the
     affine gradients) and adds the parked shortcut gradient, so that layer's backward is its apply pass alone
@@ -208,9 +209,9 @@ def test_bn_act_backward_reduce_in_the_data_gradient_epilogue(mode):
     from alignq_b200.model.fused import bn_act
     from alignq_b200.model.resnet import PreActBlock_conv_Q
     torch.manual_seed(70)
-    base = dict(variant="A", bitW=8, abitW=8, act_range=2, fuse_bn_act=True, own_conv=mode, own_conv_channels=(16,), method="none")
+    base = dict(variant="A", bitW=8, abitW=8, act_range=2, fuse_bn_act=True, own_conv=mode, own_conv_channels=(16, 32), method="none")
     aq.set_args(**base)
-    C, N, H = 16, 32, 32
+    N = 32
     blocks = torch.nn.ModuleList([PreActBlock_conv_Q("second", 8, 8, C, C, 1, variant="A") for _ in range(2)]).to(DEV).train()
     bn0 = torch.nn.BatchNorm2d(C).to(DEV).train()
     q0 = aq.activation_quantize_fn(8, "second")

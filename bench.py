@@ -543,7 +543,7 @@ def run_product(args):
     e2e = world * batch * args.steps / (ms_e2e * 1e-3)
 
     roofline = cpu = gram = None
-    if rank == 0:
+    if rank == 0 and not args.lean:
         # ---- roofline leg: the CDF-quantizer kernel pair on a stream far larger than L2 -----------
         n = 256 * (1 << 20)
         x = torch.randn(n, device=dev)
@@ -638,7 +638,7 @@ def run_product(args):
         aq.set_args(sync_bn=args.sync_bn_impl)
 
     fused_parity = no_fuse = None
-    if rank == 0 and world == 1 and fuse and args.workload == "resnet20":
+    if rank == 0 and world == 1 and fuse and args.workload == "resnet20" and not args.lean:
         fused_parity = fused_code_mismatch(dev)
         # the same step with BatchNorm / quantizer / ReLU as separate kernels, beside the fused number
         aq.set_args(fuse_bn_act=False)
@@ -718,6 +718,7 @@ def main():
     ap.add_argument("--own-dgrad-channels", type=str, default="32", help="further channel counts whose DATA gradient alone runs on the own kernel")
     ap.add_argument("--own-wgrad-channels", type=str, default="32", help="further channel counts whose WEIGHT gradient alone runs on the own kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lean", action="store_true", help="profiler runs: the timed step only (no roofline / Gram / no-fuse / parity legs)")
     ap.add_argument("--no-local-bn-line", action="store_true", help="N>1: skip the extra timing with per-rank BatchNorm statistics")
     ap.add_argument("--no-dp-parity", action="store_true", help="N>1: skip the N-rank vs single-device parity block")
     ap.add_argument("--no-fuse", action="store_true", help="run BatchNorm / quantizer / ReLU as separate kernels "

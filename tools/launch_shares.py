@@ -13,8 +13,27 @@ import sys
 
 src, one_step, out = sys.argv[1], sys.argv[2], sys.argv[3]
 rows = []
+OWN = ("alignq", "ctc::", "head::", "stem::", "lmmd::", "tcsmall::")      # ncu prints the innermost namespaces only
+
+
+def is_own(k):
+    return any(t in k for t in OWN)
+
+
 with open(src, newline="") as f:
-    lines = [l for l in f if l.startswith('"')]
+    first = f.readline()
+    f.seek(0)
+    if first.startswith("#"):                 # already a one-step list written by this tool: recompute the summary
+        rd0 = csv.reader(f)
+        next(rd0)
+        pre = [(r[1], float(r[2])) for r in rd0]
+        lines = None
+    else:
+        lines = [l for l in f if l.startswith('"')]
+if lines is None:
+    rows = [("alignq::wq_stats_kernel", 0.0)] if not pre or "wq_stats" not in pre[0][0] else []
+    rows = pre + [("alignq::wq_stats_kernel(end)", 0.0)]
+    lines = ['"Kernel Name","Metric Name","Metric Value","Metric Unit"']
 rd = csv.reader(lines)
 hdr = next(rd)
 ki, mi, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
@@ -42,8 +61,8 @@ for k, us in step:
     t = agg.setdefault(k, [0.0, 0])
     t[0] += us
     t[1] += 1
-own = sum(t[0] for k, t in agg.items() if "alignq" in k)
-nown = sum(t[1] for k, t in agg.items() if "alignq" in k)
+own = sum(t[0] for k, t in agg.items() if is_own(k))
+nown = sum(t[1] for k, t in agg.items() if is_own(k))
 with open(out, "w") as f:
     f.write(f"# kernels in the step: {len(step)}; serialised sum {tot:.1f} us\n")
     f.write(f"# alignq_b200 kernels: {nown} launches, {own:.1f} us = {100 * own / tot:.1f}% of the serialised sum\n")

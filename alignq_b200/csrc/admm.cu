@@ -89,6 +89,7 @@ gram_sums_to_d_kernel(const float* __restrict__ sums, const float* __restrict__ 
 
 __global__ void __launch_bounds__(256)
 wsym_kernel(const float* __restrict__ dLdD, int B, int Bp, float* __restrict__ W) {
+  pdl_trigger();                      // the Gram backward launches early and waits for this grid (common.cuh)
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= Bp * Bp) return;
   const int i = e / Bp, j = e - i * Bp;

@@ -99,6 +99,7 @@ template <int MODE, bool FUSED, bool STAGED>
 __global__ void __launch_bounds__(NT, 1)
 gram_tc_kernel(const float* __restrict__ x, int B, int64_t F, float eps, ActQ q, float* __restrict__ y,
                float* __restrict__ partials, int64_t ntiles, double* __restrict__ zero_acc, int ncl) {
+  pdl_trigger();                      // the finish kernel launches early and waits for this grid (common.cuh)
   using C = Cfg<MODE, FUSED, STAGED>;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* stage_base = smem;
@@ -424,6 +425,8 @@ static void launch_reduce_tc(const float* partials, int nparts, int B, int64_t F
 __global__ void __launch_bounds__(1024)
 gram_finish_tc_kernel(const float* __restrict__ partials, int nparts, int B, float invF, AdmmFinish f,
                       float* __restrict__ D, double* __restrict__ acc) {
+  pdl_wait();                         // programmatic dependent of the Gram kernel: nothing is touched before this
+
   // Round 2: ONE element per thread (1024 elements per block, 16 blocks at B = 128), every thread walks the (few, after the
   // in-cluster reduction) partial sets of its element with coalesced loads in a fixed order, then a block reduction and
   // three fp64 atomics per BLOCK.  The first version used 32 elements x 32 part lanes per block: 512 blocks, 1536 same-
@@ -503,6 +506,8 @@ gram_finish_tc_kernel(const float* __restrict__ partials, int nparts, int B, flo
 __global__ void __launch_bounds__(1024)
 gram_finish_tc_wide_kernel(const float* __restrict__ partials, int nparts, int B, float invF, AdmmFinish f,
                       float* __restrict__ D, double* __restrict__ acc) {
+  pdl_wait();                         // programmatic dependent of the Gram kernel: nothing is touched before this
+
   __shared__ float sm[2][32][33];
   __shared__ unsigned last_flag;
   const int bb = B * B;
@@ -580,11 +585,11 @@ static void launch_finish_tc(const float* partials, int nparts, int B, int64_t F
   if (fin && fused) {
     const int bb = B * B;
     if (nparts <= 64)
-      gram_finish_tc_kernel<<<(bb + 1023) / 1024, 1024, 0, s>>>(partials, nparts, B, 1.0f / (float)F, *fin, D,
-                                                                 reinterpret_cast<double*>(ws));
+      (void)launch_pdl(gram_finish_tc_kernel, dim3((bb + 1023) / 1024), dim3(1024), 0, s, partials, nparts, B, 1.0f / (float)F, *fin,
+                       D, reinterpret_cast<double*>(ws));
     else
-      gram_finish_tc_wide_kernel<<<(bb + 31) / 32, dim3(32, 32), 0, s>>>(partials, nparts, B, 1.0f / (float)F, *fin, D,
-                                                                          reinterpret_cast<double*>(ws));
+      (void)launch_pdl(gram_finish_tc_wide_kernel, dim3((bb + 31) / 32), dim3(32, 32), 0, s, partials, nparts, B, 1.0f / (float)F,
+                       *fin, D, reinterpret_cast<double*>(ws));
   } else {
     launch_reduce_tc(partials, nparts, B, F, nacc, fused, G, D, s);
   }

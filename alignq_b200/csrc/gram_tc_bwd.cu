@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(NT, 1)
 gram_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gy, const float* __restrict__ Wsym, int Bp,
                    const float* __restrict__ gloss, int B, int64_t F, float ar, float eps, int64_t ntiles,
                    float* __restrict__ gx) {
+  pdl_wait();                         // programmatic dependent of wsym_kernel: nothing is touched before this
   using LY = Lay<NS>;
   constexpr int OFF_A = LY::OFF_A, OFF_B = LY::OFF_B, OFF_RAW = LY::OFF_RAW;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -300,11 +301,13 @@ int gram_tc_backward(const float* x, const float* gy, const float* Wsym, int Bp,
   if (split) {
     e = cudaFuncSetAttribute(gram_tc_bwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<3>::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
-    gram_tc_bwd_kernel<3><<<(unsigned)grid, NT, Lay<3>::SMEM_BYTES, s>>>(x, gy, Wsym, Bp, gloss, B, F, ar, eps, ntiles, gx);
+    e = launch_pdl(gram_tc_bwd_kernel<3>, dim3((unsigned)grid), dim3(NT), Lay<3>::SMEM_BYTES, s, x, gy, Wsym, Bp, gloss, B, F, ar, eps, ntiles, gx);
+    if (e != cudaSuccess) return (int)e;
   } else {
     e = cudaFuncSetAttribute(gram_tc_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<1>::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
-    gram_tc_bwd_kernel<1><<<(unsigned)grid, NT, Lay<1>::SMEM_BYTES, s>>>(x, gy, Wsym, Bp, gloss, B, F, ar, eps, ntiles, gx);
+    e = launch_pdl(gram_tc_bwd_kernel<1>, dim3((unsigned)grid), dim3(NT), Lay<1>::SMEM_BYTES, s, x, gy, Wsym, Bp, gloss, B, F, ar, eps, ntiles, gx);
+    if (e != cudaSuccess) return (int)e;
   }
   ALIGNQ_LAUNCH_CHECK();
   return ALIGNQ_OK;

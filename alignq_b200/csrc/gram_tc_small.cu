@@ -47,6 +47,7 @@ template <bool SPLIT, bool FUSED, int RBT>
 __global__ void __launch_bounds__(NT, CTAS_PER_SM)
 gram_tc_small_kernel(const float* __restrict__ x, int B, int64_t F, float eps, ActQ q, float* __restrict__ y,
                      float* __restrict__ partials, int64_t ntiles, double* __restrict__ zero_acc) {
+  pdl_trigger();                      // the finish kernel launches early and waits for this grid (common.cuh)
   constexpr int NCOLS = FUSED ? 64 : 32;                          // accumulator columns per set = MMA N
   // both operands MN-major (bits 15, 16)
   constexpr uint32_t IDESC = make_idesc(1u /*bf16*/, 64u, (uint32_t)NCOLS) | (1u << 15) | (1u << 16);

@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(NT, Lay<NS>::CTAS_PER_SM)
 gram_tc_bwd_small_kernel(const float* __restrict__ x, const float* __restrict__ gy, const float* __restrict__ Wsym, int Bp,
                          const float* __restrict__ gloss, int B, int64_t F, float ar, float eps, int64_t ntiles,
                          float* __restrict__ gx) {
+  pdl_wait();                         // programmatic dependent of wsym_kernel: nothing is touched before this
   using LY = Lay<NS>;
   constexpr int OFF_W = LY::OFF_W, OFF_A = LY::OFF_A, OFF_XS = LY::OFF_XS, OFF_GY = LY::OFF_GY, OFF_BAR = LY::OFF_BAR;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -251,7 +252,9 @@ static int launch_bwd_small(const float* x, const float* gy, const float* Wsym, 
   using namespace tcsb;
   cudaError_t e = cudaFuncSetAttribute(gram_tc_bwd_small_kernel<NS, RBT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<NS>::SMEM_BYTES);
   if (e != cudaSuccess) return (int)e;
-  gram_tc_bwd_small_kernel<NS, RBT><<<(unsigned)grid, NT, Lay<NS>::SMEM_BYTES, s>>>(x, gy, Wsym, Bp, gloss, B, F, ar, eps, ntiles, gx);
+  e = launch_pdl(gram_tc_bwd_small_kernel<NS, RBT>, dim3((unsigned)grid), dim3(NT), Lay<NS>::SMEM_BYTES, s, x, gy, Wsym, Bp, gloss, B, F, ar, eps,
+                 ntiles, gx);
+  if (e != cudaSuccess) return (int)e;
   ALIGNQ_LAUNCH_CHECK();
   return ALIGNQ_OK;
 }

@@ -37,6 +37,7 @@ __device__ __forceinline__ void sgd_one(float& p, float& g, float& buf, const al
 __global__ void __launch_bounds__(kSgdThreads)
 sgd_kernel(const alignq_sgd_tensor_t* __restrict__ tensors, const int32_t* __restrict__ chunk_tensor,
            const int32_t* __restrict__ tensor_chunk0, SgdScalars k) {
+  pdl_wait();                         // programmatic dependent of whatever produced the gradients: nothing is touched before this
   const int ti = chunk_tensor[blockIdx.x];
   const alignq_sgd_tensor_t t = tensors[ti];
   const int64_t begin = (int64_t)(blockIdx.x - tensor_chunk0[ti]) * ALIGNQ_CHUNK;
@@ -91,8 +92,8 @@ extern "C" int alignq_sgd_step(const alignq_sgd_tensor_t* tensors, const int32_t
   k.two_lam2 = lam2 * 2.0f;
   k.levels = (float)((1ull << bitW) - 1);
   k.grad_scale = grad_scale;
-  sgd_kernel<<<(unsigned)nchunks, kSgdThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(tensors, chunk_tensor,
-                                                                                            tensor_chunk0, k);
+  (void)launch_pdl(sgd_kernel, dim3((unsigned)nchunks), dim3(kSgdThreads), 0, reinterpret_cast<cudaStream_t>(stream), tensors,
+                   chunk_tensor, tensor_chunk0, k);
   ALIGNQ_LAUNCH_CHECK();
   return ALIGNQ_OK;
 }

@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(kThreads)
 wq_stats_kernel(const float* __restrict__ flat, const int64_t* __restrict__ seg_off,
                 const int32_t* __restrict__ chunk_seg, const int32_t* __restrict__ seg_chunk0,
                 double* __restrict__ partials) {
+  pdl_trigger();                      // the apply pass launches early and waits for this grid (common.cuh)
   __shared__ double scratch[64];
   const ChunkRange r = chunk_range(seg_off, chunk_seg, seg_chunk0);
   double s = 0.0, ss = 0.0;
@@ -124,6 +125,7 @@ wq_fwd_kernel(const float* __restrict__ flat, const int64_t* __restrict__ seg_of
               const double* __restrict__ partials, float n, float inv_n,
               float* __restrict__ wq, float* __restrict__ w_cdf, float* __restrict__ w_pdf,
               int16_t* __restrict__ codes, float* __restrict__ stats) {
+  pdl_wait();                         // programmatic dependent of wq_stats_kernel: nothing is touched before this
   __shared__ double scratch[64];
   const ChunkRange r = chunk_range(seg_off, chunk_seg, seg_chunk0);
   double s, ss;
@@ -165,6 +167,7 @@ wq_bwd_partial_kernel(const float* __restrict__ flat, const float* g_wq,
                       const int64_t* __restrict__ seg_off, const int32_t* __restrict__ chunk_seg,
                       const int32_t* __restrict__ seg_chunk0, const float* __restrict__ stats,
                       double* __restrict__ partials, const __grid_constant__ GPtrTable gt, int use_gt, int seg_base) {
+  pdl_trigger();
   __shared__ double scratch[64];
   const ChunkRange r = chunk_range(seg_off, chunk_seg, seg_chunk0);
   const float mean = stats[4 * r.seg], rstd = stats[4 * r.seg + 2];
@@ -191,6 +194,8 @@ wq_bwd_apply_kernel(const float* __restrict__ flat, const float* g_wq,
                     const int32_t* __restrict__ seg_chunk0, const float* __restrict__ stats,
                     const double* __restrict__ partials, float* __restrict__ g_w,
                     const __grid_constant__ GPtrTable gt, int use_gt, int seg_base, int accumulate) {
+  pdl_trigger();                      // (the optimizer kernel may follow)
+  pdl_wait();                         // programmatic dependent of wq_bwd_partial_kernel
   __shared__ double scratch[64];
   const ChunkRange r = chunk_range(seg_off, chunk_seg, seg_chunk0);
   const float mean = stats[4 * r.seg], rstd = stats[4 * r.seg + 2];
@@ -245,8 +250,8 @@ extern "C" int alignq_wq_forward(const float* flat, const int64_t* seg_off, cons
   const float inv_n = 1.0f / n;
   wq_stats_kernel<<<(unsigned)nchunks, kThreads, 0, s>>>(flat, seg_off, chunk_seg, seg_chunk0, ws);
   ALIGNQ_LAUNCH_CHECK();
-#define WQ_FWD(V, S) wq_fwd_kernel<V, S><<<(unsigned)nchunks, kThreads, 0, s>>>( \
-      flat, seg_off, chunk_seg, seg_chunk0, ws, n, inv_n, wq, w_cdf, w_pdf, codes, stats)
+#define WQ_FWD(V, S) (void)launch_pdl(wq_fwd_kernel<V, S>, dim3((unsigned)nchunks), dim3(kThreads), 0, s, \
+      flat, seg_off, chunk_seg, seg_chunk0, (const double*)ws, n, inv_n, wq, w_cdf, w_pdf, codes, stats)
   if (variant == 0) { if (w_bit == 1) WQ_FWD(0, true); else WQ_FWD(0, false); }
   else              { if (w_bit == 1) WQ_FWD(1, true); else WQ_FWD(1, false); }
 #undef WQ_FWD
@@ -268,8 +273,8 @@ extern "C" int alignq_wq_backward(const float* flat, const float* g_wq, const fl
     wq_bwd_partial_kernel<<<(unsigned)nchunks, kThreads, 0, s>>>(flat, g_wq, seg_off, chunk_seg, seg_chunk0, stats, ws, gt,
                                                                  g_ptrs ? 1 : 0, base);
     ALIGNQ_LAUNCH_CHECK();
-    wq_bwd_apply_kernel<<<(unsigned)nchunks, kThreads, 0, s>>>(flat, g_wq, seg_off, chunk_seg, seg_chunk0, stats, ws, g_w, gt,
-                                                               g_ptrs ? 1 : 0, base, accumulate);
+    (void)launch_pdl(wq_bwd_apply_kernel, dim3((unsigned)nchunks), dim3(kThreads), 0, s, flat, g_wq, seg_off, chunk_seg, seg_chunk0,
+                     stats, (const double*)ws, g_w, gt, g_ptrs ? 1 : 0, base, accumulate);
     ALIGNQ_LAUNCH_CHECK();
   }
   return ALIGNQ_OK;

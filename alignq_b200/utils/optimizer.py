@@ -135,9 +135,27 @@ class SGD(Optimizer):
                 t.lr, t.momentum, t.dampening, t.weight_decay, t.nesterov, t.first_step = e[5:]
             # pinned staging + async copy: legal inside CUDA-graph capture (becomes a memcpy node that
             # re-reads this pinned buffer on replay, so the buffer is kept alive and never rewritten)
-            host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).pin_memory()
-            self._pinned.append(host)
             capturing = dev.type == "cuda" and torch.cuda.is_current_stream_capturing()
+            raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+            if capturing:
+                host = raw.pin_memory()
+                self._pinned.append(host)                  # re-read by the graph's memcpy node: lives as long as the graph
+            else:
+                # eager: a ring of four pinned buffers, each reused once the copy that read it has completed -- the table
+                # changes whenever a gradient lands at a new address, which in eager mode can be every step, and one fresh
+                # pinned allocation per step (never freed) was a leak and a cudaHostAlloc on the critical path
+                ring = self.__dict__.setdefault("_pinned_ring", [])
+                k = self.__dict__.get("_pinned_next", 0) % 4
+                if len(ring) <= k:
+                    ring.append([None, None])
+                slot = ring[k]
+                if slot[1] is not None:
+                    slot[1].synchronize()
+                if slot[0] is None or slot[0].numel() != raw.numel():
+                    slot[0] = torch.empty(raw.numel(), dtype=torch.uint8).pin_memory()
+                slot[0].copy_(raw)
+                host = slot[0]
+                self._pinned_next = k + 1
             if capturing and self.defer_uploads_in_capture and self._table_dev is not None \
                     and self._table_dev.numel() == host.numel() and not self._table_in_graph_pool:
                 # Captured iteration after eager warm-up: the pointers this table holds are fixed for the life of the
@@ -154,6 +172,10 @@ class SGD(Optimizer):
                     self._table_in_graph_pool = capturing
                     self._table_bound_to_graph = False
                 self._table_dev.copy_(host, non_blocking=True)     # under capture: a memcpy node re-reading `host`
+                if not capturing:
+                    ev = torch.cuda.Event()
+                    ev.record(torch.cuda.current_stream(dev))
+                    self._pinned_ring[(self._pinned_next - 1) % 4][1] = ev
             if self._chunk_dev is None or self._chunk_key != tuple(e[0].numel() for e in ents):
                 _, chunk_t, t_chunk0, nchunks = L.plan_chunks([e[0].numel() for e in ents])
                 self._chunk_key = tuple(e[0].numel() for e in ents)

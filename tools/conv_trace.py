@@ -2,8 +2,7 @@
 (csrc/conv_tc.cu + abi.cu built with -DALIGNQ_CONV_TRACE: thread 0 of every CTA stamps %globaltimer at the phase
 boundaries) and prints, per phase, the mean / max over the CTAs and the spread of the CTAs' start times.
 
-  nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -DALIGNQ_CONV_TRACE -shared \
-       -o tools/libalignq_conv_trace.so alignq_b200/csrc/conv_tc.cu alignq_b200/csrc/abi.cu -lcudart
+  make -C alignq_b200/csrc trace        # -> tools/libalignq_conv_trace.so (git-ignored; travels to the GPU box)
 """
 import ctypes as C
 import os
@@ -70,6 +69,6 @@ def run(fn, shape, flush):
 if __name__ == "__main__":
     shapes = [(128, 16, 32, 32), (128, 32, 16, 16), (128, 64, 8, 8)]
     for shape in shapes:
-        for fn in ("alignq_conv3x3_bwd_weight",):
+        for fn in (sys.argv[1:] or ["alignq_conv3x3_fwd", "alignq_conv3x3_bwd_data", "alignq_conv3x3_bwd_weight"]):
             run(fn, shape, True)
     run("alignq_conv3x3_fwd", shapes[0], False)

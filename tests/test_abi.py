@@ -62,3 +62,28 @@ def test_ws_bytes_is_monotone_and_capped():
     c = lib.alignq_gram_ws_bytes(128, 1 << 24)
     assert 0 < a <= b <= c <= (256 << 20)
     assert lib.alignq_gram_ws_bytes(0, 10) == 0
+
+
+def test_header_is_plain_c_and_argument_counts_match_the_binding(tmp_path):
+    """include/alignq_b200.h is the drop-in boundary: it must compile as C99 (no C++ / torch types) and every prototype
+    must take exactly as many arguments as the ctypes signature table passes."""
+    import re
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "t.c"
+    src.write_text('#include "alignq_b200.h"\nint main(void) { return alignq_abi_version() == 0; }\n')
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(REPO, "include"), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    text = open(os.path.join(REPO, "include", "alignq_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = dict((m.group(1), m.group(2)) for m in re.finditer(r"\b(alignq_\w+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S))
+    assert len(protos) >= 40
+    for name, (_, argtypes) in L.SIGNATURES.items():
+        assert name in protos, name
+        params = protos[name].strip()
+        n = 0 if params in ("", "void") else len([p for p in params.split(",") if p.strip()])
+        assert n == len(argtypes), f"{name}: header has {n} parameters, the binding passes {len(argtypes)}"

@@ -162,6 +162,8 @@ bnq_stats_kernel(const float* __restrict__ x, int64_t R, int C, float* __restric
   extern __shared__ float sh[];
   __shared__ unsigned flag;
 
+  pdl_trigger();                                            // the apply kernel launches early and waits for this grid
+  pdl_wait();                                               // (and this one beside the tail of the convolution before it)
   const int C4 = C >> 2, k = blockDim.x / C4;
   const int c4 = threadIdx.x % C4, rsub = threadIdx.x / C4;
   float s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
@@ -619,9 +621,9 @@ extern "C" int alignq_bn_act_fwd(const float* x, int64_t rows, int C, const floa
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const BnLaunch L = bn_launch(rows, C);
   if (training) {
-    bnq_stats_kernel<<<L.grid, L.threads, L.smem, s>>>(x, rows, C, running_mean, running_var, momentum, bn_eps,
+    { cudaError_t pe_ = launch_pdl(bnq_stats_kernel, dim3(L.grid), dim3(L.threads), L.smem, s, x, rows, C, running_mean, running_var, momentum, bn_eps,
                                                        save_mean, save_invstd, ws, counter,
-                                                       reinterpret_cast<long long*>(num_batches_tracked), nullptr, PeerCtx{});
+                                                       reinterpret_cast<long long*>(num_batches_tracked), nullptr, PeerCtx{}); if (pe_ != cudaSuccess) return (int)pe_; }
   } else {
     bnq_eval_stats_kernel<<<(C + 255) / 256, 256, 0, s>>>(running_mean, running_var, bn_eps, C, save_mean, save_invstd);
   }
@@ -719,8 +721,8 @@ extern "C" int alignq_bn_act_sync_stats(const float* x, int64_t rows, int C, dou
   if (rows < 1 || C < 4 || (C & 3) || C > 4 * BN_MAX_THREADS || !x || !sums || !ws || !counter) return ALIGNQ_EINVAL;
   if (!aligned16(x)) return ALIGNQ_EALIGN;
   const BnLaunch L = bn_launch(rows, C);
-  bnq_stats_kernel<<<L.grid, L.threads, L.smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-      x, rows, C, nullptr, nullptr, 0.f, 0.f, nullptr, nullptr, ws, counter, nullptr, sums, PeerCtx{});
+  { cudaError_t pe_ = launch_pdl(bnq_stats_kernel, dim3(L.grid), dim3(L.threads), L.smem, reinterpret_cast<cudaStream_t>(stream),
+      x, rows, C, nullptr, nullptr, 0.f, 0.f, nullptr, nullptr, ws, counter, nullptr, sums, PeerCtx{}); if (pe_ != cudaSuccess) return (int)pe_; }
   ALIGNQ_LAUNCH_CHECK();
   return ALIGNQ_OK;
 }
@@ -806,9 +808,9 @@ extern "C" int alignq_bn_act_fwd_peer(const float* x, int64_t rows, int64_t rows
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const PeerCtx pc{const_cast<void* const*>(peer_bufs), peer_seq, rank, world, (double)rows_global};
   const BnLaunch L = bn_launch(rows, C);
-  bnq_stats_kernel<<<L.grid, L.threads, L.smem, s>>>(x, rows, C, running_mean, running_var, momentum, bn_eps, save_mean,
+  { cudaError_t pe_ = launch_pdl(bnq_stats_kernel, dim3(L.grid), dim3(L.threads), L.smem, s, x, rows, C, running_mean, running_var, momentum, bn_eps, save_mean,
                                                      save_invstd, ws, counter,
-                                                     reinterpret_cast<long long*>(num_batches_tracked), nullptr, pc);
+                                                     reinterpret_cast<long long*>(num_batches_tracked), nullptr, pc); if (pe_ != cudaSuccess) return (int)pe_; }
   ALIGNQ_LAUNCH_CHECK();
   { cudaError_t pe_ = launch_pdl(bnq_apply_kernel, dim3(L.grid * 2), dim3(L.threads), 0, s, x, rows, C, gamma, beta, save_mean, save_invstd,
                                                     make_bnq(a_bit, act_range, variant, relu), residual, y); if (pe_ != cudaSuccess) return (int)pe_; }

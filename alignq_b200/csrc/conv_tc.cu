@@ -15,11 +15,18 @@
 //   * an MN-major UMMA operand (MN = channels, K = positions: 8 K-rows x 16 B core matrices, LBO = 128 B so K is LINEAR
 //     in the position, SBO = PS), used by the weight-gradient GEMM  dW_tap[cout, cin] = sum_pos gy[pos, cout] x[pos + shift, cin];
 // and because the position enters linearly, tap (kh, kw) is just the descriptor start address moved by (kh Wp + kw) * 16
-// bytes: nine shifted views of ONE staged tile, no data duplication.  Pad positions (xx >= W or yy >= H) produce junk
-// output rows that are never stored (forward) or carry zero gy (weight gradient).
+// bytes: shifted views of ONE staged tile, no data duplication (the forward uses the three kh shifts this way and folds the
+// kw taps into the MMA's N, see FwdCfg; the weight gradient stages an im2col of the x operand instead, see below).
+// Pad positions (xx >= W or yy >= H) produce junk output rows that are never stored (forward) or carry zero gy (weight
+// gradient).
+//
+// Around the GEMM: the kernels are launched as programmatic dependents of the kernel before them (common.cuh: pdl_wait);
+// the forward epilogue can reduce the batch statistics of the BatchNorm that follows (STATS), the data-gradient epilogue
+// the backward sums of the bn-act layer that precedes (BNRED, bn_stat.cuh) -- one launch fewer per layer either way.
 //
 // Numerics (mode): ALIGNQ_CONV_TF32 = one kind::tf32 MMA per k-step on operands rounded to tf32 (what cuDNN runs by
-// default under torch.backends.cudnn.allow_tf32 = True, the reference's own GPU path; ~5e-4 relative); ALIGNQ_CONV_TF32X3 =
+// default under torch.backends.cudnn.allow_tf32 = True, the reference's own GPU path; ~3e-4 of max|ref|; the weight
+// gradient: one kind::f16 MMA on fp16 operands -- the same 11 significand bits -- with gy scaled per CTA); ALIGNQ_CONV_TF32X3 =
 // operands split v = H + L (H = top 19 bits), three MMAs (H H into the main accumulator, H L + L H into a second one:
 // the tensor core truncates when it adds into the fp32 accumulator), fp32-level parity with F.conv2d (tested to 1e-5).
 #include <cuda_fp16.h>

@@ -5,6 +5,13 @@ files (stem, strided, 1x1 projection, depthwise, NCHW inputs) keeps calling the 
 
 ``args.own_conv``: "off" (library convolution everywhere), "tf32" (one tensor-core pass on tf32 operands: the numerics of
 cuDNN under torch's default ``allow_tf32 = True``) or "tf32x3" (three passes on H + L split operands: fp32 parity, 1e-5).
+``own_conv_channels`` routes forward + both gradients, ``own_dgrad_channels`` / ``own_wgrad_channels`` one gradient alone.
+
+Besides the convolution itself this module carries the step-level plumbing around it: weight gradients on side streams
+(``WgradStream``), the BatchNorm statistics of the following layer from the forward epilogue (``conv_with_bn_stats``), and
+-- ``args.fuse_dgrad_bn`` -- the backward reduce pass of the PRECEDING fused bn-act layer from the data-gradient epilogue:
+``_ConvQFn.backward`` finds that layer's saved tensors in the ``link`` its output carries (model/fused.py), adds a parked
+shortcut gradient, and leaves the affine gradients and the two means for ``alignq_bn_act_bwd_apply``.
 """
 from __future__ import annotations
 

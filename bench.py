@@ -75,6 +75,8 @@ def cpu_reference_run(steps, warmup, budget_s=150.0, batch=BATCH, workload="resn
     torch.manual_seed(0)
     if workload == "resnet56_admm":                        # configs[1]: QB + ADMM (oracle pinned by make_model_golden.py)
         model = MO.OracleResNet([9, 9, 9], 8, 8, "B", 2.0, dim=batch).train()
+    elif workload == "densenet40":                         # configs[3] (oracle pinned by make_model_golden.py --job densenet40_A)
+        model = MO.OracleDenseNet(8, 8, 2.0).train()
     else:
         model = MO.resnet20_oracle(8, 8, "A", act_range=2.0, dim=batch).train()
     tr = MO.OracleTrainer(model, lr=0.04, momentum=0.9, weight_decay=1e-4, lam=1.0, lam2=4.0, bitW=8)
@@ -130,9 +132,14 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb = cpu_reference_run(args.steps, args.warmup)
+    wl = args.workload if args.workload in ("resnet20", "resnet56_admm", "densenet40") else "resnet20"
+    cb = cpu_reference_run(args.steps, args.warmup, workload=wl)
     # same config keys as the product arm's line (the CPU arm has one process whatever N is: it does not scale)
     cfg = dict(CONFIG, global_batch=BATCH, parallelism="cpu", cpu_steps_timed=cb["steps_timed"])
+    if wl == "resnet56_admm":
+        cfg.update(workload="resnet56_quant W8A8 (QB) + ADMM, CIFAR-10 synthetic, QAT step", variant="B")
+    elif wl == "densenet40":
+        cfg.update(workload="densenet_40_quant W8A8 (QA) CIFAR-10 synthetic, QAT step")
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "img/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
@@ -601,7 +608,7 @@ def run_product(args):
             del xg, Gg, wsg
         except Exception as e:                              # pragma: no cover
             gram = {"error": str(e)[:200]}
-        if world == 1 and not args.no_cpu_baseline and args.workload in ("resnet20", "resnet56_admm"):
+        if world == 1 and not args.no_cpu_baseline and args.workload in ("resnet20", "resnet56_admm", "densenet40"):
             cb = cpu_reference_run(20, 3, budget_s=40.0, workload=args.workload)
             cpu = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
             if args.workload == "resnet20":

@@ -184,6 +184,41 @@ def worker(job: str) -> None:
             out["logits_after_2_steps"] = (r[0] if isinstance(r, tuple) else r).numpy()
         print(f"  {job}: oracle model + 2 training iterations bit-identical to the reference")
 
+    if job == "densenet40_A":
+        orc = MO.OracleDenseNet(8, 8, 2.0)
+        orc.load_state_dict(sd)
+        orc.train()
+        lo, _, fpo = run(orc)
+        assert torch.equal(lo, logits), "oracle DenseNet logits != reference"
+        assert np.array_equal(fpo, fp), "oracle DenseNet grads != reference"
+        # two reference training iterations (dense-cifar-10/main.py:285-325) vs OracleTrainer
+        import utils.optimizer as ropt
+        ropt.args.bitW = 8
+        ref.load_state_dict(sd)
+        orc.load_state_dict(sd)
+        named = list(ref.named_parameters())
+        opt = ropt.SGD([p for _, p in named], lr=0.04, momentum=0.9, weight_decay=1e-4)
+        trainer = MO.OracleTrainer(orc, lr=0.04, momentum=0.9, weight_decay=1e-4, lam=1.0, lam2=4.0, bitW=8)
+        for it in range(2):
+            opt.zero_grad()
+            torch.nn.functional.cross_entropy(ref(x), tgt).backward()
+            idx = [j for j, (n, _) in enumerate(named) if "conv" in n and "weight" in n]        # main.py:297-300: all of them
+            convs = [ref.conv1]
+            for j, layer in enumerate([ref.dense1, ref.trans1, ref.dense2, ref.trans2, ref.dense3]):
+                convs += [blk.conv1 for blk in layer] if j % 2 == 0 else [layer.conv1]
+            w_cdf, w_pdf = [], []          # QA does not store the attributes: recompute them
+            for conv in convs:
+                c, p_ = q.cdf(torch.mean(conv.weight), torch.std(conv.weight), "w")(conv.weight)
+                w_cdf.append(c.detach())
+                w_pdf.append(p_.detach())
+            opt.step(idx, w_cdf, w_pdf, 1.0, 4.0)
+            trainer.step(x, tgt)
+            for (n, p), (_, po) in zip(ref.named_parameters(), orc.named_parameters()):
+                assert torch.equal(p.detach(), po.detach()), f"iteration {it}: parameter {n} diverged"
+        with torch.no_grad():
+            out["logits_after_2_steps"] = ref(x).numpy()
+        print(f"  {job}: oracle DenseNet + 2 training iterations bit-identical to the reference")
+
     os.makedirs(os.path.join(REPO, "tests", "golden"), exist_ok=True)
     np.savez_compressed(os.path.join(REPO, "tests", "golden", f"model_{job}.npz"), **out)
     with open(os.path.join(REPO, "tests", "golden", f"model_keys_{job}.json"), "w") as f:

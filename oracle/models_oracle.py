@@ -141,6 +141,67 @@ def resnet56_oracle(wbit, abit, variant="A", **kw):
     return OracleResNet([9, 9, 9], wbit, abit, variant, **kw)
 
 
+# ---- DenseNet-40 (variant A): cdf_alignment/dense-cifar-10/model/densenet.py:17-159 -------------------------------------
+class OracleDenseBlock(nn.Module):                               # DenseBasicBlock, densenet.py:17-42
+    def __init__(self, wbit, abit, inplanes, growth, ar):
+        super().__init__()
+        self.act_q0 = OracleAct(abit, "A", ar)
+        self.bn1 = nn.BatchNorm2d(inplanes)
+        self.conv1 = OracleConv(inplanes, growth, 3, 1, 1, wbit, "A")
+
+    def forward(self, x):
+        out = self.conv1(F.relu(self.act_q0(self.bn1(x))))
+        return torch.cat((x, out), 1)
+
+
+class OracleTransition(nn.Module):                               # Transition, densenet.py:45-63
+    def __init__(self, wbit, abit, inplanes, outplanes, ar):
+        super().__init__()
+        self.act_q0 = OracleAct(abit, "A", ar)
+        self.bn1 = nn.BatchNorm2d(inplanes)
+        self.conv1 = OracleConv(inplanes, outplanes, 1, 1, 0, wbit, "A")
+
+    def forward(self, x):
+        return F.avg_pool2d(self.conv1(F.relu(self.act_q0(self.bn1(x)))), 2)
+
+
+class OracleDenseNet(nn.Module):                                 # DenseNet(depth=40, compressionRate=1), densenet.py:66-159
+    admm = False
+
+    def __init__(self, wbit, abit, act_range=2.0, depth=40, growth=12, num_classes=10):
+        super().__init__()
+        n = (depth - 4) // 3
+        planes = 2 * growth
+        self.conv1 = OracleConv(3, planes, 3, 1, 1, wbit, "A")
+        stages = []
+        for st in range(3):
+            blocks = []
+            for _ in range(n):
+                blocks.append(OracleDenseBlock(wbit, abit, planes, growth, act_range))
+                planes += growth
+            stages.append(nn.Sequential(*blocks))
+            if st < 2:
+                stages.append(OracleTransition(wbit, abit, planes, planes, act_range))      # compressionRate = 1
+        self.dense1, self.trans1, self.dense2, self.trans2, self.dense3 = stages
+        self.bn = nn.BatchNorm2d(planes)
+        self.fc = nn.Linear(planes, num_classes)
+        self.act_q0 = OracleAct(abit, "A", act_range)
+
+    def forward(self, x):
+        x = self.dense3(self.trans2(self.dense2(self.trans1(self.dense1(self.conv1(x))))))
+        x = F.relu(self.act_q0(self.bn(x)))
+        return self.fc(F.avg_pool2d(x, 8).view(x.size(0), -1))
+
+    def quant_convs(self):
+        """The convolutions in the order dense-cifar-10/main.py:303-316 collects weight_cdf / weight_pdf."""
+        convs = [self.conv1]
+        for j, layer in enumerate((self.dense1, self.trans1, self.dense2, self.trans2, self.dense3)):
+            convs += [blk.conv1 for blk in layer] if j % 2 == 0 else [layer.conv1]
+        return convs
+
+    skip_first_conv = False                                      # main.py:297-300: every conv weight takes the surrogate
+
+
 def deterministic_fill(state_dict, seed=0):
     """Return a copy of the state_dict filled with seeded values that depend only on key order and shape, so the
     reference, the oracle and the product can be given identical weights without shipping them."""
@@ -173,15 +234,19 @@ class OracleTrainer:
     """One iteration of the reference's train() body on synthetic tensors (main.py:269-313 for QA,
     cdf_alignment_admm/.../main.py:286-379 for QB), with the optimizers restated functionally."""
 
-    def __init__(self, model: OracleResNet, lr=0.04, momentum=0.9, weight_decay=1e-4, lam=1.0, lam2=4.0, bitW=8):
+    def __init__(self, model, lr=0.04, momentum=0.9, weight_decay=1e-4, lam=1.0, lam2=4.0, bitW=8):
         self.model = model
         self.named = [(n, p) for n, p in model.named_parameters() if "alterD" not in n and "gamma" not in n]
         self.bufs = [None] * len(self.named)
         self.hp = dict(lr=lr, momentum=momentum, weight_decay=weight_decay)
         self.lam, self.lam2, self.bitW = lam, lam2, bitW
         idx = [j for j, (n, _) in enumerate(self.named) if "conv" in n and "weight" in n]
-        self.idx = idx[1:]                                       # main.py:299-304
-        self.convs = [c for layer in model.layers for c in (layer.conv0, layer.conv1, layer.skip_conv) if c is not None]
+        if hasattr(model, "quant_convs"):                        # DenseNet: its own collection order, every conv
+            self.idx = idx[1:] if model.skip_first_conv else idx
+            self.convs = model.quant_convs()
+        else:
+            self.idx = idx[1:]                                   # main.py:299-304
+            self.convs = [c for layer in model.layers for c in (layer.conv0, layer.conv1, layer.skip_conv) if c is not None]
         self.admms = []
         if model.admm:
             self.admms.append(model.admm0)

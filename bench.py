@@ -77,9 +77,12 @@ def cpu_reference_run(steps, warmup, budget_s=150.0, batch=BATCH, workload="resn
         model = MO.OracleResNet([9, 9, 9], 8, 8, "B", 2.0, dim=batch).train()
     elif workload == "densenet40":                         # configs[3] (oracle pinned by make_model_golden.py --job densenet40_A)
         model = MO.OracleDenseNet(8, 8, 2.0).train()
+    elif workload == "mobilenetv2":                        # configs[2]: W4A4, batch 256 (pinned by --job mobilenetv2_A)
+        model = MO.OracleMobileNetV2(4, 4, 2.0).train()
     else:
         model = MO.resnet20_oracle(8, 8, "A", act_range=2.0, dim=batch).train()
-    tr = MO.OracleTrainer(model, lr=0.04, momentum=0.9, weight_decay=1e-4, lam=1.0, lam2=4.0, bitW=8)
+    bits = 4 if workload == "mobilenetv2" else 8
+    tr = MO.OracleTrainer(model, lr=0.04, momentum=0.9, weight_decay=1e-4, lam=1.0, lam2=4.0, bitW=bits)
     x = torch.randn(batch, 3, 32, 32)
     t = torch.randint(0, 10, (batch,))
     t0 = time.perf_counter()
@@ -132,11 +135,14 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    wl = args.workload if args.workload in ("resnet20", "resnet56_admm", "densenet40") else "resnet20"
-    cb = cpu_reference_run(args.steps, args.warmup, workload=wl)
+    wl = args.workload if args.workload in ("resnet20", "resnet56_admm", "densenet40", "mobilenetv2") else "resnet20"
+    ref_batch = 256 if wl == "mobilenetv2" else BATCH
+    cb = cpu_reference_run(args.steps, args.warmup, batch=ref_batch, workload=wl)
     # same config keys as the product arm's line (the CPU arm has one process whatever N is: it does not scale)
-    cfg = dict(CONFIG, global_batch=BATCH, parallelism="cpu", cpu_steps_timed=cb["steps_timed"])
-    if wl == "resnet56_admm":
+    cfg = dict(CONFIG, global_batch=ref_batch, parallelism="cpu", cpu_steps_timed=cb["steps_timed"])
+    if wl == "mobilenetv2":
+        cfg.update(workload="mobile_v2 W4A4 (QA) SVHN synthetic 32x32, QAT step", bitW=4, abitW=4, per_gpu_batch=ref_batch)
+    elif wl == "resnet56_admm":
         cfg.update(workload="resnet56_quant W8A8 (QB) + ADMM, CIFAR-10 synthetic, QAT step", variant="B")
     elif wl == "densenet40":
         cfg.update(workload="densenet_40_quant W8A8 (QA) CIFAR-10 synthetic, QAT step")
@@ -608,8 +614,8 @@ def run_product(args):
             del xg, Gg, wsg
         except Exception as e:                              # pragma: no cover
             gram = {"error": str(e)[:200]}
-        if world == 1 and not args.no_cpu_baseline and args.workload in ("resnet20", "resnet56_admm", "densenet40"):
-            cb = cpu_reference_run(20, 3, budget_s=40.0, workload=args.workload)
+        if world == 1 and not args.no_cpu_baseline and args.workload in ("resnet20", "resnet56_admm", "densenet40", "mobilenetv2"):
+            cb = cpu_reference_run(20, 3, budget_s=40.0, batch=batch, workload=args.workload)
             cpu = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
             if args.workload == "resnet20":
                 try:

@@ -219,6 +219,43 @@ def worker(job: str) -> None:
             out["logits_after_2_steps"] = ref(x).numpy()
         print(f"  {job}: oracle DenseNet + 2 training iterations bit-identical to the reference")
 
+    if job == "mobilenetv2_A":
+        orc = MO.OracleMobileNetV2(4, 4, 2.0)
+        orc.load_state_dict(sd)
+        orc.train()
+        lo, _, fpo = run(orc)
+        assert torch.equal(lo, logits), "oracle MobileNet-v2 logits != reference"
+        assert np.array_equal(fpo, fp), "oracle MobileNet-v2 grads != reference"
+        # two reference training iterations (mobilenet-v2-svhn/main.py:160-204) vs OracleTrainer
+        import utils.optimizer as ropt
+        ropt.args.bitW = 4
+        ref.load_state_dict(sd)
+        orc.load_state_dict(sd)
+        named = list(ref.named_parameters())
+        opt = ropt.SGD([p for _, p in named], lr=0.04, momentum=0.9, weight_decay=1e-4)
+        trainer = MO.OracleTrainer(orc, lr=0.04, momentum=0.9, weight_decay=1e-4, lam=1.0, lam2=4.0, bitW=4)
+        for it in range(2):
+            opt.zero_grad()
+            torch.nn.functional.cross_entropy(ref(x), tgt).backward()
+            idx = [j for j, (n, _) in enumerate(named)
+                   if ("conv" in n and "weight" in n) or ("shortcut.0" in n and "weight" in n)]          # main.py:175-179
+            convs = [ref.conv1]
+            for layer in ref.layers:
+                convs += [layer.conv1, layer.conv2, layer.conv3] + ([layer.shortcut[0]] if layer.shortcut is not None else [])
+            convs.append(ref.conv2)
+            w_cdf, w_pdf = [], []          # QA does not store the attributes: recompute them
+            for conv in convs:
+                c, p_ = q.cdf(torch.mean(conv.weight), torch.std(conv.weight), "w")(conv.weight)
+                w_cdf.append(c.detach())
+                w_pdf.append(p_.detach())
+            opt.step(idx, w_cdf, w_pdf, 1.0, 4.0)
+            trainer.step(x, tgt)
+            for (n, p), (_, po) in zip(ref.named_parameters(), orc.named_parameters()):
+                assert torch.equal(p.detach(), po.detach()), f"iteration {it}: parameter {n} diverged"
+        with torch.no_grad():
+            out["logits_after_2_steps"] = ref(x).numpy()
+        print(f"  {job}: oracle MobileNet-v2 + 2 training iterations bit-identical to the reference")
+
     os.makedirs(os.path.join(REPO, "tests", "golden"), exist_ok=True)
     np.savez_compressed(os.path.join(REPO, "tests", "golden", f"model_{job}.npz"), **out)
     with open(os.path.join(REPO, "tests", "golden", f"model_keys_{job}.json"), "w") as f:

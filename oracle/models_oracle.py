@@ -30,14 +30,14 @@ class OracleADMM(nn.Module):                                     # utils/admm.py
 
 
 class OracleConv(nn.Conv2d):                                     # quantization.py:107-122
-    def __init__(self, cin, cout, k, stride, padding, w_bit, variant):
-        super().__init__(cin, cout, k, stride, padding, bias=False)
+    def __init__(self, cin, cout, k, stride, padding, w_bit, variant, groups=1):
+        super().__init__(cin, cout, k, stride, padding, groups=groups, bias=False)
         self.w_bit, self.variant = w_bit, variant
         self.weight_cdf = self.weight_pdf = None
 
     def forward(self, x):
         wq, self.weight_cdf, self.weight_pdf = O.weight_quantize(self.weight, self.w_bit, self.variant)
-        return F.conv2d(x, wq, None, self.stride, self.padding)
+        return F.conv2d(x, wq, None, self.stride, self.padding, self.dilation, self.groups)
 
 
 class OracleAct(nn.Module):
@@ -202,6 +202,73 @@ class OracleDenseNet(nn.Module):                                 # DenseNet(dept
     skip_first_conv = False                                      # main.py:297-300: every conv weight takes the surrogate
 
 
+# ---- MobileNet-v2 (variant A): cdf_alignment/mobilenet-v2-svhn/model/mobilenetV2.py:23-130 ---------------------------
+class OracleMBBlock(nn.Module):                                  # Block, mobilenetV2.py:23-71
+    def __init__(self, wbit, abit, cin, cout, expansion, stride, ar):
+        super().__init__()
+        self.stride = stride
+        planes = expansion * cin
+        self.act_q1, self.act_q2, self.act_q3 = (OracleAct(abit, "A", ar) for _ in range(3))
+        self.act_skip = OracleAct(abit, "A", ar)
+        self.conv1 = OracleConv(cin, planes, 1, 1, 0, wbit, "A")
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.conv2 = OracleConv(planes, planes, 3, stride, 1, wbit, "A", groups=planes)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.conv3 = OracleConv(planes, cout, 1, 1, 0, wbit, "A")
+        self.bn3 = nn.BatchNorm2d(cout)
+        self.shortcut = None
+        if stride == 1:
+            self.shortcut = nn.Sequential(OracleConv(cin, cout, 1, 1, 0, wbit, "A"), nn.BatchNorm2d(cout), self.act_skip, nn.ReLU())
+
+    def forward(self, x):
+        out = F.relu6(self.act_q1(self.bn1(self.conv1(x))))
+        out = F.relu6(self.act_q2(self.bn2(self.conv2(out))))
+        out = self.act_q3(self.bn3(self.conv3(out)))
+        if self.stride == 1:
+            out += self.shortcut(x)
+        return out
+
+
+class OracleMobileNetV2(nn.Module):                              # MobileNetV2, mobilenetV2.py:74-130
+    admm = False
+    cfg = [(1, 16, 1, 1), (6, 24, 2, 1), (6, 32, 3, 2), (6, 64, 4, 2), (6, 96, 3, 1), (6, 160, 3, 2), (6, 320, 1, 1)]
+
+    def __init__(self, wbit, abit, act_range=2.0, num_classes=10):
+        super().__init__()
+        self.act_q1, self.act_q2 = OracleAct(abit, "A", act_range), OracleAct(abit, "A", act_range)
+        self.conv1 = OracleConv(3, 32, 3, 1, 1, wbit, "A")
+        self.bn1 = nn.BatchNorm2d(32)
+        layers, cin = [], 32
+        for expansion, cout, nblocks, stride in self.cfg:
+            for st in [stride] + [1] * (nblocks - 1):
+                layers.append(OracleMBBlock(wbit, abit, cin, cout, expansion, st, act_range))
+                cin = cout
+        self.layers = nn.Sequential(*layers)
+        self.conv2 = OracleConv(320, 1280, 1, 1, 0, wbit, "A")
+        self.bn2 = nn.BatchNorm2d(1280)
+        self.linear = nn.Linear(1280, num_classes)
+
+    def forward(self, x):
+        out = F.relu(self.act_q1(self.bn1(self.conv1(x))))
+        out = self.layers(out)
+        out = F.relu(self.act_q2(self.bn2(self.conv2(out))))
+        out = F.avg_pool2d(out, 4)
+        return self.linear(out.view(out.size(0), -1))
+
+    def quant_convs(self):
+        """The convolutions in the order mobilenet-v2-svhn/main.py:182-199 collects weight_cdf / weight_pdf."""
+        convs = [self.conv1]
+        for layer in self.layers:
+            convs += [layer.conv1, layer.conv2, layer.conv3] + ([layer.shortcut[0]] if layer.shortcut is not None else [])
+        return convs + [self.conv2]
+
+    skip_first_conv = False                                      # main.py:176-180 (`idx = idx[1:]` is commented out there)
+
+    @staticmethod
+    def quant_weight_name(n):                                    # main.py:177
+        return ("conv" in n and "weight" in n) or ("shortcut.0" in n and "weight" in n)
+
+
 def deterministic_fill(state_dict, seed=0):
     """Return a copy of the state_dict filled with seeded values that depend only on key order and shape, so the
     reference, the oracle and the product can be given identical weights without shipping them."""
@@ -240,7 +307,8 @@ class OracleTrainer:
         self.bufs = [None] * len(self.named)
         self.hp = dict(lr=lr, momentum=momentum, weight_decay=weight_decay)
         self.lam, self.lam2, self.bitW = lam, lam2, bitW
-        idx = [j for j, (n, _) in enumerate(self.named) if "conv" in n and "weight" in n]
+        is_q = getattr(model, "quant_weight_name", lambda n: "conv" in n and "weight" in n)
+        idx = [j for j, (n, _) in enumerate(self.named) if is_q(n)]
         if hasattr(model, "quant_convs"):                        # DenseNet: its own collection order, every conv
             self.idx = idx[1:] if model.skip_first_conv else idx
             self.convs = model.quant_convs()

@@ -74,6 +74,22 @@ def test_oracle_densenet_reproduces_reference_logits_and_two_training_iterations
         assert torch.equal(m(x), torch.from_numpy(g["logits_after_2_steps"]))
 
 
+def test_oracle_mobilenetv2_reproduces_reference_logits_and_two_training_iterations():
+    """oracle/models_oracle.OracleMobileNetV2 (W4A4; the CPU baseline of the mobilenetv2 workload) against the goldens of
+    oracle/make_model_golden.py --job mobilenetv2_A (imported reference, mobilenet-v2-svhn), bit for bit."""
+    g = np.load(os.path.join(GOLDEN, "model_mobilenetv2_A.npz"))
+    x, tgt = torch.from_numpy(g["x"]), torch.from_numpy(g["target"])
+    m = MO.OracleMobileNetV2(4, 4, 2.0)
+    m.load_state_dict(MO.deterministic_fill(m.state_dict(), seed=11))
+    m.train()
+    assert torch.equal(m(x).detach(), torch.from_numpy(g["logits"]))
+    tr = MO.OracleTrainer(m, bitW=4)
+    for _ in range(2):
+        tr.step(x, tgt)
+    with torch.no_grad():
+        assert torch.equal(m(x), torch.from_numpy(g["logits_after_2_steps"]))
+
+
 def test_collectors_follow_reference_indexing():
     from alignq_b200.utils.train import collect_sgd_args, quantized_convs
     aq.set_args(variant="A", bitW=8, abitW=8)
